@@ -1,0 +1,234 @@
+/* mallie_b200.h -- C ABI of the B200-native Mallie render hot path.
+ *
+ * Drop-in boundary.  Mallie has no FFI layer of its own; the
+ * seam it uses to swap its ray-tracing backend is the ENABLE_EMBREE #ifdef in
+ * Scene (scene.h:70-76, scene.cc:172-221 build, :254-311 trace, :318-320 bbox).
+ * This header is what a `#ifdef ENABLE_B200` branch at the same three places
+ * binds to (see INTEGRATION.md for the exact patch), plus the frame-level entry
+ * that replaces the OpenMP scanline loop of mallie::Render (render.cc:657-698).
+ *
+ * Conventions
+ *  - plain C, pointers + sizes, no C++/torch types; every function returns
+ *    MB200_OK (0) or a negative mb200_status and never aborts; the message for
+ *    the calling thread's last failure is mb200_last_error().
+ *  - "rays", "hits", "image" ... buffers may be HOST or DEVICE pointers (the
+ *    library asks cudaPointerGetAttributes); host buffers are staged through
+ *    pinned memory inside the call.  Calls block until host-visible results are
+ *    readable.  When every buffer of a call is a DEVICE pointer and no host-side
+ *    output (counters / stats) is requested, mb200_render_* and the *_async
+ *    variants only enqueue on the scene's stream: order later work on
+ *    mb200_scene_stream() or call mb200_scene_synchronize().
+ *  - inputs are borrowed for the duration of the call only.
+ *  - one scene lives on one GPU; use one scene per GPU for multi-GPU (tiles).
+ *  - All arithmetic that decides a result is IEEE double in the reference's
+ *    operation order without FMA contraction: hit records are bit-identical
+ *    to BVHAccel::Traverse (bvh_accel.cc:773-844).
+ */
+#ifndef MALLIE_B200_H_
+#define MALLIE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  MB200_OK = 0,
+  MB200_ERR_INVALID_ARG = -1,  /* null pointer, bad size, malformed BVH        */
+  MB200_ERR_CUDA = -2,         /* a CUDA runtime call failed                    */
+  MB200_ERR_NO_DEVICE = -3,    /* no usable sm_100 GPU / bad device ordinal     */
+  MB200_ERR_OUT_OF_MEMORY = -4,
+  MB200_ERR_IO = -5,           /* file could not be read / written              */
+  MB200_ERR_UNSUPPORTED = -6
+} mb200_status;
+
+/* -------------------------------------------------------------------------
+ * POD records.  Layouts are the leading fields of the reference structs so a
+ * Mallie caller can pass its own arrays without conversion.
+ * ---------------------------------------------------------------------- */
+
+/* struct Ray (common.h:78-83): org, dir.  invDir/dirSign are recomputed by
+ * Traverse itself (bvh_accel.cc:787-797) and are not part of the ABI.  48 B. */
+typedef struct { double org[3]; double dir[3]; } mb200_ray;
+
+/* Head of struct Intersection (intersection.h:6-11).  32 B.
+ * Miss: t = DBL_MAX, u = v = 0, faceID = 0xFFFFFFFF, materialID = 0xFFFFFFFF. */
+typedef struct { double t, u, v; uint32_t faceID, materialID; } mb200_hit;
+
+/* Full struct Intersection (intersection.h:6-24), 184 B, as filled by
+ * BuildIntersection (bvh_accel.cc:699-769).  tangent/binormal are never written
+ * by the BVH path (left zero here).  On a miss only t,u,v,faceID are defined. */
+typedef struct {
+  double t, u, v;
+  uint32_t faceID, materialID;
+  uint32_t f0, f1, f2, pad_;
+  double position[3];
+  double geometricNormal[3];
+  double normal[3];
+  double tangent[3];
+  double binormal[3];
+  double texcoord[2];
+} mb200_isect;
+
+/* class BVHNode (bvh_accel.h:10-29), 64 B: what BVHAccel::GetNodes() returns
+ * and BVHAccel::Dump writes. */
+typedef struct {
+  double bmin[3];
+  double bmax[3];
+  int32_t flag;     /* 1 = leaf, 0 = branch */
+  int32_t axis;     /* branch: split axis; leaf: ignored */
+  uint32_t data[2]; /* branch: child0, child1; leaf: ntris, first index */
+} mb200_bvh_node;
+
+/* struct BVHBuildOptions (bvh_accel.h:32-42). */
+typedef struct {
+  double cost_taabb;       /* 0.2 */
+  int min_leaf_primitives; /* 16  */
+  int max_tree_depth;      /* 256 */
+  int bin_size;            /* 64  */
+} mb200_build_options;
+
+/* struct BVHBuildStatistics (bvh_accel.h:45-52). */
+typedef struct { int max_tree_depth, num_leaf_nodes, num_branch_nodes; } mb200_build_stats;
+
+/* Per-call traversal counters (optional outputs). */
+typedef struct {
+  uint64_t nodes_tested; /* box tests == nodes popped by the reference loop (bvh_accel.cc:805-811) */
+  uint64_t tris_tested;  /* triangles run through TriangleIsect (bvh_accel.cc:656-694)            */
+  uint64_t rays;         /* rays traced                                                            */
+  uint64_t max_stack;    /* deepest traversal stack seen                                           */
+} mb200_counters;
+
+typedef struct mb200_bvh mb200_bvh;     /* host-side BVH (reference layout)           */
+typedef struct mb200_scene mb200_scene; /* device-resident scene: BVH + mesh, one GPU */
+
+/* -------------------------------------------------------------------------
+ * Library
+ * ---------------------------------------------------------------------- */
+const char *mb200_last_error(void);
+const char *mb200_version(void);
+/* Number of visible CUDA devices (0 when there is none; never fails). */
+int mb200_device_count(void);
+/* Kernel launches this library has issued in this process (monitoring; bench.py's gpu_launches). */
+int mb200_launches_issued(void);
+
+/* -------------------------------------------------------------------------
+ * Host BVH: replaces BVHAccel::Build / Dump / Load (bvh_accel.cc:445-544).
+ * The tree is bit-identical to the reference builder's (same node order,
+ * same index permutation) so faceID tie-breaks agree.
+ * ---------------------------------------------------------------------- */
+void mb200_build_options_default(mb200_build_options *opt);
+int mb200_bvh_build(mb200_bvh **out, const double *vertices, size_t nverts, const uint32_t *faces, size_t nfaces,
+                    const mb200_build_options *opt /* NULL = defaults */);
+int mb200_bvh_load(mb200_bvh **out, const char *path);       /* BVHAccel::Load  */
+int mb200_bvh_dump(const mb200_bvh *bvh, const char *path);  /* BVHAccel::Dump  */
+size_t mb200_bvh_num_nodes(const mb200_bvh *bvh);
+size_t mb200_bvh_num_indices(const mb200_bvh *bvh);
+const mb200_bvh_node *mb200_bvh_nodes(const mb200_bvh *bvh); /* BVHAccel::GetNodes   */
+const uint32_t *mb200_bvh_indices(const mb200_bvh *bvh);     /* BVHAccel::GetIndices */
+int mb200_bvh_stats(const mb200_bvh *bvh, mb200_build_stats *out); /* BVHAccel::GetStatistics */
+void mb200_bvh_destroy(mb200_bvh *bvh);
+
+/* -------------------------------------------------------------------------
+ * Device scene: replaces the accel_ member of Scene (scene.h:75) and what
+ * Scene::Init does after loading the mesh (scene.cc:224-230).
+ * vertices [3*nverts] f64, faces [3*nfaces] u32 as in struct Mesh (mesh.h:7-18);
+ * material_ids [nfaces], fv_normals [9*nfaces], fv_uvs [6*nfaces] may be NULL.
+ * nodes/indices: the reference-layout BVH (from mb200_bvh_* or from Mallie's own
+ * BVHAccel::GetNodes()/GetIndices()).  The library validates the tree, re-lays it
+ * out for the GPU and uploads it; nothing is retained from the caller's arrays.
+ * ---------------------------------------------------------------------- */
+int mb200_scene_create(mb200_scene **out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
+                       size_t nfaces, const uint32_t *material_ids, const double *fv_normals, const double *fv_uvs,
+                       const mb200_bvh_node *nodes, size_t nnodes, const uint32_t *indices, size_t nindices);
+void mb200_scene_destroy(mb200_scene *scene);
+/* Scene::BoundingBox (scene.cc:317-333): root node bounds. */
+int mb200_scene_bounds(const mb200_scene *scene, double bmin[3], double bmax[3]);
+/* Bytes resident in HBM for this scene, and the CUDA stream (cudaStream_t) work is enqueued on. */
+size_t mb200_scene_device_bytes(const mb200_scene *scene);
+void *mb200_scene_stream(const mb200_scene *scene);
+int mb200_scene_device(const mb200_scene *scene);
+/* 1 when every vertex coordinate is exactly float-representable and the compact
+ * fp32 triangle records are in use (still widened to double before any arithmetic). */
+int mb200_scene_uses_f32_vertices(const mb200_scene *scene);
+
+/* -------------------------------------------------------------------------
+ * Queries: replace bool Scene::Trace(Intersection&, Ray&) (scene.cc:253-315) ->
+ * BVHAccel::Traverse (bvh_accel.cc:773-844), batched.
+ * ---------------------------------------------------------------------- */
+/* Closest hit; hits[i] is the 32-byte record head.  counters may be NULL. */
+int mb200_trace_closest(mb200_scene *scene, const mb200_ray *rays, size_t n, mb200_hit *hits,
+                        mb200_counters *counters);
+/* Closest hit + BuildIntersection: full 184-byte records. hit_mask (n bytes) may be NULL. */
+int mb200_trace_closest_full(mb200_scene *scene, const mb200_ray *rays, size_t n, mb200_isect *isects,
+                             uint8_t *hit_mask);
+/* Occlusion (any hit): occluded[i] = 1 iff closest-hit Traverse would return t < tmax[i]
+ * (the shadow-ray query the reference leaves as an empty block, render.cc:425-426). */
+int mb200_trace_occluded(mb200_scene *scene, const mb200_ray *rays, const double *tmax, size_t n, uint8_t *occluded,
+                         mb200_counters *counters);
+/* Enqueue-only variants for DEVICE buffers (no host synchronisation); pair with
+ * mb200_scene_synchronize or CUDA events on mb200_scene_stream(). */
+int mb200_trace_closest_async(mb200_scene *scene, const mb200_ray *d_rays, size_t n, mb200_hit *d_hits);
+int mb200_scene_synchronize(mb200_scene *scene);
+
+/* -------------------------------------------------------------------------
+ * Camera: Camera::BuildCameraFrame (camera.cc:40-220) on the host,
+ * Camera::GenerateRay (camera.cc:222-240) on the device.
+ * ---------------------------------------------------------------------- */
+typedef struct { double origin[3], corner[3], du[3], dv[3]; } mb200_camera_frame;
+int mb200_camera_frame_build(mb200_camera_frame *out, const double eye[3], const double lookat[3], const double up[3],
+                             double fov, const double quat[4], int width, int height);
+/* rays[i] = GenerateRay(px[i], py[i]); px/py/rays host or device. */
+int mb200_generate_rays(mb200_scene *scene, const mb200_camera_frame *frame, const double *px, const double *py,
+                        size_t n, mb200_ray *rays);
+/* Un-jittered primary rays GenerateRay((double)x,(double)y) for the tile [x0,x1)x[y0,y1), row-major. */
+int mb200_generate_rays_grid(mb200_scene *scene, const mb200_camera_frame *frame, int x0, int y0, int x1, int y1,
+                             mb200_ray *rays);
+
+/* -------------------------------------------------------------------------
+ * Frame: replaces the body of mallie::Render (render.cc:593-708) for one pass.
+ * ---------------------------------------------------------------------- */
+typedef enum {
+  MB200_SHADER_PATHTRACE = 0,      /* PathTrace, render.cc:381-456 */
+  MB200_SHADER_PRIMARY_SHADOW = 1, /* primary closest hit + one shadow ray to `light` */
+  MB200_SHADER_PRIMARY_ONLY = 2    /* primary closest hit; radiance = |normal| visualisation-free: hit ? 1 : 0 */
+} mb200_shader;
+
+typedef struct {
+  int width, height;          /* full image size (RenderConfig::width/height)                        */
+  int x0, y0, x1, y1;         /* tile rendered by this call (whole image: 0,0,width,height)           */
+  mb200_camera_frame frame;
+  int use_plane;              /* RenderConfig::plane                                                  */
+  float plane[4];             /* Plane::set(a,b,c,d), render.cc:620-627 (mb200_plane_from_bounds)     */
+  int max_path_length;        /* kMaxPathLength, render.cc:52 (16)                                    */
+  uint32_t pass;              /* sample index: seeds the per-pixel RNG stream                         */
+  int jitter;                 /* 1 = PathTrace's [-0.5,0.5) jitter (render.cc:388-391); 0 = pixel coords as is */
+  int shader;                 /* mb200_shader                                                         */
+  double light[3];            /* MB200_SHADER_PRIMARY_SHADOW                                          */
+} mb200_render_params;
+
+typedef struct {
+  uint64_t primary_rays;  /* closest-hit queries for camera rays               */
+  uint64_t bounce_rays;   /* closest-hit queries for path continuation         */
+  uint64_t shadow_rays;   /* occlusion queries                                 */
+  uint64_t zombie_segments; /* post-escape segments resolved in closed form, NOT counted as rays */
+} mb200_render_stats;
+
+void mb200_render_params_default(mb200_render_params *p, int width, int height);
+void mb200_plane_from_bounds(const double bmin[3], const double bmax[3], float abcd[4]);
+/* image: float[3*width*height] RGB row-major, FULL-image indexing (only the tile's pixels are written,
+ * overwritten not accumulated, as render.cc:673-675); count: int[width*height], ++ per tile pixel
+ * (render.cc:677-679).  Host or device pointers.  stats may be NULL. */
+int mb200_render_pass(mb200_scene *scene, const mb200_render_params *params, float *image, int *count,
+                      mb200_render_stats *stats);
+/* N passes accumulated on the device: accum[p] += pass image, count[p] += N; what the SDL render thread does
+ * with AccumImage (main_sdl.cc:572-606).  accum: float[3*W*H], count: int[W*H], host or device. */
+int mb200_render_accumulate(mb200_scene *scene, const mb200_render_params *params, int num_passes, float *accum,
+                            int *count, mb200_render_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MALLIE_B200_H_ */

@@ -1,0 +1,370 @@
+"""ctypes binding of the mallie_b200 C ABI (include/mallie_b200.h).
+
+This is the Python face of the product: tests and bench.py drive the CUDA path
+through exactly the entry points a Mallie `#ifdef ENABLE_B200` build would call
+(INTEGRATION.md).  There is NO fallback: if libmallie_b200.so is missing or no
+B200 is visible the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmallie_b200.so")
+
+RAY_DTYPE = np.dtype([("org", "<f8", 3), ("dir", "<f8", 3)])
+HIT_DTYPE = np.dtype([("t", "<f8"), ("u", "<f8"), ("v", "<f8"), ("faceID", "<u4"), ("materialID", "<u4")])
+ISECT_DTYPE = np.dtype([("t", "<f8"), ("u", "<f8"), ("v", "<f8"), ("faceID", "<u4"), ("materialID", "<u4"),
+                        ("f0", "<u4"), ("f1", "<u4"), ("f2", "<u4"), ("_pad", "<u4"),
+                        ("position", "<f8", 3), ("geometricNormal", "<f8", 3), ("normal", "<f8", 3),
+                        ("tangent", "<f8", 3), ("binormal", "<f8", 3), ("texcoord", "<f8", 2)])
+NODE_DTYPE = np.dtype([("bmin", "<f8", 3), ("bmax", "<f8", 3), ("flag", "<i4"), ("axis", "<i4"),
+                       ("data", "<u4", 2)])
+assert RAY_DTYPE.itemsize == 48 and HIT_DTYPE.itemsize == 32
+assert ISECT_DTYPE.itemsize == 184 and NODE_DTYPE.itemsize == 64
+
+SHADER_PATHTRACE, SHADER_PRIMARY_SHADOW, SHADER_PRIMARY_ONLY = 0, 1, 2
+
+# Every symbol include/mallie_b200.h declares (tests/test_abi.py checks the header against this list).
+EXPORTS = [
+    "mb200_last_error", "mb200_version", "mb200_device_count", "mb200_launches_issued",
+    "mb200_build_options_default", "mb200_bvh_build", "mb200_bvh_load", "mb200_bvh_dump",
+    "mb200_bvh_num_nodes", "mb200_bvh_num_indices", "mb200_bvh_nodes", "mb200_bvh_indices",
+    "mb200_bvh_stats", "mb200_bvh_destroy",
+    "mb200_scene_create", "mb200_scene_destroy", "mb200_scene_bounds", "mb200_scene_device_bytes",
+    "mb200_scene_stream", "mb200_scene_device", "mb200_scene_uses_f32_vertices", "mb200_scene_synchronize",
+    "mb200_trace_closest", "mb200_trace_closest_full", "mb200_trace_occluded", "mb200_trace_closest_async",
+    "mb200_camera_frame_build", "mb200_generate_rays", "mb200_generate_rays_grid",
+    "mb200_render_params_default", "mb200_plane_from_bounds", "mb200_render_pass", "mb200_render_accumulate",
+]
+
+
+class BuildOptions(C.Structure):
+    _fields_ = [("cost_taabb", C.c_double), ("min_leaf_primitives", C.c_int), ("max_tree_depth", C.c_int),
+                ("bin_size", C.c_int)]
+
+
+class BuildStats(C.Structure):
+    _fields_ = [("max_tree_depth", C.c_int), ("num_leaf_nodes", C.c_int), ("num_branch_nodes", C.c_int)]
+
+
+class Counters(C.Structure):
+    _fields_ = [("nodes_tested", C.c_uint64), ("tris_tested", C.c_uint64), ("rays", C.c_uint64),
+                ("max_stack", C.c_uint64)]
+
+
+class CameraFrame(C.Structure):
+    _fields_ = [("origin", C.c_double * 3), ("corner", C.c_double * 3), ("du", C.c_double * 3),
+                ("dv", C.c_double * 3)]
+
+    def arrays(self):
+        return tuple(np.array(list(getattr(self, k))) for k in ("origin", "corner", "du", "dv"))
+
+
+class RenderParams(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("x0", C.c_int), ("y0", C.c_int), ("x1", C.c_int),
+                ("y1", C.c_int), ("frame", CameraFrame), ("use_plane", C.c_int), ("plane", C.c_float * 4),
+                ("max_path_length", C.c_int), ("pass_", C.c_uint32), ("jitter", C.c_int), ("shader", C.c_int),
+                ("light", C.c_double * 3)]
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("primary_rays", C.c_uint64), ("bounce_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
+                ("zombie_segments", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class MallieB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Loads libmallie_b200.so.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MallieB200Error(
+                f"{LIB_PATH} is missing: build it with `make -C mallie_b200/csrc` "
+                "(or python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        vp, sz, i32, dbl = C.c_void_p, C.c_size_t, C.c_int, C.c_double
+        L.mb200_last_error.restype = C.c_char_p
+        L.mb200_version.restype = C.c_char_p
+        L.mb200_device_count.restype = i32
+        L.mb200_launches_issued.restype = i32
+        L.mb200_build_options_default.argtypes = [C.POINTER(BuildOptions)]
+        L.mb200_bvh_build.argtypes = [C.POINTER(vp), vp, sz, vp, sz, C.POINTER(BuildOptions)]
+        L.mb200_bvh_load.argtypes = [C.POINTER(vp), C.c_char_p]
+        L.mb200_bvh_dump.argtypes = [vp, C.c_char_p]
+        L.mb200_bvh_num_nodes.restype = sz
+        L.mb200_bvh_num_nodes.argtypes = [vp]
+        L.mb200_bvh_num_indices.restype = sz
+        L.mb200_bvh_num_indices.argtypes = [vp]
+        L.mb200_bvh_nodes.restype = vp
+        L.mb200_bvh_nodes.argtypes = [vp]
+        L.mb200_bvh_indices.restype = vp
+        L.mb200_bvh_indices.argtypes = [vp]
+        L.mb200_bvh_stats.argtypes = [vp, C.POINTER(BuildStats)]
+        L.mb200_bvh_destroy.argtypes = [vp]
+        L.mb200_scene_create.argtypes = [C.POINTER(vp), i32, vp, sz, vp, sz, vp, vp, vp, vp, sz, vp, sz]
+        L.mb200_scene_destroy.argtypes = [vp]
+        L.mb200_scene_bounds.argtypes = [vp, vp, vp]
+        L.mb200_scene_device_bytes.restype = sz
+        L.mb200_scene_device_bytes.argtypes = [vp]
+        L.mb200_scene_stream.restype = vp
+        L.mb200_scene_stream.argtypes = [vp]
+        L.mb200_scene_device.argtypes = [vp]
+        L.mb200_scene_uses_f32_vertices.argtypes = [vp]
+        L.mb200_scene_synchronize.argtypes = [vp]
+        L.mb200_trace_closest.argtypes = [vp, vp, sz, vp, C.POINTER(Counters)]
+        L.mb200_trace_closest_full.argtypes = [vp, vp, sz, vp, vp]
+        L.mb200_trace_occluded.argtypes = [vp, vp, vp, sz, vp, C.POINTER(Counters)]
+        L.mb200_trace_closest_async.argtypes = [vp, vp, sz, vp]
+        L.mb200_camera_frame_build.argtypes = [C.POINTER(CameraFrame), vp, vp, vp, dbl, vp, i32, i32]
+        L.mb200_generate_rays.argtypes = [vp, C.POINTER(CameraFrame), vp, vp, sz, vp]
+        L.mb200_generate_rays_grid.argtypes = [vp, C.POINTER(CameraFrame), i32, i32, i32, i32, vp]
+        L.mb200_render_params_default.argtypes = [C.POINTER(RenderParams), i32, i32]
+        L.mb200_plane_from_bounds.argtypes = [vp, vp, vp]
+        L.mb200_render_pass.argtypes = [vp, C.POINTER(RenderParams), vp, vp, C.POINTER(RenderStats)]
+        L.mb200_render_accumulate.argtypes = [vp, C.POINTER(RenderParams), i32, vp, vp, C.POINTER(RenderStats)]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise MallieB200Error(f"mallie_b200 error {rc}: {lib().mb200_last_error().decode()}")
+
+
+def _p(a):
+    """numpy array -> void*; int -> device pointer passthrough; None -> NULL."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def device_count():
+    return int(lib().mb200_device_count())
+
+
+def launches_issued():
+    return int(lib().mb200_launches_issued())
+
+
+# ----------------------------------------------------------------------------------------------
+class HostBVH:
+    """mb200_bvh: the host-built, reference-layout tree (BVHAccel::Build / Dump / Load)."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @classmethod
+    def build(cls, vertices, faces, cost_taabb=0.2, min_leaf=16, max_depth=256, bin_size=64):
+        v = np.ascontiguousarray(vertices, np.float64).reshape(-1, 3)
+        f = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
+        opt = BuildOptions(cost_taabb, min_leaf, max_depth, bin_size)
+        h = C.c_void_p()
+        check(lib().mb200_bvh_build(C.byref(h), _p(v), v.shape[0], _p(f), f.shape[0], C.byref(opt)))
+        return cls(h)
+
+    @classmethod
+    def load(cls, path):
+        h = C.c_void_p()
+        check(lib().mb200_bvh_load(C.byref(h), path.encode()))
+        return cls(h)
+
+    def dump(self, path):
+        check(lib().mb200_bvh_dump(self.h, path.encode()))
+
+    def arrays(self):
+        L = lib()
+        nn, ni = L.mb200_bvh_num_nodes(self.h), L.mb200_bvh_num_indices(self.h)
+        nodes = np.zeros(nn, NODE_DTYPE)
+        idx = np.zeros(ni, np.uint32)
+        if nn:
+            C.memmove(_p(nodes), L.mb200_bvh_nodes(self.h), nn * 64)
+        if ni:
+            C.memmove(_p(idx), L.mb200_bvh_indices(self.h), ni * 4)
+        return nodes, idx
+
+    def stats(self):
+        s = BuildStats()
+        check(lib().mb200_bvh_stats(self.h, C.byref(s)))
+        return dict(maxTreeDepth=s.max_tree_depth, numLeafNodes=s.num_leaf_nodes, numBranchNodes=s.num_branch_nodes)
+
+    def close(self):
+        if self.h:
+            lib().mb200_bvh_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def camera_frame(eye, lookat, up=(0, 1, 0), fov=45.0, quat=(0, 0, 0, 0), width=512, height=512):
+    f = CameraFrame()
+    e, l, u = (np.ascontiguousarray(x, np.float64) for x in (eye, lookat, up))
+    q = np.ascontiguousarray(quat, np.float64)
+    check(lib().mb200_camera_frame_build(C.byref(f), _p(e), _p(l), _p(u), float(fov), _p(q), width, height))
+    return f
+
+
+def plane_from_bounds(bmin, bmax):
+    out = np.zeros(4, np.float32)
+    lib().mb200_plane_from_bounds(_p(np.ascontiguousarray(bmin, np.float64)),
+                                  _p(np.ascontiguousarray(bmax, np.float64)), _p(out))
+    return out
+
+
+class Scene:
+    """mb200_scene: the device-resident scene (what Scene::Init builds, scene.cc:224-230)."""
+
+    def __init__(self, vertices, faces, material_ids=None, normals=None, uvs=None, nodes=None, indices=None,
+                 device=0):
+        self.h = None
+        self.vertices = np.ascontiguousarray(vertices, np.float64).reshape(-1, 3)
+        self.faces = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
+        m = None if material_ids is None else np.ascontiguousarray(material_ids, np.uint32)
+        n = None if normals is None else np.ascontiguousarray(normals, np.float64).reshape(-1)
+        t = None if uvs is None else np.ascontiguousarray(uvs, np.float64).reshape(-1)
+        if nodes is None:
+            bvh = HostBVH.build(self.vertices, self.faces)
+            nodes, indices = bvh.arrays()
+            bvh.close()
+        self.nodes = np.ascontiguousarray(nodes)
+        self.indices = np.ascontiguousarray(indices, np.uint32)
+        assert self.nodes.dtype.itemsize == 64
+        h = C.c_void_p()
+        check(lib().mb200_scene_create(C.byref(h), device, _p(self.vertices), self.vertices.shape[0], _p(self.faces),
+                                       self.faces.shape[0], _p(m), _p(n), _p(t), _p(self.nodes),
+                                       self.nodes.shape[0], _p(self.indices), self.indices.shape[0]))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib().mb200_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- info
+    def bounds(self):
+        a, b = np.zeros(3), np.zeros(3)
+        check(lib().mb200_scene_bounds(self.h, _p(a), _p(b)))
+        return a, b
+
+    def device_bytes(self):
+        return int(lib().mb200_scene_device_bytes(self.h))
+
+    def stream(self):
+        return int(lib().mb200_scene_stream(self.h) or 0)
+
+    def uses_f32_vertices(self):
+        return bool(lib().mb200_scene_uses_f32_vertices(self.h))
+
+    def synchronize(self):
+        check(lib().mb200_scene_synchronize(self.h))
+
+    # -- queries (numpy in / numpy out, or raw device pointers as ints)
+    @staticmethod
+    def _rays(rays):
+        r = np.ascontiguousarray(rays, np.float64).reshape(-1, 6)
+        return r, r.shape[0]
+
+    def trace_closest(self, rays, counters=False):
+        r, n = self._rays(rays)
+        hits = np.zeros(n, HIT_DTYPE)
+        c = Counters()
+        check(lib().mb200_trace_closest(self.h, _p(r), n, _p(hits), C.byref(c) if counters else None))
+        if counters:
+            return hits, dict(nodes_tested=int(c.nodes_tested), tris_tested=int(c.tris_tested), rays=int(c.rays),
+                              max_stack=int(c.max_stack))
+        return hits
+
+    def trace_closest_full(self, rays):
+        r, n = self._rays(rays)
+        isects = np.zeros(n, ISECT_DTYPE)
+        mask = np.zeros(n, np.uint8)
+        check(lib().mb200_trace_closest_full(self.h, _p(r), n, _p(isects), _p(mask)))
+        return isects, mask.astype(bool)
+
+    def trace_occluded(self, rays, tmax, counters=False):
+        r, n = self._rays(rays)
+        t = np.ascontiguousarray(tmax, np.float64)
+        assert t.shape[0] == n
+        occ = np.zeros(n, np.uint8)
+        c = Counters()
+        check(lib().mb200_trace_occluded(self.h, _p(r), _p(t), n, _p(occ), C.byref(c) if counters else None))
+        if counters:
+            return occ.astype(bool), dict(nodes_tested=int(c.nodes_tested), tris_tested=int(c.tris_tested),
+                                          rays=int(c.rays), max_stack=int(c.max_stack))
+        return occ.astype(bool)
+
+    def trace_closest_device(self, d_rays, n, d_hits):
+        """Enqueue-only on the scene's stream; d_rays/d_hits are device addresses (ints)."""
+        check(lib().mb200_trace_closest_async(self.h, _p(int(d_rays)), n, _p(int(d_hits))))
+
+    def generate_rays(self, frame, px, py):
+        px = np.ascontiguousarray(px, np.float64).reshape(-1)
+        py = np.ascontiguousarray(py, np.float64).reshape(-1)
+        rays = np.zeros((px.size, 6))
+        check(lib().mb200_generate_rays(self.h, C.byref(frame), _p(px), _p(py), px.size, _p(rays)))
+        return rays
+
+    def generate_rays_grid(self, frame, x0, y0, x1, y1, out=None):
+        if out is None:
+            out = np.zeros(((y1 - y0) * (x1 - x0), 6))
+        check(lib().mb200_generate_rays_grid(self.h, C.byref(frame), x0, y0, x1, y1, _p(out)))
+        return out
+
+    # -- frame
+    def render_params(self, frame, width, height, tile=None, plane=None, max_path_length=16, pass_index=0,
+                      jitter=True, shader=SHADER_PATHTRACE, light=(0.0, 20.0, 0.0)):
+        p = RenderParams()
+        lib().mb200_render_params_default(C.byref(p), width, height)
+        p.frame = frame
+        if tile is not None:
+            p.x0, p.y0, p.x1, p.y1 = tile
+        if plane is not None:
+            p.use_plane = 1
+            for k in range(4):
+                p.plane[k] = float(plane[k])
+        p.max_path_length, p.pass_, p.jitter, p.shader = max_path_length, pass_index, int(jitter), shader
+        for k in range(3):
+            p.light[k] = float(light[k])
+        return p
+
+    def render_pass(self, params, image=None, count=None, stats=True):
+        """image/count: numpy arrays (host) or ints (device addresses)."""
+        if image is None:
+            image = np.zeros((params.height, params.width, 3), np.float32)
+        if count is None:
+            count = np.zeros((params.height, params.width), np.int32)
+        st = RenderStats()
+        check(lib().mb200_render_pass(self.h, C.byref(params), _p(image), _p(count), C.byref(st) if stats else None))
+        return image, count, (st.as_dict() if stats else None)
+
+    def render_accumulate(self, params, num_passes, image=None, count=None, stats=True):
+        if image is None:
+            image = np.zeros((params.height, params.width, 3), np.float32)
+        if count is None:
+            count = np.zeros((params.height, params.width), np.int32)
+        st = RenderStats()
+        check(lib().mb200_render_accumulate(self.h, C.byref(params), num_passes, _p(image), _p(count),
+                                            C.byref(st) if stats else None))
+        return image, count, (st.as_dict() if stats else None)

@@ -1,0 +1,405 @@
+// capi.cc -- the extern "C" boundary declared in include/mallie_b200.h.
+//
+// Thin glue only: argument checking, host<->device staging for callers that pass
+// host buffers, stream ordering, error strings.  No algorithm lives here and there
+// is NO CPU fallback: without a GPU every compute entry returns MB200_ERR_NO_DEVICE.
+#include <cuda_runtime_api.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "device/kernels.h"
+#include "device/scene.h"
+#include "host/bvh_build.h"
+#include "mallie_b200.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int set_err(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+int cuda_err(cudaError_t e, const char *what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return e == cudaErrorMemoryAllocation ? MB200_ERR_OUT_OF_MEMORY : MB200_ERR_CUDA;
+}
+
+#define CU(call)                                             \
+  do {                                                       \
+    cudaError_t e_ = (call);                                 \
+    if (e_ != cudaSuccess) return cuda_err(e_, #call);       \
+  } while (0)
+
+bool is_device_ptr(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int ensure(mb200_scene::Staging &st, size_t bytes) {
+  if (st.cap >= bytes) return MB200_OK;
+  if (st.pinned) cudaFreeHost(st.pinned);
+  if (st.dev) cudaFree(st.dev);
+  st.pinned = st.dev = nullptr;
+  st.cap = 0;
+  size_t cap = bytes + bytes / 4 + 4096;
+  CU(cudaMallocHost(&st.pinned, cap));
+  CU(cudaMalloc(&st.dev, cap));
+  st.cap = cap;
+  return MB200_OK;
+}
+
+// Brings `src` (host or device, `bytes`) to the device; returns the device pointer to use.
+int stage_in(mb200_scene *s, mb200_scene::Staging &st, const void *src, size_t bytes, const void **dptr) {
+  if (is_device_ptr(src)) {
+    *dptr = src;
+    return MB200_OK;
+  }
+  int rc = ensure(st, bytes);
+  if (rc != MB200_OK) return rc;
+  memcpy(st.pinned, src, bytes);
+  CU(cudaMemcpyAsync(st.dev, st.pinned, bytes, cudaMemcpyHostToDevice, s->stream));
+  *dptr = st.dev;
+  return MB200_OK;
+}
+
+// Chooses where a kernel should write an output of `bytes`: the caller's device buffer or staging.
+int stage_out_begin(mb200_scene::Staging &st, void *dst, size_t bytes, void **dptr, bool *staged) {
+  if (is_device_ptr(dst)) {
+    *dptr = dst;
+    *staged = false;
+    return MB200_OK;
+  }
+  int rc = ensure(st, bytes);
+  if (rc != MB200_OK) return rc;
+  *dptr = st.dev;
+  *staged = true;
+  return MB200_OK;
+}
+
+int stage_out_enqueue(mb200_scene *s, mb200_scene::Staging &st, size_t bytes) {
+  CU(cudaMemcpyAsync(st.pinned, st.dev, bytes, cudaMemcpyDeviceToHost, s->stream));
+  return MB200_OK;
+}
+
+int read_counters(mb200_scene *s, unsigned long long out[4]) {
+  CU(cudaMemcpyAsync(out, s->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return MB200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *mb200_last_error(void) { return g_err.c_str(); }
+const char *mb200_version(void) { return "mallie_b200 0.1 (sm_100a)"; }
+
+int mb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int mb200_launches_issued(void) { return mb200::launches_issued(); }
+
+// ---------------------------------------------------------------------------- host BVH
+void mb200_build_options_default(mb200_build_options *opt) {
+  if (!opt) return;
+  opt->cost_taabb = 0.2;
+  opt->min_leaf_primitives = 16;
+  opt->max_tree_depth = 256;
+  opt->bin_size = 64;
+}
+
+int mb200_bvh_build(mb200_bvh **out, const double *vertices, size_t nverts, const uint32_t *faces, size_t nfaces,
+                    const mb200_build_options *opt) {
+  if (!out) return set_err(MB200_ERR_INVALID_ARG, "out is null");
+  *out = nullptr;
+  if ((nfaces && (!vertices || !faces))) return set_err(MB200_ERR_INVALID_ARG, "null mesh array");
+  mb200_build_options o;
+  mb200_build_options_default(&o);
+  if (opt) o = *opt;
+  mb200_bvh *b = new mb200_bvh;
+  std::string err;
+  if (!mb200::build_bvh(b->bvh, vertices, nverts, faces, nfaces, o, &err)) {
+    delete b;
+    return set_err(MB200_ERR_INVALID_ARG, err);
+  }
+  *out = b;
+  return MB200_OK;
+}
+
+int mb200_bvh_load(mb200_bvh **out, const char *path) {
+  if (!out || !path) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  mb200_bvh *b = new mb200_bvh;
+  std::string err;
+  if (!mb200::load_bvh(b->bvh, path, &err)) {
+    delete b;
+    return set_err(MB200_ERR_IO, err);
+  }
+  *out = b;
+  return MB200_OK;
+}
+
+int mb200_bvh_dump(const mb200_bvh *bvh, const char *path) {
+  if (!bvh || !path) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  std::string err;
+  if (!mb200::dump_bvh(bvh->bvh, path, &err)) return set_err(MB200_ERR_IO, err);
+  return MB200_OK;
+}
+
+size_t mb200_bvh_num_nodes(const mb200_bvh *bvh) { return bvh ? bvh->bvh.nodes.size() : 0; }
+size_t mb200_bvh_num_indices(const mb200_bvh *bvh) { return bvh ? bvh->bvh.indices.size() : 0; }
+const mb200_bvh_node *mb200_bvh_nodes(const mb200_bvh *bvh) { return bvh ? bvh->bvh.nodes.data() : nullptr; }
+const uint32_t *mb200_bvh_indices(const mb200_bvh *bvh) { return bvh ? bvh->bvh.indices.data() : nullptr; }
+int mb200_bvh_stats(const mb200_bvh *bvh, mb200_build_stats *out) {
+  if (!bvh || !out) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  *out = bvh->bvh.stats;
+  return MB200_OK;
+}
+void mb200_bvh_destroy(mb200_bvh *bvh) { delete bvh; }
+
+// ---------------------------------------------------------------------------- scene
+int mb200_scene_create(mb200_scene **out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
+                       size_t nfaces, const uint32_t *material_ids, const double *fv_normals, const double *fv_uvs,
+                       const mb200_bvh_node *nodes, size_t nnodes, const uint32_t *indices, size_t nindices) {
+  if (!out) return set_err(MB200_ERR_INVALID_ARG, "out is null");
+  std::string err;
+  int rc = mb200::scene_create(out, device, vertices, nverts, faces, nfaces, material_ids, fv_normals, fv_uvs, nodes,
+                               nnodes, indices, nindices, &err);
+  if (rc != MB200_OK) return set_err(rc, err);
+  return MB200_OK;
+}
+
+void mb200_scene_destroy(mb200_scene *scene) { mb200::scene_destroy(scene); }
+
+int mb200_scene_bounds(const mb200_scene *scene, double bmin[3], double bmax[3]) {
+  if (!scene || !bmin || !bmax) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  if (scene->view.empty) return set_err(MB200_ERR_INVALID_ARG, "empty scene has no bounds");
+  for (int k = 0; k < 3; k++) bmin[k] = scene->root_bmin[k], bmax[k] = scene->root_bmax[k];
+  return MB200_OK;
+}
+
+size_t mb200_scene_device_bytes(const mb200_scene *scene) { return scene ? scene->device_bytes : 0; }
+void *mb200_scene_stream(const mb200_scene *scene) { return scene ? (void *)scene->stream : nullptr; }
+int mb200_scene_device(const mb200_scene *scene) { return scene ? scene->device : -1; }
+int mb200_scene_uses_f32_vertices(const mb200_scene *scene) { return scene ? scene->view.tri_f32 : 0; }
+
+int mb200_scene_synchronize(mb200_scene *scene) {
+  if (!scene) return set_err(MB200_ERR_INVALID_ARG, "scene is null");
+  CU(cudaSetDevice(scene->device));
+  CU(cudaStreamSynchronize(scene->stream));
+  return MB200_OK;
+}
+
+// ---------------------------------------------------------------------------- queries
+int mb200_trace_closest_async(mb200_scene *s, const mb200_ray *d_rays, size_t n, mb200_hit *d_hits) {
+  if (!s || (n && (!d_rays || !d_hits))) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  if (n == 0) return MB200_OK;
+  CU(cudaSetDevice(s->device));
+  CU(mb200::launch_trace_closest(s->view, s->stack_cap, d_rays, n, d_hits, s->d_work, nullptr, s->stream));
+  return MB200_OK;
+}
+
+int mb200_trace_closest(mb200_scene *s, const mb200_ray *rays, size_t n, mb200_hit *hits, mb200_counters *counters) {
+  if (!s || (n && (!rays || !hits))) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  if (counters) memset(counters, 0, sizeof(*counters));
+  if (n == 0) return MB200_OK;
+  CU(cudaSetDevice(s->device));
+  const void *d_rays;
+  void *d_hits;
+  bool staged;
+  int rc;
+  if ((rc = stage_in(s, s->in0, rays, n * sizeof(mb200_ray), &d_rays)) != MB200_OK) return rc;
+  if ((rc = stage_out_begin(s->out0, hits, n * sizeof(mb200_hit), &d_hits, &staged)) != MB200_OK) return rc;
+  if (counters) CU(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream));
+  CU(mb200::launch_trace_closest(s->view, s->stack_cap, (const mb200_ray *)d_rays, n, (mb200_hit *)d_hits, s->d_work,
+                                 counters ? s->d_counters : nullptr, s->stream));
+  if (staged && (rc = stage_out_enqueue(s, s->out0, n * sizeof(mb200_hit))) != MB200_OK) return rc;
+  if (counters) {
+    unsigned long long c[4];
+    if ((rc = read_counters(s, c)) != MB200_OK) return rc;
+    counters->nodes_tested = c[0], counters->tris_tested = c[1], counters->rays = c[2], counters->max_stack = c[3];
+  }
+  CU(cudaStreamSynchronize(s->stream));
+  if (staged) memcpy(hits, s->out0.pinned, n * sizeof(mb200_hit));
+  return MB200_OK;
+}
+
+int mb200_trace_closest_full(mb200_scene *s, const mb200_ray *rays, size_t n, mb200_isect *isects,
+                             uint8_t *hit_mask) {
+  if (!s || (n && (!rays || !isects))) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  if (n == 0) return MB200_OK;
+  CU(cudaSetDevice(s->device));
+  const void *d_rays;
+  void *d_is, *d_mask = nullptr;
+  bool st_is, st_mask = false;
+  int rc;
+  if ((rc = stage_in(s, s->in0, rays, n * sizeof(mb200_ray), &d_rays)) != MB200_OK) return rc;
+  if ((rc = stage_out_begin(s->out0, isects, n * sizeof(mb200_isect), &d_is, &st_is)) != MB200_OK) return rc;
+  if (hit_mask && (rc = stage_out_begin(s->out1, hit_mask, n, &d_mask, &st_mask)) != MB200_OK) return rc;
+  CU(mb200::launch_trace_closest_full(s->view, s->stack_cap, (const mb200_ray *)d_rays, n, (mb200_isect *)d_is,
+                                      (unsigned char *)d_mask, s->d_work, s->stream));
+  if (st_is && (rc = stage_out_enqueue(s, s->out0, n * sizeof(mb200_isect))) != MB200_OK) return rc;
+  if (st_mask && (rc = stage_out_enqueue(s, s->out1, n)) != MB200_OK) return rc;
+  CU(cudaStreamSynchronize(s->stream));
+  if (st_is) memcpy(isects, s->out0.pinned, n * sizeof(mb200_isect));
+  if (st_mask) memcpy(hit_mask, s->out1.pinned, n);
+  return MB200_OK;
+}
+
+int mb200_trace_occluded(mb200_scene *s, const mb200_ray *rays, const double *tmax, size_t n, uint8_t *occluded,
+                         mb200_counters *counters) {
+  if (!s || (n && (!rays || !tmax || !occluded))) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  if (counters) memset(counters, 0, sizeof(*counters));
+  if (n == 0) return MB200_OK;
+  CU(cudaSetDevice(s->device));
+  const void *d_rays, *d_tmax;
+  void *d_occ;
+  bool staged;
+  int rc;
+  if ((rc = stage_in(s, s->in0, rays, n * sizeof(mb200_ray), &d_rays)) != MB200_OK) return rc;
+  if ((rc = stage_in(s, s->in1, tmax, n * sizeof(double), &d_tmax)) != MB200_OK) return rc;
+  if ((rc = stage_out_begin(s->out0, occluded, n, &d_occ, &staged)) != MB200_OK) return rc;
+  if (counters) CU(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream));
+  CU(mb200::launch_trace_occluded(s->view, s->stack_cap, (const mb200_ray *)d_rays, (const double *)d_tmax, n,
+                                  (unsigned char *)d_occ, s->d_work, counters ? s->d_counters : nullptr, s->stream));
+  if (staged && (rc = stage_out_enqueue(s, s->out0, n)) != MB200_OK) return rc;
+  if (counters) {
+    unsigned long long c[4];
+    if ((rc = read_counters(s, c)) != MB200_OK) return rc;
+    counters->nodes_tested = c[0], counters->tris_tested = c[1], counters->rays = c[2], counters->max_stack = c[3];
+  }
+  CU(cudaStreamSynchronize(s->stream));
+  if (staged) memcpy(occluded, s->out0.pinned, n);
+  return MB200_OK;
+}
+
+// ---------------------------------------------------------------------------- camera
+int mb200_generate_rays(mb200_scene *s, const mb200_camera_frame *frame, const double *px, const double *py, size_t n,
+                        mb200_ray *rays) {
+  if (!s || !frame || (n && (!px || !py || !rays))) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  if (n == 0) return MB200_OK;
+  CU(cudaSetDevice(s->device));
+  const void *d_px, *d_py;
+  void *d_rays;
+  bool staged;
+  int rc;
+  if ((rc = stage_in(s, s->in0, px, n * sizeof(double), &d_px)) != MB200_OK) return rc;
+  if ((rc = stage_in(s, s->in1, py, n * sizeof(double), &d_py)) != MB200_OK) return rc;
+  if ((rc = stage_out_begin(s->out0, rays, n * sizeof(mb200_ray), &d_rays, &staged)) != MB200_OK) return rc;
+  CU(mb200::launch_generate_rays(*frame, (const double *)d_px, (const double *)d_py, n, (mb200_ray *)d_rays,
+                                 s->stream));
+  if (staged && (rc = stage_out_enqueue(s, s->out0, n * sizeof(mb200_ray))) != MB200_OK) return rc;
+  CU(cudaStreamSynchronize(s->stream));
+  if (staged) memcpy(rays, s->out0.pinned, n * sizeof(mb200_ray));
+  return MB200_OK;
+}
+
+int mb200_generate_rays_grid(mb200_scene *s, const mb200_camera_frame *frame, int x0, int y0, int x1, int y1,
+                             mb200_ray *rays) {
+  if (!s || !frame || !rays || x1 < x0 || y1 < y0) return set_err(MB200_ERR_INVALID_ARG, "bad argument");
+  const size_t n = (size_t)(x1 - x0) * (size_t)(y1 - y0);
+  if (n == 0) return MB200_OK;
+  CU(cudaSetDevice(s->device));
+  void *d_rays;
+  bool staged;
+  int rc;
+  if ((rc = stage_out_begin(s->out0, rays, n * sizeof(mb200_ray), &d_rays, &staged)) != MB200_OK) return rc;
+  CU(mb200::launch_generate_grid(*frame, x0, y0, x1 - x0, y1 - y0, (mb200_ray *)d_rays, s->stream));
+  if (staged && (rc = stage_out_enqueue(s, s->out0, n * sizeof(mb200_ray))) != MB200_OK) return rc;
+  CU(cudaStreamSynchronize(s->stream));
+  if (staged) memcpy(rays, s->out0.pinned, n * sizeof(mb200_ray));
+  return MB200_OK;
+}
+
+// ---------------------------------------------------------------------------- frame
+void mb200_render_params_default(mb200_render_params *p, int width, int height) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->width = width, p->height = height;
+  p->x0 = 0, p->y0 = 0, p->x1 = width, p->y1 = height;
+  p->max_path_length = 16;
+  p->jitter = 1;
+  p->shader = MB200_SHADER_PATHTRACE;
+  p->light[0] = 0.0, p->light[1] = 20.0, p->light[2] = 0.0;
+}
+
+// gPlaneObject.set(0, 1, 0, -(zmin - zsize * 0.0001f)) with float zmin/zsize (render.cc:620-627)
+void mb200_plane_from_bounds(const double bmin[3], const double bmax[3], float abcd[4]) {
+  const float zmin = (float)bmin[1];
+  const float zsize = (float)(bmax[1] - bmin[1]);
+  abcd[0] = 0, abcd[1] = 1, abcd[2] = 0;
+  abcd[3] = -(zmin - zsize * 0.0001f);
+}
+
+static int render_common(mb200_scene *s, const mb200_render_params *p, int num_passes, int accumulate, float *image,
+                         int *count, mb200_render_stats *stats) {
+  if (!s || !p || !image || !count) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  if (p->width <= 0 || p->height <= 0 || p->x0 < 0 || p->y0 < 0 || p->x1 > p->width || p->y1 > p->height ||
+      p->x0 > p->x1 || p->y0 > p->y1 || p->max_path_length < 1 || num_passes < 1)
+    return set_err(MB200_ERR_INVALID_ARG, "bad render parameters");
+  if (p->shader < 0 || p->shader > MB200_SHADER_PRIMARY_ONLY) return set_err(MB200_ERR_INVALID_ARG, "unknown shader");
+  if (stats) memset(stats, 0, sizeof(*stats));
+  CU(cudaSetDevice(s->device));
+  const size_t npix = (size_t)p->width * p->height;
+  const size_t img_bytes = npix * 3 * sizeof(float), cnt_bytes = npix * sizeof(int);
+  const bool dev_img = is_device_ptr(image), dev_cnt = is_device_ptr(count);
+  float *d_img = image;
+  int *d_cnt = count;
+  int rc;
+  if (!dev_img) {
+    if ((rc = ensure(s->out0, img_bytes)) != MB200_OK) return rc;
+    d_img = (float *)s->out0.dev;
+    // the tile's pixels are overwritten / added to; the rest of the caller's image must survive
+    memcpy(s->out0.pinned, image, img_bytes);
+    CU(cudaMemcpyAsync(d_img, s->out0.pinned, img_bytes, cudaMemcpyHostToDevice, s->stream));
+  }
+  if (!dev_cnt) {
+    if ((rc = ensure(s->out1, cnt_bytes)) != MB200_OK) return rc;
+    d_cnt = (int *)s->out1.dev;
+    memcpy(s->out1.pinned, count, cnt_bytes);
+    CU(cudaMemcpyAsync(d_cnt, s->out1.pinned, cnt_bytes, cudaMemcpyHostToDevice, s->stream));
+  }
+  CU(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream));
+  CU(mb200::launch_render(s->view, s->stack_cap, *p, num_passes, accumulate, d_img, d_cnt, s->d_work, s->d_counters,
+                          s->stream));
+  if (!dev_img) CU(cudaMemcpyAsync(s->out0.pinned, d_img, img_bytes, cudaMemcpyDeviceToHost, s->stream));
+  if (!dev_cnt) CU(cudaMemcpyAsync(s->out1.pinned, d_cnt, cnt_bytes, cudaMemcpyDeviceToHost, s->stream));
+  unsigned long long c[4] = {0, 0, 0, 0};
+  if (stats || !dev_img || !dev_cnt) {
+    if (stats) CU(cudaMemcpyAsync(c, s->d_counters, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+  }
+  if (!dev_img) memcpy(image, s->out0.pinned, img_bytes);
+  if (!dev_cnt) memcpy(count, s->out1.pinned, cnt_bytes);
+  if (stats) {
+    stats->primary_rays = c[0], stats->bounce_rays = c[1], stats->shadow_rays = c[2], stats->zombie_segments = c[3];
+  }
+  return MB200_OK;
+}
+
+int mb200_render_pass(mb200_scene *scene, const mb200_render_params *params, float *image, int *count,
+                      mb200_render_stats *stats) {
+  return render_common(scene, params, 1, 0, image, count, stats);
+}
+
+int mb200_render_accumulate(mb200_scene *scene, const mb200_render_params *params, int num_passes, float *accum,
+                            int *count, mb200_render_stats *stats) {
+  return render_common(scene, params, num_passes, 1, accum, count, stats);
+}
+
+} // extern "C"

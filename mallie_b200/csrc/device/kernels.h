@@ -1,0 +1,37 @@
+// kernels.h -- launchers of the sm_100a kernels (kernels.cu).  All pointers are DEVICE
+// pointers; every launcher enqueues on `s` and returns the launch status.
+#ifndef MALLIE_B200_KERNELS_H_
+#define MALLIE_B200_KERNELS_H_
+
+#include <cuda_runtime_api.h>
+
+#include "layout.h"
+#include "mallie_b200.h"
+
+namespace mb200 {
+
+// `work` is an 8-byte device scratch word (persistent-warp work counter, reset by the launcher);
+// `counters` (nullable) is unsigned long long[4]: nodes, tris, rays, max stack (accumulated).
+cudaError_t launch_trace_closest(const SceneView &sc, int stack_cap, const mb200_ray *rays, size_t n,
+                                 mb200_hit *hits, unsigned long long *work, unsigned long long *counters,
+                                 cudaStream_t s);
+cudaError_t launch_trace_closest_full(const SceneView &sc, int stack_cap, const mb200_ray *rays, size_t n,
+                                      mb200_isect *isects, unsigned char *mask, unsigned long long *work,
+                                      cudaStream_t s);
+cudaError_t launch_trace_occluded(const SceneView &sc, int stack_cap, const mb200_ray *rays, const double *tmax,
+                                  size_t n, unsigned char *occluded, unsigned long long *work,
+                                  unsigned long long *counters, cudaStream_t s);
+// stats: unsigned long long[4] primary, bounce, shadow, zombie (accumulated).
+cudaError_t launch_render(const SceneView &sc, int stack_cap, const mb200_render_params &p, int num_passes,
+                          int accumulate, float *image, int *count, unsigned long long *work,
+                          unsigned long long *stats, cudaStream_t s);
+cudaError_t launch_generate_rays(const mb200_camera_frame &f, const double *px, const double *py, size_t n,
+                                 mb200_ray *rays, cudaStream_t s);
+cudaError_t launch_generate_grid(const mb200_camera_frame &f, int x0, int y0, int w, int h, mb200_ray *rays,
+                                 cudaStream_t s);
+// Number of kernel launches issued by this library in this process (bench.py's gpu_launches).
+int launches_issued();
+
+} // namespace mb200
+
+#endif

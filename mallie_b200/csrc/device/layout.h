@@ -1,0 +1,85 @@
+// layout.h -- how a Mallie scene is laid out in HBM for the sm_100a kernels.
+//
+// The reference walks 64-byte BVHNode records that each carry their OWN box
+// (bvh_accel.h:10-29) and fetches triangles through two indirections
+// (indices_[i] -> faces[3f+k] -> vertices[3v+c], bvh_accel.cc:661-678).  On the
+// device the same tree is stored "children-in-parent":
+//
+//   PairNode (128 B, 128-B aligned, one per reference BRANCH node)
+//     box[c][0..2] = child c bmin, box[c][3..5] = child c bmax   (exact doubles)
+//     ref[c]       = child c: PairNode index (branch) or first TriRecord (leaf)
+//     cnt[c]       = kBranch for a branch child, else the leaf's triangle count
+//     axis         = the reference node's split axis (near/far order, bvh_accel.cc:818-823)
+//   -> one inner-node visit = ONE 128-byte line = eight 16-byte vector loads,
+//      and yields both child tests; half the dependent round trips of the
+//      reference layout for the same bytes per box (64 B/box incl. metadata).
+//
+//   TriRecord (leaf order = indices_ order, so "last visited wins" ties are kept)
+//     f32 variant, 48 B : p0.xyz, faceID | p1.xyz, materialID | p2.xyz, pad
+//         used when every vertex coordinate is exactly float-representable
+//         (always true for OBJ input with scene_scale 1: positions are parsed as
+//         float, tiny_obj_loader.cc:696-697); values are widened to double
+//         before any arithmetic, so results are unchanged.
+//     f64 variant, 80 B : p0,p1,p2 as doubles | faceID, materialID
+//   -> one triangle test = 3 (or 5) 16-byte vector loads, no indirection.
+//
+// The original faces/vertices/normals/uvs arrays are also resident (verbatim)
+// for BuildIntersection (bvh_accel.cc:699-769), which runs once per hit ray.
+#ifndef MALLIE_B200_DEVICE_LAYOUT_H_
+#define MALLIE_B200_DEVICE_LAYOUT_H_
+
+#include <stdint.h>
+
+namespace mb200 {
+
+static const uint32_t kBranch = 0xFFFFFFFFu;
+
+struct alignas(128) PairNode {
+  double box[2][6];
+  uint32_t ref[2];
+  uint32_t cnt[2];
+  uint32_t axis;
+  uint32_t pad_[3];
+};
+static_assert(sizeof(PairNode) == 128, "PairNode must be one 128-byte line");
+
+struct alignas(16) TriRecordF32 {
+  float p0[3];
+  uint32_t face;
+  float p1[3];
+  uint32_t mat;
+  float p2[3];
+  uint32_t pad_;
+};
+static_assert(sizeof(TriRecordF32) == 48, "TriRecordF32");
+
+struct alignas(16) TriRecordF64 {
+  double p[9];
+  uint32_t face;
+  uint32_t mat;
+};
+static_assert(sizeof(TriRecordF64) == 80, "TriRecordF64");
+
+// Everything a kernel needs, passed by value as a __grid_constant__ parameter.
+struct SceneView {
+  const PairNode *nodes;     // [num_pair_nodes]
+  const void *tris;          // TriRecordF32[] or TriRecordF64[]  (num_tris)
+  double root_box[6];        // reference node 0 bounds
+  uint32_t root_ref;         // as PairNode::ref
+  uint32_t root_cnt;         // as PairNode::cnt
+  uint32_t num_pair_nodes;
+  uint32_t num_tris;
+  int empty;                 // no nodes at all: every ray misses
+  int tri_f32;               // 1 = TriRecordF32
+  // verbatim mesh (mesh.h:7-18) for BuildIntersection
+  const double *vertices;    // [3*nv]
+  const uint32_t *faces;     // [3*nf]
+  const double *fv_normals;  // [9*nf] or null
+  const double *fv_uvs;      // [6*nf] or null
+  uint32_t num_vertices;
+  uint32_t num_faces;
+};
+
+} // namespace mb200
+
+#endif

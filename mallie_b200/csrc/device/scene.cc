@@ -1,0 +1,266 @@
+// scene.cc -- builds the device-resident scene from Mallie's host data:
+// validates the reference-layout BVH (so a malformed tree can never hang a GPU),
+// converts it to the children-in-parent PairNode layout + leaf-ordered triangle
+// records (layout.h) and uploads it together with the verbatim mesh arrays.
+#include "scene.h"
+
+#include <cmath>
+#include <cstring>
+
+namespace mb200 {
+
+namespace {
+
+bool all_float_exact(const double *v, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    const double x = v[i];
+    if (!std::isfinite(x)) return false;
+    if ((double)(float)x != x) return false;
+  }
+  return true;
+}
+
+} // namespace
+
+int relayout_bvh(Relayout &out, const double *vertices, size_t nverts, const uint32_t *faces, size_t nfaces,
+                 const uint32_t *material_ids, const mb200_bvh_node *nodes, size_t nnodes, const uint32_t *indices,
+                 size_t nindices, std::string *err) {
+  auto fail = [&](const char *m) {
+    if (err) *err = m;
+    return (int)MB200_ERR_INVALID_ARG;
+  };
+  out = Relayout();
+  if (nnodes == 0) return MB200_OK; // empty scene: every ray misses
+  if (!nodes || !indices || !vertices || !faces) return fail("null mesh/BVH array");
+  if (nnodes >= 0xFFFFFFF0ull || nindices >= 0xFFFFFFF0ull) return fail("BVH too large for 32-bit references");
+  for (size_t i = 0; i < nindices; i++)
+    if (indices[i] >= nfaces) return fail("BVH index array references a face out of range");
+  for (size_t i = 0; i < 3 * nfaces; i++)
+    if (faces[i] >= nverts) return fail("face references a vertex out of range");
+
+  // ---- pass 1: walk the tree (pre-order, explicit stack), validate, number the branches
+  std::vector<uint32_t> pair_of(nnodes, 0xFFFFFFFFu);
+  std::vector<unsigned char> seen(nnodes, 0);
+  struct Item {
+    uint32_t node;
+    int depth;
+  };
+  std::vector<Item> stack;
+  stack.push_back({0u, 0});
+  uint32_t npairs = 0;
+  int max_depth = 0;
+  while (!stack.empty()) {
+    Item it = stack.back();
+    stack.pop_back();
+    if (it.node >= nnodes) return fail("BVH child index out of range");
+    if (seen[it.node]) return fail("BVH is not a tree (node reachable twice)");
+    seen[it.node] = 1;
+    if (it.depth > max_depth) max_depth = it.depth;
+    const mb200_bvh_node &nd = nodes[it.node];
+    if (nd.flag == 0) {
+      if (nd.axis < 0 || nd.axis > 2) return fail("BVH branch node has an invalid split axis");
+      pair_of[it.node] = npairs++;
+      stack.push_back({nd.data[1], it.depth + 1});
+      stack.push_back({nd.data[0], it.depth + 1});
+    } else {
+      if ((size_t)nd.data[1] + (size_t)nd.data[0] > nindices) return fail("BVH leaf range exceeds the index array");
+    }
+  }
+  if (max_depth > 500) return fail("BVH deeper than 500 levels (reference stack is 512, bvh_accel.cc:548)");
+
+  // ---- pass 2: emit PairNodes
+  out.empty = false;
+  out.depth = max_depth;
+  out.pairs.resize(npairs);
+  auto child_ref = [&](uint32_t node, uint32_t &ref, uint32_t &cnt) {
+    const mb200_bvh_node &c = nodes[node];
+    if (c.flag == 0) {
+      ref = pair_of[node];
+      cnt = kBranch;
+    } else {
+      ref = c.data[1];
+      cnt = c.data[0];
+    }
+  };
+  child_ref(0, out.root_ref, out.root_cnt);
+  for (size_t i = 0; i < nnodes; i++) {
+    if (!seen[i] || nodes[i].flag != 0) continue;
+    PairNode &p = out.pairs[pair_of[i]];
+    memset(&p, 0, sizeof(p));
+    for (int c = 0; c < 2; c++) {
+      const mb200_bvh_node &ch = nodes[nodes[i].data[c]];
+      for (int k = 0; k < 3; k++) {
+        p.box[c][k] = ch.bmin[k];
+        p.box[c][3 + k] = ch.bmax[k];
+      }
+      child_ref(nodes[i].data[c], p.ref[c], p.cnt[c]);
+    }
+    p.axis = (uint32_t)nodes[i].axis;
+  }
+
+  // ---- triangle records in indices_ order
+  out.f32 = all_float_exact(vertices, 3 * nverts);
+  if (out.f32) {
+    out.tris32.resize(nindices);
+    for (size_t i = 0; i < nindices; i++) {
+      const uint32_t f = indices[i];
+      TriRecordF32 &t = out.tris32[i];
+      const double *a = vertices + 3 * (size_t)faces[3 * (size_t)f + 0];
+      const double *b = vertices + 3 * (size_t)faces[3 * (size_t)f + 1];
+      const double *c = vertices + 3 * (size_t)faces[3 * (size_t)f + 2];
+      for (int k = 0; k < 3; k++) t.p0[k] = (float)a[k], t.p1[k] = (float)b[k], t.p2[k] = (float)c[k];
+      t.face = f;
+      t.mat = material_ids ? material_ids[f] : 0xFFFFFFFFu; // bvh_accel.cc:685-689
+      t.pad_ = 0;
+    }
+  } else {
+    out.tris64.resize(nindices);
+    for (size_t i = 0; i < nindices; i++) {
+      const uint32_t f = indices[i];
+      TriRecordF64 &t = out.tris64[i];
+      for (int j = 0; j < 3; j++) {
+        const double *a = vertices + 3 * (size_t)faces[3 * (size_t)f + j];
+        for (int k = 0; k < 3; k++) t.p[3 * j + k] = a[k];
+      }
+      t.face = f;
+      t.mat = material_ids ? material_ids[f] : 0xFFFFFFFFu;
+    }
+  }
+  return MB200_OK;
+}
+
+namespace {
+
+struct Uploader {
+  mb200_scene *s;
+  std::string *err;
+  int status = MB200_OK;
+  template <typename T> const T *put(const T *host, size_t count) {
+    if (status != MB200_OK || count == 0 || !host) return nullptr;
+    void *d = nullptr;
+    const size_t bytes = count * sizeof(T);
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) {
+      status = (e == cudaErrorMemoryAllocation) ? MB200_ERR_OUT_OF_MEMORY : MB200_ERR_CUDA;
+      if (err) *err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+      return nullptr;
+    }
+    s->allocs.push_back(d);
+    s->device_bytes += bytes;
+    e = cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, s->stream);
+    if (e != cudaSuccess) {
+      status = MB200_ERR_CUDA;
+      if (err) *err = std::string("cudaMemcpy H2D: ") + cudaGetErrorString(e);
+      return nullptr;
+    }
+    return reinterpret_cast<const T *>(d);
+  }
+};
+
+} // namespace
+
+int scene_create(mb200_scene **out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
+                 size_t nfaces, const uint32_t *material_ids, const double *fv_normals, const double *fv_uvs,
+                 const mb200_bvh_node *nodes, size_t nnodes, const uint32_t *indices, size_t nindices,
+                 std::string *err) {
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    if (err) *err = std::string("no CUDA device: ") + cudaGetErrorString(e);
+    return MB200_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) {
+    if (err) *err = "device ordinal out of range";
+    return MB200_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+    if (err) *err = "device is not sm_100 class (this library ships sm_100a code only)";
+    return MB200_ERR_NO_DEVICE;
+  }
+
+  Relayout rl;
+  int st = relayout_bvh(rl, vertices, nverts, faces, nfaces, material_ids, nodes, nnodes, indices, nindices, err);
+  if (st != MB200_OK) return st;
+
+  if ((e = cudaSetDevice(device)) != cudaSuccess) {
+    if (err) *err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return MB200_ERR_CUDA;
+  }
+  mb200_scene *s = new mb200_scene;
+  s->device = device;
+  if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    if (err) *err = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+    delete s;
+    return MB200_ERR_CUDA;
+  }
+
+  Uploader up{s, err};
+  SceneView &v = s->view;
+  memset(&v, 0, sizeof(v));
+  v.empty = rl.empty ? 1 : 0;
+  v.tri_f32 = rl.f32 ? 1 : 0;
+  v.num_vertices = (uint32_t)nverts;
+  v.num_faces = (uint32_t)nfaces;
+  if (!rl.empty) {
+    v.nodes = up.put(rl.pairs.data(), rl.pairs.size());
+    v.tris = rl.f32 ? (const void *)up.put(rl.tris32.data(), rl.tris32.size())
+                    : (const void *)up.put(rl.tris64.data(), rl.tris64.size());
+    v.num_pair_nodes = (uint32_t)rl.pairs.size();
+    v.num_tris = (uint32_t)nindices;
+    v.root_ref = rl.root_ref;
+    v.root_cnt = rl.root_cnt;
+    for (int k = 0; k < 3; k++) {
+      v.root_box[k] = nodes[0].bmin[k];
+      v.root_box[3 + k] = nodes[0].bmax[k];
+      s->root_bmin[k] = nodes[0].bmin[k];
+      s->root_bmax[k] = nodes[0].bmax[k];
+    }
+    v.vertices = up.put(vertices, 3 * nverts);
+    v.faces = up.put(faces, 3 * nfaces);
+    v.fv_normals = fv_normals ? up.put(fv_normals, 9 * nfaces) : nullptr;
+    v.fv_uvs = fv_uvs ? up.put(fv_uvs, 6 * nfaces) : nullptr;
+  }
+  s->tree_depth = rl.depth;
+  s->stack_cap = rl.depth + 2;
+
+  if (up.status == MB200_OK) {
+    void *d = nullptr;
+    if ((e = cudaMalloc(&d, 8 * sizeof(unsigned long long))) != cudaSuccess) {
+      up.status = MB200_ERR_CUDA;
+      if (err) *err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+    } else {
+      s->allocs.push_back(d);
+      s->d_work = (unsigned long long *)d;
+      s->d_counters = s->d_work + 1;
+      cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), s->stream);
+    }
+  }
+  if (up.status == MB200_OK && (e = cudaStreamSynchronize(s->stream)) != cudaSuccess) {
+    up.status = MB200_ERR_CUDA;
+    if (err) *err = std::string("upload: ") + cudaGetErrorString(e);
+  }
+  if (up.status != MB200_OK) {
+    scene_destroy(s);
+    return up.status;
+  }
+  *out = s;
+  return MB200_OK;
+}
+
+void scene_destroy(mb200_scene *s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  for (void *p : s->allocs) cudaFree(p);
+  mb200_scene::Staging *sts[4] = {&s->in0, &s->in1, &s->out0, &s->out1};
+  for (auto *st : sts) {
+    if (st->pinned) cudaFreeHost(st->pinned);
+    if (st->dev) cudaFree(st->dev);
+  }
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+} // namespace mb200

@@ -1,0 +1,62 @@
+// scene.h -- the device-resident scene behind the opaque mb200_scene handle.
+#ifndef MALLIE_B200_SCENE_H_
+#define MALLIE_B200_SCENE_H_
+
+#include <cuda_runtime_api.h>
+
+#include <string>
+#include <vector>
+
+#include "layout.h"
+#include "mallie_b200.h"
+
+struct mb200_scene {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  mb200::SceneView view{};
+  int stack_cap = 64;          // traversal stack entries a ray can need (tree depth + 2)
+  int tree_depth = 0;
+  size_t device_bytes = 0;
+  double root_bmin[3] = {0, 0, 0}, root_bmax[3] = {0, 0, 0};
+
+  // owned device allocations
+  std::vector<void *> allocs;
+  unsigned long long *d_work = nullptr;     // persistent-warp work counter
+  unsigned long long *d_counters = nullptr; // [4] traversal counters / render stats
+
+  // staging for host-pointer calls: pinned host + device mirrors, grown on demand
+  struct Staging {
+    void *pinned = nullptr;
+    void *dev = nullptr;
+    size_t cap = 0;
+  };
+  Staging in0, in1, out0, out1;
+};
+
+namespace mb200 {
+
+// Validates the reference-layout BVH, re-lays it out (layout.h) and uploads everything.
+// On failure returns a negative mb200_status and fills err.
+int scene_create(mb200_scene **out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
+                 size_t nfaces, const uint32_t *material_ids, const double *fv_normals, const double *fv_uvs,
+                 const mb200_bvh_node *nodes, size_t nnodes, const uint32_t *indices, size_t nindices,
+                 std::string *err);
+void scene_destroy(mb200_scene *s);
+
+// Host-side relayout only (no CUDA): exposed for CPU tests of the layout logic.
+struct Relayout {
+  std::vector<PairNode> pairs;
+  std::vector<TriRecordF32> tris32;
+  std::vector<TriRecordF64> tris64;
+  bool f32 = false;
+  uint32_t root_ref = 0, root_cnt = 0;
+  int depth = 0;
+  bool empty = true;
+};
+int relayout_bvh(Relayout &out, const double *vertices, size_t nverts, const uint32_t *faces, size_t nfaces,
+                 const uint32_t *material_ids, const mb200_bvh_node *nodes, size_t nnodes, const uint32_t *indices,
+                 size_t nindices, std::string *err);
+
+} // namespace mb200
+
+#endif

@@ -1,0 +1,31 @@
+// bvh_build.h -- host BVH container + builder entry points (see bvh_build.cc).
+#ifndef MALLIE_B200_BVH_BUILD_H_
+#define MALLIE_B200_BVH_BUILD_H_
+
+#include <string>
+#include <vector>
+
+#include "mallie_b200.h"
+
+namespace mb200 {
+
+// Reference-layout BVH on the host: what BVHAccel keeps in nodes_/indices_ (bvh_accel.h:83-86).
+struct HostBVH {
+  std::vector<mb200_bvh_node> nodes;
+  std::vector<uint32_t> indices;
+  mb200_build_stats stats{0, 0, 0};
+};
+
+bool build_bvh(HostBVH &out, const double *vertices, size_t nverts, const uint32_t *faces, size_t nfaces,
+               const mb200_build_options &opt, std::string *err);
+bool dump_bvh(const HostBVH &bvh, const char *path, std::string *err);
+bool load_bvh(HostBVH &out, const char *path, std::string *err);
+
+} // namespace mb200
+
+// The opaque C handle is the container itself.
+struct mb200_bvh {
+  mb200::HostBVH bvh;
+};
+
+#endif

@@ -1,0 +1,91 @@
+"""Shared helpers for the test-suite: golden fixtures, scenes, comparisons."""
+import functools
+import json
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+
+from mallie_b200.procedural import bumpy_sphere  # noqa: E402
+from oracle import orabind as O  # noqa: E402
+
+
+@functools.lru_cache(maxsize=None)
+def golden():
+    with open(os.path.join(GOLDEN, "golden.json")) as fp:
+        return json.load(fp)
+
+
+@functools.lru_cache(maxsize=None)
+def load_mesh(name):
+    """name in {cornellbox, teapot, sphere40, sphere500}: dict(vertices f64, faces, material_ids, normals, uvs)."""
+    if name.startswith("sphere"):
+        v, f = bumpy_sphere(int(name[len("sphere"):]))
+        return dict(vertices=v, faces=f, material_ids=None, normals=None, uvs=None)
+    z = np.load(os.path.join(GOLDEN, f"{name}_mesh.npz"))
+    return dict(vertices=z["vertices"].astype(np.float64), faces=z["faces"],
+                material_ids=z["material_ids"] if "material_ids" in z else None,
+                normals=z["normals"] if "normals" in z else None, uvs=z["uvs"] if "uvs" in z else None)
+
+
+def sample(name):
+    z = np.load(os.path.join(GOLDEN, f"{name}_hits_sample.npz"))
+    return z["index"], z["hits"], z["mask"], z["isects"]
+
+
+def oracle_mesh(m):
+    return O.Mesh(m["vertices"], m["faces"], m["material_ids"], m["normals"], m["uvs"])
+
+
+@functools.lru_cache(maxsize=None)
+def oracle_scene(name):
+    om = oracle_mesh(load_mesh(name))
+    return om, O.BVH.build(om)
+
+
+def hexf(xs):
+    return np.array([float.fromhex(x) for x in xs])
+
+
+def golden_frame(entry):
+    f = entry["frame"]
+    return hexf(f["origin"]), hexf(f["corner"]), hexf(f["du"]), hexf(f["dv"])
+
+
+def mask_leaf_axis(nodes):
+    n = nodes.copy()
+    n["axis"][n["flag"] == 1] = 0
+    return n
+
+
+def fnv(a):
+    return "%016x" % O.fnv1a64(np.ascontiguousarray(a))
+
+
+def assert_hits_equal(got, want, what=""):
+    """Bit-exact comparison of 32-byte hit records; materialID only where something was hit."""
+    hit = want["faceID"] != 0xFFFFFFFF
+    for f in ("t", "u", "v", "faceID"):
+        a, b = np.ascontiguousarray(got[f]), np.ascontiguousarray(want[f])
+        if a.tobytes() != b.tobytes():
+            bad = np.nonzero(a.view(np.uint64 if a.dtype.itemsize == 8 else np.uint32) !=
+                             b.view(np.uint64 if b.dtype.itemsize == 8 else np.uint32))[0]
+            raise AssertionError(f"{what}: field {f} differs on {bad.size} rays, first {bad[:5]}: "
+                                 f"{a[bad[:5]]} vs {b[bad[:5]]}")
+    assert np.array_equal(got["materialID"][hit], want["materialID"][hit]), f"{what}: materialID differs"
+
+
+def random_rays(rng, n, bmin, bmax):
+    """Incoherent rays: origins on a shell around the box, directions towards random points inside it."""
+    c = 0.5 * (np.asarray(bmin) + np.asarray(bmax))
+    ext = 0.5 * (np.asarray(bmax) - np.asarray(bmin))
+    r = float(np.linalg.norm(ext)) * 2.0 + 1e-3
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    org = c + d * r
+    tgt = c + rng.uniform(-1.0, 1.0, size=(n, 3)) * ext * 1.2
+    dr = tgt - org
+    dr /= np.linalg.norm(dr, axis=1, keepdims=True)
+    return np.concatenate([org, dr], axis=1)
