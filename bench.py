@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s of the Mallie render hot path on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[3], the one the north-star target is quoted on):
+  procedurally tessellated bumpy sphere, N=500 -> exactly 1 000 000 triangles, 1920x1080, 16 spp,
+  primary closest-hit ray + one shadow (occlusion) ray per primary hit, camera eye (0,0,3) -> origin.
+A "step" is one 16-spp frame: 33.2 M primary rays + ~11.4 M shadow rays.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+* value : whole-job Mrays/s with everything resident in HBM (framebuffer stays on the device).
+          N > 1: image rows are interleaved across ranks in bands of 8 scanlines (strong scaling, the
+          frame is fixed), each rank renders its bands, one NCCL all-gather of the framebuffer per frame.
+* e2e   : the same frame through the C-ABI call a Mallie host makes (mb200_render_frame) with pinned HOST
+          image / count buffers; the device->host copy of the framebuffer is inside the timed region.
+* roofline : algorithmic bytes (64 B/node popped + 88 B/triangle tested + 48 B ray + 32 B hit record,
+          counted by the CPU oracle in reference traversal order for the exact ray set) / render-kernel time,
+          against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+* cpu_baseline : the unmodified reference (oracle/_ref) tracing a sample of the same ray set on the host cores.
+* --impl reference : times the reference's own OpenMP CPU path on the same workload (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, SPP, SPHERE_N = 1920, 1080, 16, 500
+EYE, LOOKAT, LIGHT = (0.0, 0.0, 3.0), (0.0, 0.0, 0.0), (2.0, 4.0, 3.0)
+BAND_ROWS = 8
+METRIC = "Mrays/s primary+shadow at 1920x1080"
+L2_FLUSH_BYTES = 512 << 20
+
+
+def config_dict(n_gpus):
+    return {
+        "workload": "bumpy-sphere N=500 (1,000,000 triangles, 501,501 vertices), 1920x1080, 16 spp, "
+                    "primary closest-hit + 1 shadow ray per hit, eye (0,0,3) lookat (0,0,0) fov 45, light (2,4,3)",
+        "triangles": 1000000, "resolution": [W, H], "spp": SPP, "shader": "primary+shadow",
+        "parallelism": "1 GPU" if n_gpus == 1 else f"image rows in {BAND_ROWS}-scanline bands interleaved over "
+                                                    f"{n_gpus} GPUs, full scene replica per GPU, NCCL all-gather of the framebuffer",
+        "l2": "L2 flushed between timed steps (512 MiB memset); scene (84 MB) is L2-resident within a step",
+    }
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fp:
+            return float(json.load(fp)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+                power.append(float(c[3]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if c[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=float(max(power)))
+        return out
+
+
+def build_inputs():
+    from mallie_b200.procedural import bumpy_sphere
+    return bumpy_sphere(SPHERE_N)
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU side (oracle / reference): test infrastructure, used here only as checker + baseline
+# ----------------------------------------------------------------------------------------------------
+class CpuSide:
+    def __init__(self, v, f):
+        from oracle import orabind as O
+        from oracle import refbind as R
+        self.O, self.R = O, R
+        self.mesh = O.Mesh(v, f)
+        self.bvh = O.BVH.build(self.mesh)
+        self.frame = O.camera_frame(EYE, LOOKAT, width=W, height=H)
+        self.ref = None
+        if R.available():
+            self.ref = R.RefScene.from_arrays(v, f)
+            self.ref.build()
+        self.cores = os.cpu_count() or 1
+
+    def pass_rays(self, k):
+        """Exact ray set of pass k (jittered camera rays + shadow rays) and its oracle node/triangle counts."""
+        _, _, info = self.bvh.render_pass(self.frame, W, H, rng_mode=1, pass_index=k, shader=1, light=LIGHT,
+                                          emit_rays=True)
+        rays = np.concatenate([info["primary_rays"], info["shadow_rays_buf"]], axis=0)
+        return rays, info
+
+    def algorithmic_bytes(self, passes):
+        """sum over all rays of 64*N_node + 88*N_tri + 48 + 32 (SURVEY.md §8d / BASELINE.md §3)."""
+        tot = dict(rays=0, n_node=0, n_tri=0, shadow=0)
+        for k in passes:
+            _, _, info = self.bvh.render_pass(self.frame, W, H, rng_mode=1, pass_index=k, shader=1, light=LIGHT)
+            tot["rays"] += info["trace_calls"] + info["shadow_rays"]
+            tot["shadow"] += info["shadow_rays"]
+            tot["n_node"] += info["n_node"]
+            tot["n_tri"] += info["n_tri"]
+        tot["bytes"] = 64 * tot["n_node"] + 88 * tot["n_tri"] + 80 * tot["rays"]
+        return tot
+
+    def trace_seconds(self, rays, repeat=1):
+        """Reference Scene::Trace over the ray buffer, OpenMP schedule(dynamic,1) over 1920-ray rows."""
+        if self.ref is not None:
+            return self.ref.trace(rays, row=W, nthreads=0, repeat=repeat)["seconds"], "reference"
+        best = 1e30
+        for _ in range(repeat):
+            best = min(best, self.bvh.trace(rays, row=W)["seconds"])
+        return best, "port"
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    v, f = build_inputs()
+    cpu = CpuSide(v, f)
+    secs, nrays = [], 0
+    kind = "reference"
+    for i in range(args.warmup + args.steps):
+        rays, _ = cpu.pass_rays(i % SPP)
+        s, kind = cpu.trace_seconds(rays)
+        if i >= args.warmup:
+            secs.append(s)
+            nrays += len(rays)
+    total = float(sum(secs))
+    val = nrays / total / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cpu.cores, "kind": kind,
+                         "sample": "each step = the exact ray set of ONE of the 16 passes (2.07 M jittered camera rays + "
+                                   "~0.72 M shadow rays, closest-hit Scene::Trace for both), OpenMP schedule(dynamic,1) "
+                                   "over 1920-ray rows on all host threads"},
+        "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the oracle legs (roofline bytes + cpu_baseline)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    import mallie_b200 as M
+    from mallie_b200 import tiles
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    v, f = build_inputs()
+    t0 = time.perf_counter()
+    sc = M.Scene(v, f, device=local_rank)          # host binned-SAH build + re-layout + upload (excluded)
+    build_s = time.perf_counter() - t0
+    frame = M.camera_frame(EYE, LOOKAT, width=W, height=H)
+    stream = torch.cuda.ExternalStream(sc.stream(), device=torch.device("cuda", local_rank))
+    L = M.capi.lib()
+    C = M.capi.C
+
+    bands = (BAND_ROWS, world, rank) if world > 1 else None
+    params = sc.render_params(frame, W, H, shader=M.SHADER_PRIMARY_SHADOW, light=LIGHT, pass_index=0,
+                              bands=bands, compact=world > 1)
+    rows_local = sc.band_local_rows(params) if world > 1 else H
+    d_img = torch.zeros((rows_local, W, 3), dtype=torch.float32, device="cuda")
+    d_cnt = torch.zeros((rows_local, W), dtype=torch.int32, device="cuda")
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+    gather = tiles.FramebufferGather(W, H, BAND_ROWS, world, rank, torch.device("cuda", local_rank)) if world > 1 else None
+
+    def render_device():
+        M.capi.check(L.mb200_render_frame(sc.h, C.byref(params), SPP, C.c_void_p(d_img.data_ptr()),
+                                          C.c_void_p(d_cnt.data_ptr()), None))
+
+    def step_device(ev=None):
+        """One frame, everything on the device, on the scene's stream."""
+        with torch.cuda.stream(stream):
+            render_device()
+            if ev is not None:
+                ev.record(stream)
+            if gather is not None:
+                return gather(d_img)
+        return d_img
+
+    # exact ray counts of a frame (deterministic: the same 16 passes every step)
+    _, _, st = sc.render_frame(params, SPP, d_img.data_ptr(), d_cnt.data_ptr(), stats=True)
+    rays_local = st["primary_rays"] + st["shadow_rays"]
+    rays_t = torch.tensor([rays_local, st["shadow_rays"]], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(rays_t)
+    rays_frame, shadow_frame = int(rays_t[0]), int(rays_t[1])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ value: device-resident
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    launches0 = M.capi.launches_issued()
+    sampler = ClockSampler(local_rank)
+    evs = []
+    barrier()
+    for _ in range(args.steps):
+        e0, em, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        with torch.cuda.stream(stream):
+            flush.zero_()
+            e0.record(stream)
+        step_device(em)
+        with torch.cuda.stream(stream):
+            e1.record(stream)
+        evs.append((e0, em, e1))
+    barrier()
+    clocks = sampler.stop()
+    launches = M.capi.launches_issued() - launches0
+    step_ms = [a.elapsed_time(c) for a, _, c in evs]
+    kern_ms = [a.elapsed_time(b) for a, b, _ in evs]
+    total_ms = torch.tensor([sum(step_ms), float(np.mean(kern_ms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms_max, kern_ms_max = float(total_ms[0]), float(total_ms[1])
+    value = rays_frame * args.steps / (total_ms_max * 1e-3) / 1e6
+
+    # ------------------------------------------------------------------ e2e: host buffers through the C ABI
+    h_img = torch.zeros((H, W, 3), dtype=torch.float32).pin_memory()
+    h_cnt = torch.zeros((H, W), dtype=torch.int32).pin_memory()
+    full_params = sc.render_params(frame, W, H, shader=M.SHADER_PRIMARY_SHADOW, light=LIGHT, pass_index=0)
+
+    def step_e2e():
+        if world == 1:
+            # the call a Mallie host makes: params in (by value), host framebuffer + count out
+            M.capi.check(L.mb200_render_frame(sc.h, C.byref(full_params), SPP, C.c_void_p(h_img.data_ptr()),
+                                              C.c_void_p(h_cnt.data_ptr()), None))
+        else:
+            full = step_device()
+            with torch.cuda.stream(stream):
+                if rank == 0:
+                    h_img.copy_(full, non_blocking=True)
+                    h_cnt.fill_(SPP)
+            stream.synchronize()
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        step_e2e()
+        e2e_s += time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = rays_frame * args.steps / float(e2e_t[0]) / 1e6
+    d2h = H * W * 3 * 4 + H * W * 4
+    h2d = C.sizeof(M.capi.RenderParams)
+
+    # ------------------------------------------------------------------ oracle legs (rank 0)
+    roofline, cpu_baseline = None, None
+    peak, peak_src = hbm_peak()
+    if rank == 0 and not args.no_cpu:
+        cpu = CpuSide(v, f)
+        alg = cpu.algorithmic_bytes(range(SPP))
+        assert alg["rays"] == rays_frame, (alg["rays"], rays_frame)
+        bytes_launch = alg["bytes"] / world        # one render launch per rank covers 1/world of the bands
+        achieved = bytes_launch / (kern_ms_max * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "kernel": "k_render (raygen + closest-hit + shadow + shade)",
+                    "kernel_ms": kern_ms_max, "algorithmic_bytes_per_launch": bytes_launch,
+                    "bytes_per_ray": alg["bytes"] / alg["rays"],
+                    "nodes_per_ray": alg["n_node"] / alg["rays"], "tris_per_ray": alg["n_tri"] / alg["rays"]}
+        if world == 1:
+            sample_passes = 4
+            rays = np.concatenate([cpu.pass_rays(k)[0] for k in range(sample_passes)], axis=0)
+            sec, kind = cpu.trace_seconds(rays, repeat=2)
+            cpu_baseline = {"value": len(rays) / sec / 1e6, "unit": "Mrays/s", "cores": cpu.cores, "kind": kind,
+                            "sample": f"{sample_passes} of the {SPP} passes, all pixels: {len(rays)} rays (camera + shadow, "
+                                      "closest-hit Scene::Trace), OpenMP schedule(dynamic,1) over 1920-ray rows, best of 2"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(world), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * float(e2e_t[0]) / args.steps},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "rays_per_step": rays_frame, "shadow_rays_per_step": shadow_frame, "scene_build_upload_s": build_s,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    sc.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -207,6 +207,11 @@ typedef struct {
   int jitter;                 /* 1 = PathTrace's [-0.5,0.5) jitter (render.cc:388-391); 0 = pixel coords as is */
   int shader;                 /* mb200_shader                                                         */
   double light[3];            /* MB200_SHADER_PRIMARY_SHADOW                                          */
+  /* Multi-GPU row-band interleave.  band_rows == 0: disabled.  Otherwise the tile's rows are
+   * cut into bands of band_rows scanlines (a multiple of 4) and this call renders only bands
+   * b with b % band_count == band_index; with band_compact != 0 the image/count buffers hold just those
+   * rows, packed band after band (float[3*width*mb200_band_local_rows()], the NCCL gather send buffer). */
+  int band_rows, band_count, band_index, band_compact;
 } mb200_render_params;
 
 typedef struct {
@@ -227,6 +232,14 @@ int mb200_render_pass(mb200_scene *scene, const mb200_render_params *params, flo
  * with AccumImage (main_sdl.cc:572-606).  accum: float[3*W*H], count: int[W*H], host or device. */
 int mb200_render_accumulate(mb200_scene *scene, const mb200_render_params *params, int num_passes, float *accum,
                             int *count, mb200_render_stats *stats);
+/* A whole frame of num_passes samples per pixel: image = sum of the passes, count = num_passes, both
+ * OVERWRITTEN for the tile's pixels (what DoMainConsole does with zeroed buffers and one pass,
+ * main_console.cc:57-75, generalised to N passes); nothing is read from image/count, so host
+ * buffers cost one device->host copy only. */
+int mb200_render_frame(mb200_scene *scene, const mb200_render_params *params, int num_passes, float *image,
+                       int *count, mb200_render_stats *stats);
+/* Rows of the image a banded call owns (== y1-y0 when bands are disabled). */
+int mb200_band_local_rows(const mb200_render_params *params);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,7 @@ EXPORTS = [
     "mb200_trace_closest", "mb200_trace_closest_full", "mb200_trace_occluded", "mb200_trace_closest_async",
     "mb200_camera_frame_build", "mb200_generate_rays", "mb200_generate_rays_grid",
     "mb200_render_params_default", "mb200_plane_from_bounds", "mb200_render_pass", "mb200_render_accumulate",
+    "mb200_render_frame", "mb200_band_local_rows",
 ]
 
 
@@ -66,7 +67,8 @@ class RenderParams(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("x0", C.c_int), ("y0", C.c_int), ("x1", C.c_int),
                 ("y1", C.c_int), ("frame", CameraFrame), ("use_plane", C.c_int), ("plane", C.c_float * 4),
                 ("max_path_length", C.c_int), ("pass_", C.c_uint32), ("jitter", C.c_int), ("shader", C.c_int),
-                ("light", C.c_double * 3)]
+                ("light", C.c_double * 3),
+                ("band_rows", C.c_int), ("band_count", C.c_int), ("band_index", C.c_int), ("band_compact", C.c_int)]
 
 
 class RenderStats(C.Structure):
@@ -133,6 +135,8 @@ def lib():
         L.mb200_plane_from_bounds.argtypes = [vp, vp, vp]
         L.mb200_render_pass.argtypes = [vp, C.POINTER(RenderParams), vp, vp, C.POINTER(RenderStats)]
         L.mb200_render_accumulate.argtypes = [vp, C.POINTER(RenderParams), i32, vp, vp, C.POINTER(RenderStats)]
+        L.mb200_render_frame.argtypes = [vp, C.POINTER(RenderParams), i32, vp, vp, C.POINTER(RenderStats)]
+        L.mb200_band_local_rows.argtypes = [C.POINTER(RenderParams)]
         _lib = L
     return _lib
 
@@ -334,7 +338,8 @@ class Scene:
 
     # -- frame
     def render_params(self, frame, width, height, tile=None, plane=None, max_path_length=16, pass_index=0,
-                      jitter=True, shader=SHADER_PATHTRACE, light=(0.0, 20.0, 0.0)):
+                      jitter=True, shader=SHADER_PATHTRACE, light=(0.0, 20.0, 0.0), bands=None, compact=False):
+        """bands = (band_rows, band_count, band_index) enables the multi-GPU row-band interleave."""
         p = RenderParams()
         lib().mb200_render_params_default(C.byref(p), width, height)
         p.frame = frame
@@ -347,7 +352,30 @@ class Scene:
         p.max_path_length, p.pass_, p.jitter, p.shader = max_path_length, pass_index, int(jitter), shader
         for k in range(3):
             p.light[k] = float(light[k])
+        if bands is not None:
+            p.band_rows, p.band_count, p.band_index = bands
+            p.band_compact = int(compact)
         return p
+
+    @staticmethod
+    def band_local_rows(params):
+        return int(lib().mb200_band_local_rows(C.byref(params)))
+
+    def _out_buffers(self, params, image, count):
+        rows = self.band_local_rows(params) if (params.band_rows > 0 and params.band_compact) else params.height
+        if image is None:
+            image = np.zeros((rows, params.width, 3), np.float32)
+        if count is None:
+            count = np.zeros((rows, params.width), np.int32)
+        return image, count
+
+    def render_frame(self, params, num_passes, image=None, count=None, stats=True):
+        """image = sum of num_passes samples, count = num_passes (both overwritten)."""
+        image, count = self._out_buffers(params, image, count)
+        st = RenderStats()
+        check(lib().mb200_render_frame(self.h, C.byref(params), num_passes, _p(image), _p(count),
+                                       C.byref(st) if stats else None))
+        return image, count, (st.as_dict() if stats else None)
 
     def render_pass(self, params, image=None, count=None, stats=True):
         """image/count: numpy arrays (host) or ints (device addresses)."""

@@ -34,18 +34,25 @@ int cuda_err(cudaError_t e, const char *what) {
     if (e_ != cudaSuccess) return cuda_err(e_, #call);       \
   } while (0)
 
-bool is_device_ptr(const void *p) {
-  if (!p) return false;
+enum HostKind { kDevice = 0, kPinned = 1, kPageable = 2 };
+
+// Where does a caller's buffer live?  Device/managed memory is used in place, page-locked host
+// memory is DMA'd directly, pageable host memory goes through the scene's pinned staging.
+HostKind classify(const void *p) {
   cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+  if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) {
     cudaGetLastError();
-    return false;
+    return kPageable;
   }
-  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+  if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return kDevice;
+  if (a.type == cudaMemoryTypeHost) return kPinned;
+  return kPageable;
 }
 
-int ensure(mb200_scene::Staging &st, size_t bytes) {
-  if (st.cap >= bytes) return MB200_OK;
+bool is_device_ptr(const void *p) { return p && classify(p) == kDevice; }
+
+int ensure(mb200_scene::Staging &st, size_t bytes, bool need_pinned = true) {
+  if (st.cap >= bytes && (!need_pinned || st.pinned)) return MB200_OK;
   if (st.pinned) cudaFreeHost(st.pinned);
   if (st.dev) cudaFree(st.dev);
   st.pinned = st.dev = nullptr;
@@ -346,50 +353,78 @@ void mb200_plane_from_bounds(const double bmin[3], const double bmax[3], float a
   abcd[3] = -(zmin - zsize * 0.0001f);
 }
 
-static int render_common(mb200_scene *s, const mb200_render_params *p, int num_passes, int accumulate, float *image,
+// mode 0: one pass, image overwritten, count++ (Render);  1: accumulate (image +=, count +=);
+// mode 2: fresh frame (image = sum, count = N; nothing is read from the caller's buffers).
+static int render_common(mb200_scene *s, const mb200_render_params *p, int num_passes, int mode, float *image,
                          int *count, mb200_render_stats *stats) {
   if (!s || !p || !image || !count) return set_err(MB200_ERR_INVALID_ARG, "null argument");
   if (p->width <= 0 || p->height <= 0 || p->x0 < 0 || p->y0 < 0 || p->x1 > p->width || p->y1 > p->height ||
       p->x0 > p->x1 || p->y0 > p->y1 || p->max_path_length < 1 || num_passes < 1)
     return set_err(MB200_ERR_INVALID_ARG, "bad render parameters");
   if (p->shader < 0 || p->shader > MB200_SHADER_PRIMARY_ONLY) return set_err(MB200_ERR_INVALID_ARG, "unknown shader");
+  if (p->band_rows < 0 || (p->band_rows > 0 && (p->band_rows % 4 != 0 || p->band_count < 1 || p->band_index < 0 ||
+                                                 p->band_index >= p->band_count)))
+    return set_err(MB200_ERR_INVALID_ARG, "bad band parameters (band_rows must be a multiple of 4)");
   if (stats) memset(stats, 0, sizeof(*stats));
   CU(cudaSetDevice(s->device));
-  const size_t npix = (size_t)p->width * p->height;
+  const bool compact = p->band_rows > 0 && p->band_compact;
+  const size_t rows = compact ? (size_t)mb200_band_local_rows(p) : (size_t)p->height;
+  const size_t npix = (size_t)p->width * rows;
+  if (npix == 0) return MB200_OK;
   const size_t img_bytes = npix * 3 * sizeof(float), cnt_bytes = npix * sizeof(int);
-  const bool dev_img = is_device_ptr(image), dev_cnt = is_device_ptr(count);
+  const HostKind img_kind = classify(image), cnt_kind = classify(count);
   float *d_img = image;
   int *d_cnt = count;
   int rc;
-  if (!dev_img) {
-    if ((rc = ensure(s->out0, img_bytes)) != MB200_OK) return rc;
+  // whole-buffer coverage: every pixel of the buffer is produced by this call
+  const bool covers_all = compact || (p->band_rows == 0 && p->x0 == 0 && p->y0 == 0 && p->x1 == p->width &&
+                                      p->y1 == p->height);
+  const bool need_img_in = (mode == 1) || !covers_all;  // pixels outside the tile must survive
+  const bool need_cnt_in = (mode != 2) || !covers_all;
+  if (img_kind != kDevice) {
+    if ((rc = ensure(s->out0, img_bytes, img_kind == kPageable)) != MB200_OK) return rc;
     d_img = (float *)s->out0.dev;
-    // the tile's pixels are overwritten / added to; the rest of the caller's image must survive
-    memcpy(s->out0.pinned, image, img_bytes);
-    CU(cudaMemcpyAsync(d_img, s->out0.pinned, img_bytes, cudaMemcpyHostToDevice, s->stream));
+    if (need_img_in) {
+      const void *src = image;
+      if (img_kind == kPageable) memcpy(s->out0.pinned, image, img_bytes), src = s->out0.pinned;
+      CU(cudaMemcpyAsync(d_img, src, img_bytes, cudaMemcpyHostToDevice, s->stream));
+    }
   }
-  if (!dev_cnt) {
-    if ((rc = ensure(s->out1, cnt_bytes)) != MB200_OK) return rc;
+  if (cnt_kind != kDevice) {
+    if ((rc = ensure(s->out1, cnt_bytes, cnt_kind == kPageable)) != MB200_OK) return rc;
     d_cnt = (int *)s->out1.dev;
-    memcpy(s->out1.pinned, count, cnt_bytes);
-    CU(cudaMemcpyAsync(d_cnt, s->out1.pinned, cnt_bytes, cudaMemcpyHostToDevice, s->stream));
+    if (need_cnt_in) {
+      const void *src = count;
+      if (cnt_kind == kPageable) memcpy(s->out1.pinned, count, cnt_bytes), src = s->out1.pinned;
+      CU(cudaMemcpyAsync(d_cnt, src, cnt_bytes, cudaMemcpyHostToDevice, s->stream));
+    }
   }
   CU(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream));
-  CU(mb200::launch_render(s->view, s->stack_cap, *p, num_passes, accumulate, d_img, d_cnt, s->d_work, s->d_counters,
+  CU(mb200::launch_render(s->view, s->stack_cap, *p, num_passes, mode, d_img, d_cnt, s->d_work, s->d_counters,
                           s->stream));
-  if (!dev_img) CU(cudaMemcpyAsync(s->out0.pinned, d_img, img_bytes, cudaMemcpyDeviceToHost, s->stream));
-  if (!dev_cnt) CU(cudaMemcpyAsync(s->out1.pinned, d_cnt, cnt_bytes, cudaMemcpyDeviceToHost, s->stream));
+  if (img_kind != kDevice)
+    CU(cudaMemcpyAsync(img_kind == kPinned ? (void *)image : s->out0.pinned, d_img, img_bytes, cudaMemcpyDeviceToHost,
+                       s->stream));
+  if (cnt_kind != kDevice)
+    CU(cudaMemcpyAsync(cnt_kind == kPinned ? (void *)count : s->out1.pinned, d_cnt, cnt_bytes, cudaMemcpyDeviceToHost,
+                       s->stream));
   unsigned long long c[4] = {0, 0, 0, 0};
-  if (stats || !dev_img || !dev_cnt) {
+  if (stats || img_kind != kDevice || cnt_kind != kDevice) {
     if (stats) CU(cudaMemcpyAsync(c, s->d_counters, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
   }
-  if (!dev_img) memcpy(image, s->out0.pinned, img_bytes);
-  if (!dev_cnt) memcpy(count, s->out1.pinned, cnt_bytes);
+  if (img_kind == kPageable) memcpy(image, s->out0.pinned, img_bytes);
+  if (cnt_kind == kPageable) memcpy(count, s->out1.pinned, cnt_bytes);
   if (stats) {
     stats->primary_rays = c[0], stats->bounce_rays = c[1], stats->shadow_rays = c[2], stats->zombie_segments = c[3];
   }
   return MB200_OK;
+}
+
+int mb200_band_local_rows(const mb200_render_params *p) {
+  if (!p) return 0;
+  if (p->band_rows <= 0) return p->y1 - p->y0;
+  return mb200::band_rows_owned(p->y1 - p->y0, p->band_rows, p->band_count, p->band_index);
 }
 
 int mb200_render_pass(mb200_scene *scene, const mb200_render_params *params, float *image, int *count,
@@ -400,6 +435,11 @@ int mb200_render_pass(mb200_scene *scene, const mb200_render_params *params, flo
 int mb200_render_accumulate(mb200_scene *scene, const mb200_render_params *params, int num_passes, float *accum,
                             int *count, mb200_render_stats *stats) {
   return render_common(scene, params, num_passes, 1, accum, count, stats);
+}
+
+int mb200_render_frame(mb200_scene *scene, const mb200_render_params *params, int num_passes, float *image,
+                       int *count, mb200_render_stats *stats) {
+  return render_common(scene, params, num_passes, 2, image, count, stats);
 }
 
 } // extern "C"

@@ -433,13 +433,26 @@ __device__ __forceinline__ void shade_sample(const SceneView &sc, const mb200_re
   }
 }
 
+// Rows owned by band `index` of `count` when `rows` scanlines are cut into bands of `band_rows`.
+__host__ __device__ inline int band_local_rows(int rows, int band_rows, int count, int index) {
+  const int nbands = (rows + band_rows - 1) / band_rows;
+  int local = 0;
+  for (int b = index; b < nbands; b += count) {
+    const int lo = b * band_rows, hi = lo + band_rows < rows ? lo + band_rows : rows;
+    local += hi - lo;
+  }
+  return local;
+}
+
 // Persistent warps; each fetch is one 8x4 pixel tile of the render rectangle (coherent
-// primary rays per warp).  num_passes samples per pixel are taken back to back and either
-// overwrite (accumulate = 0, one pass: render.cc:673-679) or add to (accumulate = 1) image.
+// primary rays per warp).  num_passes samples per pixel are taken back to back.
+// mode 0: image = last pass, count += passes (one pass: render.cc:673-679)
+// mode 1: image += passes, count += passes   (AccumImage, main_sdl.cc:138-143)
+// mode 2: image = sum of passes, count = passes (fresh frame; nothing read)
 template <bool F32, int CAP>
 __global__ void __launch_bounds__(kBlock)
     k_render(const __grid_constant__ SceneView sc, const __grid_constant__ mb200_render_params p, int num_passes,
-             int accumulate, float *__restrict__ image, int *__restrict__ count,
+             int mode, float *__restrict__ image, int *__restrict__ count,
              unsigned long long *__restrict__ work, unsigned long long *__restrict__ gstats) {
   extern __shared__ uint4 smem_stack[];
   TravStack<kSmemStack, CAP> st;
@@ -447,25 +460,33 @@ __global__ void __launch_bounds__(kBlock)
   st.stride = kBlock;
   RenderCounters rc = {0u, 0u, 0u, 0u};
 
-  const int tw = (p.x1 - p.x0 + 7) >> 3, th = (p.y1 - p.y0 + 3) >> 2;
+  // rows this call owns: all of [y0,y1), or every band_count-th band of band_rows scanlines
+  const int rows_total = p.y1 - p.y0;
+  int rows_local = rows_total;
+  if (p.band_rows > 0) rows_local = band_local_rows(rows_total, p.band_rows, p.band_count, p.band_index);
+  const int tw = (p.x1 - p.x0 + 7) >> 3, th = (rows_local + 3) >> 2;
   const unsigned long long ntiles = (unsigned long long)tw * th;
   for (;;) {
     const unsigned long long tile = warp_fetch(work, 1u);
     if (tile >= ntiles) break;
     const int tx = (int)(tile % tw), ty = (int)(tile / tw);
-    const int x = p.x0 + tx * 8 + (int)(lane_id() & 7u), y = p.y0 + ty * 4 + (int)(lane_id() >> 3);
-    if (x < p.x1 && y < p.y1) {
-      const size_t pix = (size_t)y * p.width + x;
+    const int x = p.x0 + tx * 8 + (int)(lane_id() & 7u);
+    const int rl = ty * 4 + (int)(lane_id() >> 3); // row among the rows this call owns
+    int y = p.y0 + rl;
+    if (p.band_rows > 0) y = p.y0 + ((rl / p.band_rows) * p.band_count + p.band_index) * p.band_rows + rl % p.band_rows;
+    if (x < p.x1 && rl < rows_local) {
+      const size_t pix = (p.band_rows > 0 && p.band_compact) ? ((size_t)rl * p.width + x) : ((size_t)y * p.width + x);
       float ar = 0.f, ag = 0.f, ab = 0.f;
-      if (accumulate) ar = image[3 * pix + 0], ag = image[3 * pix + 1], ab = image[3 * pix + 2];
+      if (mode == 1) ar = image[3 * pix + 0], ag = image[3 * pix + 1], ab = image[3 * pix + 2];
       for (int s = 0; s < num_passes; s++) {
         double r, g, b;
         shade_sample<F32, CAP>(sc, p, x, y, p.pass + (uint32_t)s, st, rc, r, g, b);
-        if (accumulate) ar += (float)r, ag += (float)g, ab += (float)b; // AccumImage: float += float
+        if (mode != 0) ar += (float)r, ag += (float)g, ab += (float)b; // AccumImage: float += float
         else ar = (float)r, ag = (float)g, ab = (float)b;
       }
       image[3 * pix + 0] = ar, image[3 * pix + 1] = ag, image[3 * pix + 2] = ab;
-      count[pix] += num_passes;
+      if (mode == 2) count[pix] = num_passes;
+      else count[pix] += num_passes;
     }
   }
   unsigned long long a = rc.primary, b = rc.bounce, c = rc.shadow, d = rc.zombie;
@@ -511,6 +532,10 @@ template <typename K> cudaError_t prepare(K kernel) {
 } // namespace
 
 int launches_issued() { return g_launches; }
+
+int band_rows_owned(int rows, int band_rows, int count, int index) {
+  return band_local_rows(rows, band_rows, count, index);
+}
 
 template <bool F32, int CAP>
 static cudaError_t do_trace_closest(const SceneView &sc, const mb200_ray *rays, size_t n, mb200_hit *hits,

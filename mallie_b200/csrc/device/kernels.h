@@ -22,6 +22,7 @@ cudaError_t launch_trace_occluded(const SceneView &sc, int stack_cap, const mb20
                                   size_t n, unsigned char *occluded, unsigned long long *work,
                                   unsigned long long *counters, cudaStream_t s);
 // stats: unsigned long long[4] primary, bounce, shadow, zombie (accumulated).
+// accumulate (mode): 0 = overwrite image / count += passes, 1 = accumulate both, 2 = overwrite both.
 cudaError_t launch_render(const SceneView &sc, int stack_cap, const mb200_render_params &p, int num_passes,
                           int accumulate, float *image, int *count, unsigned long long *work,
                           unsigned long long *stats, cudaStream_t s);
@@ -29,6 +30,8 @@ cudaError_t launch_generate_rays(const mb200_camera_frame &f, const double *px, 
                                  mb200_ray *rays, cudaStream_t s);
 cudaError_t launch_generate_grid(const mb200_camera_frame &f, int x0, int y0, int w, int h, mb200_ray *rays,
                                  cudaStream_t s);
+// Rows owned by one band index (see mb200_render_params::band_rows).
+int band_rows_owned(int rows, int band_rows, int count, int index);
 // Number of kernel launches issued by this library in this process (bench.py's gpu_launches).
 int launches_issued();
 

@@ -884,7 +884,7 @@ static const double kFar = 1.0e+30;      /* render.cc:50 */
  * post-escape segments -- which can never hit -- are not traced; their
  * contribution throughput*0.5/pathLength is accumulated in the same order. */
 static v3 path_trace(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, ora_rng *rng, int px,
-                     int py, uint64_t cnt[3]) {
+                     int py, uint64_t cnt[5]) {
   float ju = (float)(ora_randomreal(rng) - 0.5);
   float jv = (float)(ora_randomreal(rng) - 0.5);
   double ray[6];
@@ -902,7 +902,12 @@ static v3 path_trace(const ora_bvh *b, const ora_mesh *mesh, const ora_render_pa
     } else {
       if (escaped) cnt[1]++;
       cnt[0]++;
-      hit = ora_traverse(b, mesh, ray, ray + 3, &is, NULL);
+      {
+        uint64_t tc[3] = {0, 0, 0};
+        hit = ora_traverse(b, mesh, ray, ray + 3, &is, tc);
+        cnt[3] += tc[0];
+        cnt[4] += tc[1];
+      }
       if (p->use_plane) hit |= ora_plane_intersect(p->plane, ray, ray + 3, &is);
     }
     if (!hit) {
@@ -942,7 +947,7 @@ static v3 path_trace(const ora_bvh *b, const ora_mesh *mesh, const ora_render_pa
  * empty (render.cc:425-426), defined in DESIGN.md §"primary+shadow".  One closest-hit
  * primary ray; on a hit, one occlusion ray towards the point light. */
 static v3 primary_shadow(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, ora_rng *rng, int px,
-                         int py, uint64_t cnt[3]) {
+                         int py, uint64_t cnt[5], double *primary_out, double *shadow_out) {
   float ju = (float)(ora_randomreal(rng) - 0.5);
   float jv = (float)(ora_randomreal(rng) - 0.5);
   double ray[6];
@@ -951,9 +956,15 @@ static v3 primary_shadow(const ora_bvh *b, const ora_mesh *mesh, const ora_rende
   memset(&is, 0, sizeof(is));
   is.t = kFar;
   cnt[0]++;
-  int hit = ora_traverse(b, mesh, ray, ray + 3, &is, NULL);
+  uint64_t tc[3] = {0, 0, 0};
+  if (primary_out) memcpy(primary_out, ray, sizeof(ray));
+  int hit = ora_traverse(b, mesh, ray, ray + 3, &is, tc);
   if (p->use_plane) hit |= ora_plane_intersect(p->plane, ray, ray + 3, &is);
-  if (!hit) return v3_make(0.0, 0.0, 0.0);
+  if (!hit) {
+    cnt[3] += tc[0];
+    cnt[4] += tc[1];
+    return v3_make(0.0, 0.0, 0.0);
+  }
   v3 org = v3_ptr(ray), dir = v3_ptr(ray + 3);
   v3 hit_p = v3_add(org, v3_scale(dir, is.t));
   v3 n = v3_ptr(is.normal);
@@ -967,7 +978,10 @@ static v3 primary_shadow(const ora_bvh *b, const ora_mesh *mesh, const ora_rende
   ora_isect sh;
   memset(&sh, 0, sizeof(sh));
   cnt[2]++;
-  int occ = ora_traverse(b, mesh, sray, sray + 3, &sh, NULL) && sh.t < tmax;
+  if (shadow_out) { memcpy(shadow_out, sray, sizeof(sray)); shadow_out[6] = tmax; }
+  int occ = ora_traverse(b, mesh, sray, sray + 3, &sh, tc) && sh.t < tmax;
+  cnt[3] += tc[0];
+  cnt[4] += tc[1];
   double ndotl = v3_dot(n, ld);
   if (occ || !(ndotl > 0.0)) return v3_make(0.0, 0.0, 0.0);
   double kd = (is.material_id != (uint32_t)-1) ? 0.5 : 1.0;
@@ -975,46 +989,69 @@ static v3 primary_shadow(const ora_bvh *b, const ora_mesh *mesh, const ora_rende
   return v3_make(c, c, c);
 }
 
-/* Render, render.cc:593-708 (OpenMP scanline loop :657-698; step == 1) */
-void ora_render_pass(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, int x0, int y0, int x1,
-                     int y1, float *image, int *count, uint64_t ray_counts[3], int nthreads) {
+/* One pixel sample with either shader. */
+static v3 shade_pixel(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, ora_rng *rng, int x, int y,
+                      uint64_t c[5], double *primary_out, double *shadow_out) {
+  if (p->shader == 0) return path_trace(b, mesh, p, rng, x, y, c);
+  return primary_shadow(b, mesh, p, rng, x, y, c, primary_out, shadow_out);
+}
+
+/* Render, render.cc:593-708 (OpenMP scanline loop :657-698; step == 1).
+ * primary_rays_out (nullable, shader 1): [6*W*H] the jittered camera rays; shadow_rays_out (nullable):
+ * [7*W*H] org, dir, tmax of each shadow ray (NaN-filled where the primary ray missed). */
+void ora_render_pass_ex(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, int x0, int y0, int x1,
+                        int y1, float *image, int *count, uint64_t ray_counts[5], int nthreads,
+                        double *primary_rays_out, double *shadow_rays_out) {
   const int W = p->width;
-  uint64_t c0 = 0, c1 = 0, c2 = 0;
+  uint64_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+  if (shadow_rays_out)
+    for (size_t i = 0; i < (size_t)7 * W * p->height; i++) shadow_rays_out[i] = NAN;
   if (p->rng_mode == 0) {
-    /* sequential stream of OpenMP thread 0: identical to the reference with OMP_NUM_THREADS=1 */
+    /* sequential stream of OpenMP thread 0: identical to the reference with OMP_NUM_THREADS=1.  The
+     * reference keeps the stream across Render() calls (gSeed is global); only the first pass is
+     * reproducible here. */
     ora_rng rng;
     ora_rng_seed_reference(&rng, 0);
-    /* honour earlier passes: the reference keeps the stream across Render() calls (gSeed is global);
-     * callers needing pass>0 in this mode must render passes in order within one process -> not supported. */
     for (int y = y0; y < y1; y++)
       for (int x = x0; x < x1; x++) {
-        uint64_t c[3] = {0, 0, 0};
-        v3 r = p->shader == 0 ? path_trace(b, mesh, p, &rng, x, y, c) : primary_shadow(b, mesh, p, &rng, x, y, c);
-        image[3 * ((size_t)y * W + x) + 0] = (float)r.x;
-        image[3 * ((size_t)y * W + x) + 1] = (float)r.y;
-        image[3 * ((size_t)y * W + x) + 2] = (float)r.z;
-        count[(size_t)y * W + x]++;
-        c0 += c[0]; c1 += c[1]; c2 += c[2];
+        uint64_t c[5] = {0, 0, 0, 0, 0};
+        size_t pix = (size_t)y * W + x;
+        v3 r = shade_pixel(b, mesh, p, &rng, x, y, c, primary_rays_out ? primary_rays_out + 6 * pix : NULL,
+                           shadow_rays_out ? shadow_rays_out + 7 * pix : NULL);
+        image[3 * pix + 0] = (float)r.x;
+        image[3 * pix + 1] = (float)r.y;
+        image[3 * pix + 2] = (float)r.z;
+        count[pix]++;
+        c0 += c[0]; c1 += c[1]; c2 += c[2]; c3 += c[3]; c4 += c[4];
       }
   } else {
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
-#pragma omp parallel for schedule(dynamic, 1) reduction(+ : c0, c1, c2)
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : c0, c1, c2, c3, c4)
     for (int y = y0; y < y1; y++)
       for (int x = x0; x < x1; x++) {
         ora_rng rng;
-        ora_rng_seed_pixel(&rng, (uint32_t)((size_t)y * W + x), p->pass);
-        uint64_t c[3] = {0, 0, 0};
-        v3 r = p->shader == 0 ? path_trace(b, mesh, p, &rng, x, y, c) : primary_shadow(b, mesh, p, &rng, x, y, c);
-        image[3 * ((size_t)y * W + x) + 0] = (float)r.x;
-        image[3 * ((size_t)y * W + x) + 1] = (float)r.y;
-        image[3 * ((size_t)y * W + x) + 2] = (float)r.z;
-        count[(size_t)y * W + x]++;
-        c0 += c[0]; c1 += c[1]; c2 += c[2];
+        size_t pix = (size_t)y * W + x;
+        ora_rng_seed_pixel(&rng, (uint32_t)pix, p->pass);
+        uint64_t c[5] = {0, 0, 0, 0, 0};
+        v3 r = shade_pixel(b, mesh, p, &rng, x, y, c, primary_rays_out ? primary_rays_out + 6 * pix : NULL,
+                           shadow_rays_out ? shadow_rays_out + 7 * pix : NULL);
+        image[3 * pix + 0] = (float)r.x;
+        image[3 * pix + 1] = (float)r.y;
+        image[3 * pix + 2] = (float)r.z;
+        count[pix]++;
+        c0 += c[0]; c1 += c[1]; c2 += c[2]; c3 += c[3]; c4 += c[4];
       }
   }
-  if (ray_counts) { ray_counts[0] += c0; ray_counts[1] += c1; ray_counts[2] += c2; }
+  if (ray_counts) {
+    ray_counts[0] += c0; ray_counts[1] += c1; ray_counts[2] += c2; ray_counts[3] += c3; ray_counts[4] += c4;
+  }
+}
+
+void ora_render_pass(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, int x0, int y0, int x1,
+                     int y1, float *image, int *count, uint64_t ray_counts[5], int nthreads) {
+  ora_render_pass_ex(b, mesh, p, x0, y0, x1, y1, image, count, ray_counts, nthreads, NULL, NULL);
 }
 
 /* ======================================================================

@@ -120,9 +120,16 @@ typedef struct {
   double light[3];     /* shader 1 */
 } ora_render_params;
 /* image: float[3*W*H] overwritten; count[W*H] incremented; x0..x1,y0..y1 tile (whole image: 0,0,W,H).
- * ray_counts (nullable): [0]+=Trace calls made, [1]+=zombie segments skipped/traced, [2]+=shadow rays. */
+ * ray_counts (nullable, accumulated): [0] Trace calls for camera/bounce rays, [1] zombie segments,
+ * [2] shadow rays, [3] nodes popped, [4] triangles tested over all those rays (reference traversal order;
+ * shadow rays counted as the closest-hit Traverse that defines the occlusion oracle). */
 void ora_render_pass(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, int x0, int y0, int x1,
-                     int y1, float *image, int *count, uint64_t ray_counts[3], int nthreads);
+                     int y1, float *image, int *count, uint64_t ray_counts[5], int nthreads);
+/* Same, also emitting the exact ray set of the pass for the CPU-baseline timing (shader 1 only):
+ * primary_rays_out [6*W*H]; shadow_rays_out [7*W*H] = org, dir, tmax (NaN where the camera ray missed). */
+void ora_render_pass_ex(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, int x0, int y0, int x1,
+                        int y1, float *image, int *count, uint64_t ray_counts[5], int nthreads,
+                        double *primary_rays_out, double *shadow_rays_out);
 
 /* --- misc ---------------------------------------------------------------- */
 uint64_t ora_fnv1a64(const void *data, size_t nbytes, uint64_t seed /* 0 = standard offset basis */);

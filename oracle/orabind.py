@@ -84,6 +84,8 @@ def lib():
         L.ora_plane_from_bbox.argtypes = [vp, vp, vp]
         L.ora_render_pass.argtypes = [vp, C.POINTER(_Mesh), C.POINTER(_RenderParams), i32, i32, i32, i32,
                                       vp, vp, vp, i32]
+        L.ora_render_pass_ex.argtypes = [vp, C.POINTER(_Mesh), C.POINTER(_RenderParams), i32, i32, i32, i32,
+                                         vp, vp, vp, i32, vp, vp]
         L.ora_fnv1a64.restype = C.c_uint64
         L.ora_fnv1a64.argtypes = [vp, sz, C.c_uint64]
         L.ora_rng_seed_pixel.argtypes = [vp, C.c_uint32, C.c_uint32]
@@ -186,7 +188,7 @@ class BVH:
 
     def render_pass(self, frame, width, height, plane=None, max_path_length=16, rng_mode=1, pass_index=0,
                     skip_zombies=1, shader=0, light=(0.0, 0.0, 0.0), tile=None, image=None, count=None,
-                    nthreads=0):
+                    nthreads=0, emit_rays=False):
         p = _RenderParams()
         p.width, p.height = width, height
         o, c, du, dv = frame
@@ -204,10 +206,19 @@ class BVH:
         if count is None:
             count = np.zeros((height, width), np.int32)
         x0, y0, x1, y1 = tile if tile is not None else (0, 0, width, height)
-        rc = np.zeros(3, np.uint64)
-        lib().ora_render_pass(self.h, C.byref(self.mesh.c), C.byref(p), x0, y0, x1, y1, _p(image), _p(count),
-                              _p(rc), nthreads)
-        return image, count, dict(trace_calls=int(rc[0]), zombies=int(rc[1]), shadow_rays=int(rc[2]))
+        rc = np.zeros(5, np.uint64)
+        prim = np.zeros((height * width, 6)) if emit_rays else None
+        shad = np.zeros((height * width, 7)) if emit_rays else None
+        lib().ora_render_pass_ex(self.h, C.byref(self.mesh.c), C.byref(p), x0, y0, x1, y1, _p(image), _p(count),
+                                 _p(rc), nthreads, _p(prim), _p(shad))
+        info = dict(trace_calls=int(rc[0]), zombies=int(rc[1]), shadow_rays=int(rc[2]), n_node=int(rc[3]),
+                    n_tri=int(rc[4]))
+        if emit_rays:
+            info["primary_rays"] = prim
+            ok = ~np.isnan(shad[:, 0])
+            info["shadow_rays_buf"] = np.ascontiguousarray(shad[ok, :6])
+            info["shadow_tmax"] = np.ascontiguousarray(shad[ok, 6])
+        return image, count, info
 
 
 def camera_frame(eye, lookat, up=(0, 1, 0), fov=45.0, quat=(0, 0, 0, 0), width=512, height=512):

@@ -212,7 +212,7 @@ def test_deep_tree_uses_big_stack():
     rng = np.random.default_rng(11)
     n = 300
     c = rng.uniform(-1, 1, (n, 1, 3)) * np.array([1.0, 1.0, 0.2])
-    v = (c + rng.normal(0, 0.6, (n, 3, 3))).reshape(-1, 3).astype(np.float32).astype(np.float64)
+    v = (c + rng.normal(0, 2.0, (n, 3, 3))).reshape(-1, 3).astype(np.float32).astype(np.float64)
     f = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
     nodes, idx = chain_bvh(v, f)
     sc = M.Scene(v, f, nodes=nodes, indices=idx)

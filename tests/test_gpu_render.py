@@ -1,0 +1,187 @@
+"""GPU parity of the frame-level path (K1 raygen + K2/K4 traversal + K3 hit record + shading) against the
+oracle's restatement of Render/PathTrace (render.cc:381-456, 593-708) with the same per-pixel RNG streams.
+
+* primary+shadow uses only +,-,*,/ and sqrt (all IEEE-exact on both sides) -> images must be BIT-IDENTICAL.
+* PathTrace also calls acos/sin/cos, where CUDA's libdevice and glibc may differ in the last ulp.  Radiance
+  only depends on the hit/miss pattern of the path, so a pixel changes only if such an ulp flips a hit; the
+  test demands >= 99.9 % bit-identical pixels and a relative image-sum error < 1e-4.
+"""
+import numpy as np
+import pytest
+
+import mallie_b200 as M
+from oracle import orabind as O
+from tests import common as T
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_scene(name):
+    m = T.load_mesh(name)
+    return M.Scene(m["vertices"], m["faces"], m["material_ids"], m["normals"], m["uvs"])
+
+
+def frames(eye, lookat, W, H):
+    fg = M.camera_frame(eye, lookat, width=W, height=H)
+    fo = O.camera_frame(eye, lookat, width=W, height=H)
+    return fg, fo
+
+
+@pytest.mark.parametrize("mesh,eye,lookat,light,W,H", [
+    ("cornellbox", (0, 0, 20), (0, 0, 0), (0.0, 6.0, 8.0), 384, 256),
+    ("teapot", (5, 40, 150), (5, 40, 0), (80.0, 120.0, 100.0), 480, 270),
+    ("sphere40", (0.3, 0.2, 3), (0, 0, 0), (2.0, 4.0, 3.0), 301, 203),
+])
+def test_primary_shadow_bit_identical(mesh, eye, lookat, light, W, H):
+    sc = gpu_scene(mesh)
+    om, ob = T.oracle_scene(mesh)
+    fg, fo = frames(eye, lookat, W, H)
+    for pass_index in (0, 5):
+        p = sc.render_params(fg, W, H, shader=M.SHADER_PRIMARY_SHADOW, light=light, pass_index=pass_index)
+        img, cnt, st = sc.render_pass(p)
+        oimg, ocnt, oc = ob.render_pass(fo, W, H, rng_mode=1, pass_index=pass_index, shader=1, light=light)
+        assert img.tobytes() == oimg.tobytes()
+        assert np.array_equal(cnt, ocnt) and cnt.min() == 1 and cnt.max() == 1
+        assert st["primary_rays"] == W * H == oc["trace_calls"]
+        assert st["shadow_rays"] == oc["shadow_rays"] > 0
+        assert (img > 0).any() and (img == 0).any()
+    sc.close()
+
+
+@pytest.mark.parametrize("plane", [False, True])
+def test_pathtrace_matches_oracle(plane):
+    W = H = 256
+    sc = gpu_scene("cornellbox")
+    om, ob = T.oracle_scene("cornellbox")
+    fg, fo = frames((0, 0, 20), (0, 0, 0), W, H)
+    pl = M.plane_from_bounds(*sc.bounds()) if plane else None
+    nodes, _ = ob.arrays()
+    opl = O.plane_from_bbox(nodes[0]["bmin"], nodes[0]["bmax"]) if plane else None
+    if plane:
+        assert pl.tobytes() == opl.tobytes()
+    p = sc.render_params(fg, W, H, plane=pl, shader=M.SHADER_PATHTRACE, pass_index=3)
+    img, cnt, st = sc.render_pass(p)
+    oimg, ocnt, oc = ob.render_pass(fo, W, H, plane=opl, rng_mode=1, pass_index=3, skip_zombies=1, shader=0)
+    same = (img.view(np.uint32) == oimg.view(np.uint32)).all(axis=2)
+    assert same.mean() >= 0.999, f"only {same.mean():.5f} of the pixels are bit-identical"
+    assert abs(float(img.sum(dtype=np.float64)) - float(oimg.sum(dtype=np.float64))) <= 1e-4 * float(oimg.sum(dtype=np.float64))
+    # ray accounting: zombies are not rays; traced rays agree up to the few ulp-flipped paths
+    traced = st["primary_rays"] + st["bounce_rays"]
+    assert st["primary_rays"] == W * H
+    assert abs(traced - oc["trace_calls"]) <= 1e-3 * oc["trace_calls"]
+    assert abs(st["zombie_segments"] - oc["zombies"]) <= 1e-3 * oc["zombies"]
+    sc.close()
+
+
+def test_max_path_length_and_unjittered_primary_only():
+    W, H = 200, 120
+    sc = gpu_scene("cornellbox")
+    om, ob = T.oracle_scene("cornellbox")
+    fg, fo = frames((0, 0, 20), (0, 0, 0), W, H)
+    for L in (1, 2, 5):
+        p = sc.render_params(fg, W, H, shader=M.SHADER_PATHTRACE, max_path_length=L, pass_index=1)
+        img, _, st = sc.render_pass(p)
+        oimg, _, oc = ob.render_pass(fo, W, H, rng_mode=1, pass_index=1, max_path_length=L)
+        same = (img.view(np.uint32) == oimg.view(np.uint32)).all(axis=2)
+        assert same.mean() >= 0.999
+        if L == 1:
+            assert not img.any() and st["bounce_rays"] == 0
+    # primary-only, no jitter: coverage mask == un-jittered closest-hit mask
+    p = sc.render_params(fg, W, H, shader=M.SHADER_PRIMARY_ONLY, jitter=False)
+    img, _, st = sc.render_pass(p)
+    rays = O.generate_grid(fo, W, H)
+    o = ob.trace(rays, row=W)
+    assert np.array_equal(img[..., 0].reshape(-1) > 0, o["mask"])
+    assert st["primary_rays"] == W * H and st["shadow_rays"] == 0
+    sc.close()
+
+
+def test_tiles_bands_and_accumulation():
+    W, H = 203, 118            # ragged: not multiples of the 8x4 warp tile nor of the band height
+    light = (2.0, 4.0, 3.0)
+    sc = gpu_scene("sphere40")
+    fg, _ = frames((0.3, 0.2, 3), (0, 0, 0), W, H)
+    full_p = sc.render_params(fg, W, H, shader=M.SHADER_PRIMARY_SHADOW, light=light, pass_index=2)
+    full, fcnt, fst = sc.render_pass(full_p)
+
+    # (a) rectangular tiles written into one caller buffer: pixels outside a tile survive
+    img = np.full((H, W, 3), -1.0, np.float32)
+    cnt = np.zeros((H, W), np.int32)
+    rays = 0
+    for (x0, y0, x1, y1) in [(0, 0, 100, 50), (100, 0, W, 50), (0, 50, 37, H), (37, 50, W, H)]:
+        p = sc.render_params(fg, W, H, tile=(x0, y0, x1, y1), shader=M.SHADER_PRIMARY_SHADOW, light=light, pass_index=2)
+        _, _, st = sc.render_pass(p, img, cnt)
+        rays += st["primary_rays"]
+    assert img.tobytes() == full.tobytes() and np.array_equal(cnt, fcnt) and rays == W * H
+
+    # (b) multi-GPU row bands: G compact band images re-assembled == full image
+    for G, rows in ((2, 8), (3, 4), (8, 16)):
+        out = np.zeros_like(full)
+        for r in range(G):
+            p = sc.render_params(fg, W, H, shader=M.SHADER_PRIMARY_SHADOW, light=light, pass_index=2,
+                                 bands=(rows, G, r), compact=True)
+            local, lcnt, _ = sc.render_frame(p, 1)
+            ys = [y for y in range(H) if (y // rows) % G == r]
+            assert local.shape[0] == len(ys) == sc.band_local_rows(p)
+            out[ys] = local
+            assert (lcnt == 1).all()
+        assert out.tobytes() == full.tobytes(), (G, rows)
+        # non-compact banded render writes straight into the full-size image
+        img = np.zeros_like(full)
+        cnt = np.zeros((H, W), np.int32)
+        for r in range(G):
+            p = sc.render_params(fg, W, H, shader=M.SHADER_PRIMARY_SHADOW, light=light, pass_index=2,
+                                 bands=(rows, G, r), compact=False)
+            sc.render_pass(p, img, cnt)
+        assert img.tobytes() == full.tobytes() and (cnt == 1).all()
+
+    # (c) accumulation order: acc += (float)pass_k, k ascending (AccumImage, main_sdl.cc:138-143)
+    passes = []
+    for k in range(4):
+        p = sc.render_params(fg, W, H, shader=M.SHADER_PRIMARY_SHADOW, light=light, pass_index=k)
+        passes.append(sc.render_pass(p)[0])
+    want = np.zeros_like(full)
+    for im in passes:
+        want += im
+    p0 = sc.render_params(fg, W, H, shader=M.SHADER_PRIMARY_SHADOW, light=light, pass_index=0)
+    acc, acnt, ast = sc.render_accumulate(p0, 4)
+    assert acc.tobytes() == want.tobytes() and (acnt == 4).all()
+    fr, frcnt, _ = sc.render_frame(p0, 4, np.full_like(full, 7.0), np.full((H, W), 9, np.int32))
+    assert fr.tobytes() == want.tobytes() and (frcnt == 4).all()
+    acc2, acnt2, _ = sc.render_accumulate(sc.render_params(fg, W, H, shader=M.SHADER_PRIMARY_SHADOW, light=light,
+                                                           pass_index=2), 2, acc.copy(), acnt.copy())
+    want2 = want.copy()
+    for k in (2, 3):
+        want2 += passes[k]
+    assert acc2.tobytes() == want2.tobytes() and (acnt2 == 6).all()
+    assert ast["primary_rays"] == 4 * W * H
+    sc.close()
+
+
+def test_device_buffers_and_pinned_host():
+    torch = pytest.importorskip("torch")
+    W, H = 256, 128
+    sc = gpu_scene("sphere40")
+    fg, _ = frames((0.3, 0.2, 3), (0, 0, 3 - 3), W, H)
+    p = sc.render_params(fg, W, H, shader=M.SHADER_PRIMARY_SHADOW, light=(2.0, 4.0, 3.0))
+    ref, rcnt, _ = sc.render_frame(p, 3)
+    d_img = torch.full((H, W, 3), 5.0, dtype=torch.float32, device="cuda")
+    d_cnt = torch.zeros((H, W), dtype=torch.int32, device="cuda")
+    sc.render_frame(p, 3, d_img.data_ptr(), d_cnt.data_ptr(), stats=False)   # enqueue-only
+    sc.synchronize()
+    assert d_img.cpu().numpy().tobytes() == ref.tobytes() and (d_cnt.cpu().numpy() == 3).all()
+    h_img = torch.zeros((H, W, 3), dtype=torch.float32).pin_memory()
+    h_cnt = torch.zeros((H, W), dtype=torch.int32).pin_memory()
+    sc.render_frame(p, 3, h_img.numpy(), h_cnt.numpy())
+    assert h_img.numpy().tobytes() == ref.tobytes() and (h_cnt.numpy() == 3).all()
+    # device-resident ray / hit buffers
+    n = W * H
+    d_rays = torch.empty(n * 6, dtype=torch.float64, device="cuda")
+    d_hits = torch.empty(n * 4, dtype=torch.float64, device="cuda")
+    sc.generate_rays_grid(fg, 0, 0, W, H, out=d_rays.data_ptr())
+    sc.trace_closest_device(d_rays.data_ptr(), n, d_hits.data_ptr())
+    sc.synchronize()
+    hits = d_hits.cpu().numpy().view(M.capi.HIT_DTYPE)
+    om, ob = T.oracle_scene("sphere40")
+    T.assert_hits_equal(hits, ob.trace(d_rays.cpu().numpy().reshape(-1, 6), row=W)["hits"], "device buffers")
+    sc.close()
