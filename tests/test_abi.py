@@ -1,0 +1,195 @@
+"""The C-ABI library without a GPU: it loads, exports every symbol include/mallie_b200.h declares, its
+host-side logic (BVH build / dump / load, camera frame, plane, band arithmetic, argument checking) matches
+the oracle bit for bit, and every compute entry fails LOUDLY (no CPU fallback) when there is no device.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import mallie_b200 as M
+from mallie_b200 import capi, tiles
+from oracle import orabind as O
+from tests import common as T
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "mallie_b200.h")
+
+
+def header_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mb200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    declared = header_symbols()
+    assert len(declared) >= 30
+    assert sorted(capi.EXPORTS) == declared, set(capi.EXPORTS) ^ set(declared)
+    lib = capi.lib()
+    for s in declared:
+        assert hasattr(lib, s), s
+    # and the dynamic symbol table agrees (nothing resolved lazily from somewhere else)
+    out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (mb200_[a-z0-9_]+)", out))
+    assert set(declared) <= exported
+
+
+def test_library_does_not_link_the_oracle():
+    out = subprocess.run(["ldd", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "mallie_ref" not in out
+    nm = subprocess.run(["nm", "-D", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "ora_" not in nm and "ref_scene" not in nm
+
+
+def test_struct_layouts_match_the_header():
+    assert C.sizeof(capi.CameraFrame) == 96
+    assert C.sizeof(capi.Counters) == 32 and C.sizeof(capi.RenderStats) == 32
+    assert C.sizeof(capi.BuildOptions) == 24 and C.sizeof(capi.BuildStats) == 12
+    # mb200_render_params: 6 ints, frame (96, 8-aligned), int, float[4], int, u32, int, int, double[3], 4 ints
+    assert C.sizeof(capi.RenderParams) == 200
+    assert capi.RAY_DTYPE.itemsize == 48 and capi.HIT_DTYPE.itemsize == 32
+    assert capi.ISECT_DTYPE.itemsize == 184 and capi.NODE_DTYPE.itemsize == 64
+    assert capi.ISECT_DTYPE.fields["position"][1] == 48 and capi.ISECT_DTYPE.fields["normal"][1] == 96
+    assert capi.ISECT_DTYPE.fields["texcoord"][1] == 168
+    assert capi.lib().mb200_version().decode().startswith("mallie_b200")
+
+
+@pytest.mark.parametrize("mesh,entry", [("cornellbox", "cornellbox_512"), ("teapot", "teapot_1080p"),
+                                        ("sphere40", "sphere40_256"), ("sphere500", "sphere500_1080p")])
+def test_host_builder_is_the_reference_builder(mesh, entry):
+    g = T.golden()[entry]
+    m = T.load_mesh(mesh)
+    hb = M.HostBVH.build(m["vertices"], m["faces"])
+    nodes, idx = hb.arrays()
+    assert hb.stats() == g["stats"]
+    assert T.fnv(idx) == g["indices_fnv"] and T.fnv(T.mask_leaf_axis(nodes)) == g["nodes_fnv"]
+    hb.close()
+
+
+def test_host_builder_options_and_degenerate_inputs():
+    rng = np.random.default_rng(4)
+    v = rng.uniform(-1, 1, (900, 3)).astype(np.float32).astype(np.float64)
+    f = np.arange(900, dtype=np.uint32).reshape(300, 3)
+    for kw, okw in ((dict(min_leaf=4), dict(min_leaf=4)), (dict(max_depth=3), dict(max_depth=3)),
+                    (dict(bin_size=8, cost_taabb=1.0), dict(bin_size=8, cost_taabb=1.0))):
+        hb = M.HostBVH.build(v, f, **kw)
+        on, oi = O.BVH.build(O.Mesh(v, f), **okw).arrays()
+        n, i = hb.arrays()
+        assert i.tobytes() == oi.tobytes() and T.mask_leaf_axis(n).tobytes() == T.mask_leaf_axis(on).tobytes(), kw
+    # empty mesh: no nodes, no indices (Build on zero faces)
+    hb = M.HostBVH.build(np.zeros((0, 3)), np.zeros((0, 3), np.uint32))
+    n, i = hb.arrays()
+    assert len(i) == 0 and len(n) <= 1
+    # single triangle: one leaf root
+    hb = M.HostBVH.build(v[:3], f[:1])
+    n, i = hb.arrays()
+    assert len(n) == 1 and n[0]["flag"] == 1 and tuple(n[0]["data"]) == (1, 0)
+    # face index out of range is an error, not a crash
+    bad = f.copy()
+    bad[10, 1] = 5000
+    with pytest.raises(M.MallieB200Error):
+        M.HostBVH.build(v, bad)
+
+
+def test_dump_load_byte_compatible(tmp_path):
+    m = T.load_mesh("sphere40")
+    hb = M.HostBVH.build(m["vertices"], m["faces"])
+    p1, p2 = str(tmp_path / "a.bvh"), str(tmp_path / "b.bvh")
+    hb.dump(p1)
+    om, ob = T.oracle_scene("sphere40")
+    ob.dump(p2)
+    a, b = open(p1, "rb").read(), open(p2, "rb").read()
+    nn = int.from_bytes(a[:8], "little")
+    assert len(a) == len(b) == 8 + 64 * nn + 8 + 4 * len(m["faces"])
+    assert T.mask_leaf_axis(np.frombuffer(a[8:8 + 64 * nn], capi.NODE_DTYPE)).tobytes() == \
+        T.mask_leaf_axis(np.frombuffer(b[8:8 + 64 * nn], capi.NODE_DTYPE)).tobytes()
+    assert a[8 + 64 * nn:] == b[8 + 64 * nn:]
+    hb2 = M.HostBVH.load(p2)                      # a file written by the oracle (== the reference's format)
+    n1, i1 = hb.arrays()
+    n2, i2 = hb2.arrays()
+    assert i1.tobytes() == i2.tobytes() and T.mask_leaf_axis(n1).tobytes() == T.mask_leaf_axis(n2).tobytes()
+    with pytest.raises(M.MallieB200Error):
+        M.HostBVH.load(str(tmp_path / "missing.bvh"))
+    open(str(tmp_path / "trunc.bvh"), "wb").write(a[:100])
+    with pytest.raises(M.MallieB200Error):
+        M.HostBVH.load(str(tmp_path / "trunc.bvh"))
+
+
+def test_camera_frame_and_plane_match_oracle():
+    rng = np.random.default_rng(9)
+    cases = [((0, 0, 20), (0, 0, 0), (0, 1, 0), 45.0, (0, 0, 0, 0), 512, 512)]
+    for _ in range(50):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        cases.append((tuple(rng.uniform(-30, 30, 3)), tuple(rng.uniform(-3, 3, 3)), tuple(rng.normal(size=3)),
+                      float(rng.uniform(10, 120)), tuple(q), int(rng.integers(16, 4000)), int(rng.integers(16, 4000))))
+    for eye, lookat, up, fov, quat, W, H in cases:
+        fg = M.camera_frame(eye, lookat, up, fov, quat, W, H)
+        fo = O.camera_frame(eye, lookat, up, fov, quat, W, H)
+        for a, b in zip(fg.arrays(), fo):
+            assert a.tobytes() == b.tobytes()
+    for g in ("cornellbox_512", "teapot_1080p", "sphere40_256", "sphere500_1080p"):
+        e = T.golden()[g]
+        fg = M.camera_frame(e["eye"], e["lookat"], width=e["width"], height=e["height"])
+        for a, b in zip(fg.arrays(), T.golden_frame(e)):
+            assert a.tobytes() == b.tobytes()
+    for _ in range(20):
+        lo = rng.uniform(-5, 0, 3)
+        hi = lo + rng.uniform(0.1, 9, 3)
+        assert M.plane_from_bounds(lo, hi).tobytes() == O.plane_from_bbox(lo, hi).tobytes()
+
+
+def test_band_arithmetic_matches_tile_scheduler():
+    p = capi.RenderParams()
+    for H in (1, 7, 118, 1080, 2160):
+        for rows in (4, 8, 16):
+            for G in (1, 2, 3, 8):
+                total = 0
+                for r in range(G):
+                    capi.lib().mb200_render_params_default(C.byref(p), 64, H)
+                    p.band_rows, p.band_count, p.band_index = rows, G, r
+                    n = int(capi.lib().mb200_band_local_rows(C.byref(p)))
+                    assert n == len(tiles.band_rows_of_rank(H, rows, G, r))
+                    total += n
+                assert total == H
+    capi.lib().mb200_render_params_default(C.byref(p), 640, 480)
+    assert (p.width, p.height, p.x0, p.y0, p.x1, p.y1) == (640, 480, 0, 0, 640, 480)
+    assert p.max_path_length == 16 and p.jitter == 1 and p.shader == M.SHADER_PATHTRACE and p.band_rows == 0
+
+
+def test_gather_permutation_is_a_bijection():
+    for H, rows, G in ((1080, 8, 8), (118, 4, 3), (2160, 16, 8), (5, 8, 2)):
+        perm = tiles.gather_permutation(H, rows, G)
+        pad = tiles.max_local_rows(H, rows, G)
+        assert len(set(perm.tolist())) == H and perm.max() < G * pad
+        for r in range(G):
+            ys = tiles.band_rows_of_rank(H, rows, G, r)
+            assert np.array_equal(perm[ys], r * pad + np.arange(len(ys)))
+
+
+def test_argument_errors_are_reported_not_fatal():
+    L = capi.lib()
+    h = C.c_void_p()
+    assert L.mb200_bvh_build(None, None, 0, None, 0, None) == -1
+    assert b"null" in L.mb200_last_error()
+    assert L.mb200_bvh_load(C.byref(h), b"/nonexistent/file") == -5
+    assert L.mb200_trace_closest(None, None, 0, None, None) == -1
+    assert L.mb200_render_pass(None, None, None, None, None) == -1
+    assert L.mb200_scene_bounds(None, None, None) == -1
+    assert L.mb200_band_local_rows(None) == 0
+    assert L.mb200_scene_device_bytes(None) == 0 and L.mb200_scene_device(None) == -1
+    L.mb200_scene_destroy(None)
+    L.mb200_bvh_destroy(None)
+
+
+@pytest.mark.skipif(M.device_count() > 0, reason="only meaningful on a box without a GPU")
+def test_no_gpu_means_loud_failure_not_fallback():
+    m = T.load_mesh("sphere40")
+    with pytest.raises(M.MallieB200Error) as e:
+        M.Scene(m["vertices"], m["faces"])
+    assert "error -3" in str(e.value)            # MB200_ERR_NO_DEVICE
+    assert capi.launches_issued() == 0
