@@ -258,8 +258,13 @@ int mb200_trace_closest_full(mb200_scene *s, const mb200_ray *rays, size_t n, mb
   if ((rc = stage_in(s, s->in0, rays, n * sizeof(mb200_ray), &d_rays)) != MB200_OK) return rc;
   if ((rc = stage_out_begin(s->out0, isects, n * sizeof(mb200_isect), &d_is, &st_is)) != MB200_OK) return rc;
   if (hit_mask && (rc = stage_out_begin(s->out1, hit_mask, n, &d_mask, &st_mask)) != MB200_OK) return rc;
-  CU(mb200::launch_trace_closest_full(s->view, s->stack_cap, (const mb200_ray *)d_rays, n, (mb200_isect *)d_is,
-                                      (unsigned char *)d_mask, s->d_work, s->stream));
+  // K2 into scratch hit records, then K3 (BuildIntersection) expands them to the 184-byte records
+  CU(mb200::frame_scratch_reserve(s->hit_scratch, n * sizeof(mb200_hit), s->stream));
+  mb200_hit *d_hits = (mb200_hit *)s->hit_scratch.base;
+  CU(mb200::launch_trace_closest(s->view, s->stack_cap, (const mb200_ray *)d_rays, n, d_hits, s->d_work, nullptr,
+                                 s->stream));
+  CU(mb200::launch_build_isects(s->view, (const mb200_ray *)d_rays, d_hits, n, (mb200_isect *)d_is,
+                                (unsigned char *)d_mask, s->stream));
   if (st_is && (rc = stage_out_enqueue(s, s->out0, n * sizeof(mb200_isect))) != MB200_OK) return rc;
   if (st_mask && (rc = stage_out_enqueue(s, s->out1, n)) != MB200_OK) return rc;
   CU(cudaStreamSynchronize(s->stream));
@@ -399,9 +404,9 @@ static int render_common(mb200_scene *s, const mb200_render_params *p, int num_p
       CU(cudaMemcpyAsync(d_cnt, src, cnt_bytes, cudaMemcpyHostToDevice, s->stream));
     }
   }
-  CU(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream));
-  CU(mb200::launch_render(s->view, s->stack_cap, *p, num_passes, mode, d_img, d_cnt, s->d_work, s->d_counters,
-                          s->stream));
+  if (stats) CU(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream));
+  CU(mb200::launch_frame(s->view, s->stack_cap, *p, num_passes, mode, d_img, d_cnt, s->frame_scratch,
+                         stats ? s->d_counters : nullptr, s->stream));
   if (img_kind != kDevice)
     CU(cudaMemcpyAsync(img_kind == kPinned ? (void *)image : s->out0.pinned, d_img, img_bytes, cudaMemcpyDeviceToHost,
                        s->stream));

@@ -1,85 +1,55 @@
-// kernels.cu -- sm_100a kernels of the Mallie render hot path.
+// kernels.cu -- sm_100a kernels of the Mallie render hot path and their launchers.
 //
-//   K1 raygen        Camera::GenerateRay           camera.cc:222-240
-//   K2 closest hit   BVHAccel::Traverse            bvh_accel.cc:773-844
-//   K3 hit record    BuildIntersection             bvh_accel.cc:699-769
+//   K1 raygen        Camera::GenerateRay           camera.cc:222-240     (k_generate_*; fused into K2 for frames)
+//   K2 closest hit   BVHAccel::Traverse            bvh_accel.cc:773-844  (k_trace_sm, trace_sm.cuh)
+//   K3 hit record    BuildIntersection             bvh_accel.cc:699-769  (k_build_isects; inside the shade kernels)
 //   K4 occlusion     closest-hit t < tmax          (render.cc:425-426 leaves NEE empty)
-//   K5 render pass   Render/PathTrace + Plane      render.cc:381-456,593-708, prim-plane.cc:8-44
+//   K5 frame         Render/PathTrace + Plane      render.cc:381-456,593-708, prim-plane.cc:8-44
+//                    as a wavefront: trace camera rays -> shade -> trace queued rays -> ... -> resolve
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo
 // (no FMA contraction: see traverse.cuh).
 #include "kernels.h"
 
 #include <cstdio>
+#include <cstdlib>
 
+#include "shade.cuh"
+#include "trace_sm.cuh"
 #include "traverse.cuh"
 
 namespace mb200 {
 
 namespace {
 
-constexpr int kBlock = 128;   // threads per CTA
-constexpr int kSmemStack = 16; // stack entries per thread kept in shared memory
+constexpr int kBlock = 128; // threads per CTA of the traversal kernels
+
+// production configuration of the traversal state machine (A/B history: DESIGN.md §5)
+constexpr int kRefillMin = 4;   // idle lanes that trigger a refill
+constexpr int kPolicy = 2;      // both step bodies every iteration
+constexpr int kSmemStack = 16;  // stack entries per thread kept in shared memory
+constexpr int kMinBlocks = 5;   // resident CTAs per SM the register allocation targets
+constexpr unsigned kChunk = 32; // ray indices per atomicAdd
 
 __device__ __forceinline__ unsigned int lane_id() { return threadIdx.x & 31u; }
 
-// Per-warp dynamic fetch of `per_warp` consecutive work items from a global counter
-// (persistent threads: the grid is sized to the machine, not to the problem).
-__device__ __forceinline__ unsigned long long warp_fetch(unsigned long long *counter, unsigned int per_warp) {
-  unsigned long long base = 0;
-  if (lane_id() == 0) base = atomicAdd(counter, (unsigned long long)per_warp);
-  return __shfl_sync(0xFFFFFFFFu, base, 0);
-}
-
-__device__ __forceinline__ void flush_counters(const TravCounters &c, unsigned long long rays,
-                                               unsigned long long *g /* [4] */) {
-  unsigned long long n = c.nodes, t = c.tris, r = rays;
-  unsigned int m = c.max_stack;
-  for (int o = 16; o > 0; o >>= 1) {
-    n += __shfl_down_sync(0xFFFFFFFFu, n, o);
-    t += __shfl_down_sync(0xFFFFFFFFu, t, o);
-    r += __shfl_down_sync(0xFFFFFFFFu, r, o);
-    m = max(m, __shfl_down_sync(0xFFFFFFFFu, m, o));
-  }
-  if (lane_id() == 0) {
-    atomicAdd(&g[0], n);
-    atomicAdd(&g[1], t);
-    atomicAdd(&g[2], r);
-    atomicMax(&g[3], (unsigned long long)m);
-  }
-}
-
-// real3::normalize (common.h:48-57)
-__device__ __forceinline__ void normalize3(double &x, double &y, double &z) {
-  const double len = sqrt(x * x + y * y + z * z);
-  if (fabs(len) > 1.0e-6) {
-    const double inv = 1.0 / len;
-    x *= inv, y *= inv, z *= inv;
-  }
-}
-
-// Camera::GenerateRay (camera.cc:222-240)
-__device__ __forceinline__ void generate_ray(const mb200_camera_frame &f, double u, double v, double &dx, double &dy,
-                                             double &dz) {
-  dx = (f.corner[0] + u * f.du[0] + v * f.dv[0]) - f.origin[0];
-  dy = (f.corner[1] + u * f.du[1] + v * f.dv[1]) - f.origin[1];
-  dz = (f.corner[2] + u * f.du[2] + v * f.dv[2]) - f.origin[2];
-  normalize3(dx, dy, dz);
-}
-
 // ---------------------------------------------------------------------------
-// K1: ray generation
+// K1: ray generation into a ray buffer
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void store_ray(mb200_ray *dst, const mb200_camera_frame &f, double dx, double dy, double dz) {
+  double2 *o = reinterpret_cast<double2 *>(dst);
+  o[0] = make_double2(f.origin[0], f.origin[1]);
+  o[1] = make_double2(f.origin[2], dx);
+  o[2] = make_double2(dy, dz);
+}
+
 __global__ void __launch_bounds__(256) k_generate_rays(const __grid_constant__ mb200_camera_frame frame,
                                                        const double *__restrict__ px, const double *__restrict__ py,
                                                        size_t n, mb200_ray *__restrict__ rays) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     double dx, dy, dz;
     generate_ray(frame, px[i], py[i], dx, dy, dz);
-    mb200_ray r;
-    r.org[0] = frame.origin[0], r.org[1] = frame.origin[1], r.org[2] = frame.origin[2];
-    r.dir[0] = dx, r.dir[1] = dy, r.dir[2] = dz;
-    rays[i] = r;
+    store_ray(rays + i, frame, dx, dy, dz);
   }
 }
 
@@ -90,418 +60,306 @@ __global__ void __launch_bounds__(256) k_generate_grid(const __grid_constant__ m
     const int x = x0 + (int)(i % w), y = y0 + (int)(i / w);
     double dx, dy, dz;
     generate_ray(frame, (double)x, (double)y, dx, dy, dz);
-    mb200_ray r;
-    r.org[0] = frame.origin[0], r.org[1] = frame.origin[1], r.org[2] = frame.origin[2];
-    r.dir[0] = dx, r.dir[1] = dy, r.dir[2] = dz;
-    rays[i] = r;
+    store_ray(rays + i, frame, dx, dy, dz);
   }
 }
 
 // ---------------------------------------------------------------------------
-// K2 / K4: batched queries over a ray buffer (persistent warps, 32 rays per fetch)
+// K2 / K4: the persistent-warp traversal state machine (trace_sm.cuh) as a kernel.
+// n_dev (nullable): the ray count lives in device memory (a queue filled by the previous kernel).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void load_ray(const mb200_ray *rays, size_t i, RayD &r) {
-  const double2 *p = reinterpret_cast<const double2 *>(rays + i);
-  const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-  ray_setup(r, a.x, a.y, b.x, b.y, c.x, c.y);
-}
-
-template <bool F32, int CAP, bool COUNT>
-__global__ void __launch_bounds__(kBlock)
-    k_trace_closest(const __grid_constant__ SceneView sc, const mb200_ray *__restrict__ rays, size_t n,
-                    mb200_hit *__restrict__ hits, unsigned long long *__restrict__ work,
-                    unsigned long long *__restrict__ gcounters) {
+template <class IO, bool F32, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int POLICY, int S, int MINB, unsigned CHUNK>
+__global__ void __launch_bounds__(kBlock, MINB)
+    k_trace_sm(const __grid_constant__ SceneView sc, const __grid_constant__ IO io, unsigned long long n,
+               const unsigned int *__restrict__ n_dev, unsigned long long *__restrict__ work,
+               unsigned long long *__restrict__ gcounters) {
   extern __shared__ uint4 smem_stack[];
-  TravStack<kSmemStack, CAP> st;
+  TravStack<S, CAP> st;
   st.sm = smem_stack + threadIdx.x;
   st.stride = kBlock;
-  TravCounters cnt = {0u, 0u, 0u};
-  unsigned long long nrays = 0;
-
-  for (;;) {
-    const unsigned long long base = warp_fetch(work, 32u);
-    if (base >= n) break;
-    const size_t i = base + lane_id();
-    if (i < n) {
-      RayD r;
-      load_ray(rays, i, r);
-      HitD h;
-      h.t = DBL_MAX, h.u = 0.0, h.v = 0.0, h.face = 0xFFFFFFFFu, h.mat = 0xFFFFFFFFu;
-      traverse<F32, kSmemStack, CAP, false, COUNT>(sc, r, h, st, cnt);
-      nrays++;
-      double2 *o = reinterpret_cast<double2 *>(hits + i);
-      o[0] = make_double2(h.t, h.u);
-      const unsigned long long ids = ((unsigned long long)h.mat << 32) | h.face;
-      o[1] = make_double2(h.v, __longlong_as_double((long long)ids));
-    }
-  }
-  if (COUNT) flush_counters(cnt, nrays, gcounters);
-}
-
-template <bool F32, int CAP, bool COUNT>
-__global__ void __launch_bounds__(kBlock)
-    k_trace_occluded(const __grid_constant__ SceneView sc, const mb200_ray *__restrict__ rays,
-                     const double *__restrict__ tmax, size_t n, unsigned char *__restrict__ occluded,
-                     unsigned long long *__restrict__ work, unsigned long long *__restrict__ gcounters) {
-  extern __shared__ uint4 smem_stack[];
-  TravStack<kSmemStack, CAP> st;
-  st.sm = smem_stack + threadIdx.x;
-  st.stride = kBlock;
-  TravCounters cnt = {0u, 0u, 0u};
-  unsigned long long nrays = 0;
-
-  for (;;) {
-    const unsigned long long base = warp_fetch(work, 32u);
-    if (base >= n) break;
-    const size_t i = base + lane_id();
-    if (i < n) {
-      RayD r;
-      load_ray(rays, i, r);
-      HitD h;
-      h.t = tmax[i], h.u = 0.0, h.v = 0.0, h.face = 0xFFFFFFFFu, h.mat = 0xFFFFFFFFu;
-      const bool occ = traverse<F32, kSmemStack, CAP, true, COUNT>(sc, r, h, st, cnt);
-      nrays++;
-      occluded[i] = occ ? 1 : 0;
-    }
-  }
-  if (COUNT) flush_counters(cnt, nrays, gcounters);
+  if (n_dev) n = __ldg(n_dev);
+  trace_state_machine<IO, F32, S, CAP, ANYHIT, COUNT, REFILL_MIN, POLICY, CHUNK>(sc, io, n, work, st, gcounters);
 }
 
 // ---------------------------------------------------------------------------
-// K3: BuildIntersection (bvh_accel.cc:699-769) from a 32-byte hit record
+// K3: BuildIntersection for a buffer of rays + hit records -> full 184-byte Intersection records
 // ---------------------------------------------------------------------------
-struct IsectD {
-  double px, py, pz;    // position
-  double gx, gy, gz;    // geometric normal
-  double nx, ny, nz;    // shading normal
-  double tu, tv;        // texcoord
-  uint32_t f0, f1, f2;
-};
-
-__device__ __forceinline__ void build_intersection(const SceneView &sc, const RayD &r, const HitD &h, IsectD &o) {
-  const uint32_t *f = sc.faces + 3 * (size_t)h.face;
-  o.f0 = __ldg(f), o.f1 = __ldg(f + 1), o.f2 = __ldg(f + 2);
-  const double *v0 = sc.vertices + 3 * (size_t)o.f0;
-  const double *v1 = sc.vertices + 3 * (size_t)o.f1;
-  const double *v2 = sc.vertices + 3 * (size_t)o.f2;
-  const double p0x = __ldg(v0), p0y = __ldg(v0 + 1), p0z = __ldg(v0 + 2);
-  const double p1x = __ldg(v1), p1y = __ldg(v1 + 1), p1z = __ldg(v1 + 2);
-  const double p2x = __ldg(v2), p2y = __ldg(v2 + 1), p2z = __ldg(v2 + 2);
-  o.px = r.ox + h.t * r.dx;
-  o.py = r.oy + h.t * r.dy;
-  o.pz = r.oz + h.t * r.dz;
-  const double ax = p1x - p0x, ay = p1y - p0y, az = p1z - p0z;
-  const double bx = p2x - p0x, by = p2y - p0y, bz = p2z - p0z;
-  double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
-  normalize3(nx, ny, nz);
-  o.gx = nx, o.gy = ny, o.gz = nz;
-  if (sc.fv_normals) {
-    const double *N = sc.fv_normals + 9 * (size_t)h.face;
-    const double w = 1.0 - h.u - h.v;
-    o.nx = w * __ldg(N + 0) + h.u * __ldg(N + 3) + h.v * __ldg(N + 6);
-    o.ny = w * __ldg(N + 1) + h.u * __ldg(N + 4) + h.v * __ldg(N + 7);
-    o.nz = w * __ldg(N + 2) + h.u * __ldg(N + 5) + h.v * __ldg(N + 8);
-  } else {
-    o.nx = nx, o.ny = ny, o.nz = nz;
-  }
-  o.tu = 0.0, o.tv = 0.0;
-  if (sc.fv_uvs) {
-    const double *T = sc.fv_uvs + 6 * (size_t)h.face;
-    const double w = 1.0 - h.u - h.v;
-    o.tu = w * __ldg(T + 0) + h.u * __ldg(T + 2) + h.v * __ldg(T + 4);
-    o.tv = w * __ldg(T + 1) + h.u * __ldg(T + 3) + h.v * __ldg(T + 5);
-  }
-}
-
-template <bool F32, int CAP>
-__global__ void __launch_bounds__(kBlock)
-    k_trace_closest_full(const __grid_constant__ SceneView sc, const mb200_ray *__restrict__ rays, size_t n,
-                         mb200_isect *__restrict__ isects, unsigned char *__restrict__ mask,
-                         unsigned long long *__restrict__ work) {
-  extern __shared__ uint4 smem_stack[];
-  TravStack<kSmemStack, CAP> st;
-  st.sm = smem_stack + threadIdx.x;
-  st.stride = kBlock;
-  TravCounters cnt = {0u, 0u, 0u};
-  for (;;) {
-    const unsigned long long base = warp_fetch(work, 32u);
-    if (base >= n) break;
-    const size_t i = base + lane_id();
-    if (i < n) {
-      RayD r;
-      load_ray(rays, i, r);
-      HitD h;
-      h.t = DBL_MAX, h.u = 0.0, h.v = 0.0, h.face = 0xFFFFFFFFu, h.mat = 0xFFFFFFFFu;
-      const bool hit = traverse<F32, kSmemStack, CAP, false, false>(sc, r, h, st, cnt);
-      mb200_isect o;
-      memset(&o, 0, sizeof(o));
-      o.t = h.t, o.u = h.u, o.v = h.v, o.faceID = h.face, o.materialID = h.mat;
-      if (hit) {
-        IsectD d;
-        build_intersection(sc, r, h, d);
-        o.f0 = d.f0, o.f1 = d.f1, o.f2 = d.f2;
-        o.position[0] = d.px, o.position[1] = d.py, o.position[2] = d.pz;
-        o.geometricNormal[0] = d.gx, o.geometricNormal[1] = d.gy, o.geometricNormal[2] = d.gz;
-        o.normal[0] = d.nx, o.normal[1] = d.ny, o.normal[2] = d.nz;
-        o.texcoord[0] = d.tu, o.texcoord[1] = d.tv;
-      }
-      isects[i] = o;
-      if (mask) mask[i] = hit ? 1 : 0;
+__global__ void __launch_bounds__(256) k_build_isects(const __grid_constant__ SceneView sc,
+                                                      const mb200_ray *__restrict__ rays,
+                                                      const mb200_hit *__restrict__ hits, size_t n,
+                                                      mb200_isect *__restrict__ isects,
+                                                      unsigned char *__restrict__ mask) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double2 *hp = reinterpret_cast<const double2 *>(hits + i);
+    const double2 h0 = __ldg(hp), h1 = __ldg(hp + 1);
+    const unsigned long long ids = (unsigned long long)__double_as_longlong(h1.y);
+    const uint32_t face = (uint32_t)ids, mat = (uint32_t)(ids >> 32);
+    const bool hit = face != 0xFFFFFFFFu;
+    mb200_isect o;
+    memset(&o, 0, sizeof(o));
+    o.t = h0.x, o.u = h0.y, o.v = h1.x, o.faceID = face, o.materialID = mat;
+    if (hit) {
+      const double2 *rp = reinterpret_cast<const double2 *>(rays + i);
+      const double2 a = __ldg(rp), b = __ldg(rp + 1), c = __ldg(rp + 2);
+      IsectD d;
+      build_intersection(sc, a.x, a.y, b.x, b.y, c.x, c.y, h0.x, h0.y, h1.x, face, d);
+      o.f0 = d.f0, o.f1 = d.f1, o.f2 = d.f2;
+      o.position[0] = d.px, o.position[1] = d.py, o.position[2] = d.pz;
+      o.geometricNormal[0] = d.gx, o.geometricNormal[1] = d.gy, o.geometricNormal[2] = d.gz;
+      o.normal[0] = d.nx, o.normal[1] = d.ny, o.normal[2] = d.nz;
+      o.texcoord[0] = d.tu, o.texcoord[1] = d.tv;
     }
+    isects[i] = o;
+    if (mask) mask[i] = hit ? 1 : 0;
   }
 }
 
 // ---------------------------------------------------------------------------
-// K5: one render pass (or several accumulated) -- Render + PathTrace
+// K5: the frame wavefront.  Work item i = one sample of one pixel (shade.cuh: FrameMap).
+//
+//   trace<IOCamera>        camera ray generated in the refill step, hits[i] <- 32-byte record
+//   k_shade_primary        hit record -> PRIMARY_ONLY: contribution | PRIMARY_SHADOW: shadow ray queued |
+//                          PATHTRACE: first bounce queued, PathState saved
+//   trace<IOQueueShadow>   unoccluded rays deposit their value into contrib[item]
+//   trace<IOQueueClosest> / k_shade_bounce   one pair per further path segment (render.cc:401-450)
+//   k_resolve              per pixel: contributions of the batch's passes added in pass order, image/count written
 // ---------------------------------------------------------------------------
-struct Xorshift128 { // randomreal, render.cc:137-168
-  uint32_t x, y, z, w;
-  __device__ __forceinline__ double next() {
-    const uint32_t t = x ^ (x << 11);
-    x = y, y = z, z = w;
-    w = (w ^ (w >> 19)) ^ (t ^ (t >> 8));
-    return w * (1.0 / 4294967296.0);
-  }
-};
-
-__device__ __forceinline__ uint32_t mix32(uint32_t h) {
-  h ^= h >> 16, h *= 0x85ebca6bu, h ^= h >> 13, h *= 0xc2b2ae35u, h ^= h >> 16;
-  return h;
+// Appends a ray to a queue: one atomicAdd per warp.  Every lane of the warp must call it.
+__device__ __forceinline__ uint32_t queue_slot(unsigned int *qcount, bool want) {
+  const unsigned m = __ballot_sync(kFullMask, want);
+  if (!m) return 0u;
+  const int leader = __ffs(m) - 1;
+  unsigned base = 0;
+  if ((int)lane_id() == leader) base = atomicAdd(qcount, (unsigned)__popc(m));
+  base = __shfl_sync(kFullMask, base, leader);
+  return base + (unsigned)__popc(m & ((1u << lane_id()) - 1u));
 }
 
-// Replaces the per-OpenMP-thread seed table gSeed[tid] (render.cc:116-135): one
-// stream per (pixel, pass), same xorshift128 generator.
-__device__ __forceinline__ void rng_seed_pixel(Xorshift128 &g, uint32_t pixel, uint32_t pass) {
-  const uint32_t k = mix32(pixel * 0x9e3779b9u + 0x7f4a7c15u) ^ mix32(pass * 0x85ebca6bu + 0x165667b1u);
-  g.x = 123456789u ^ mix32(k + 1u);
-  g.y = 362436069u ^ mix32(k + 2u);
-  g.z = 521288629u ^ mix32(k + 3u);
-  g.w = 88675123u ^ mix32(k + 4u);
-  if ((g.x | g.y | g.z | g.w) == 0u) g.w = 88675123u;
+__device__ __forceinline__ void store_qray(QRay *dst, double ox, double oy, double oz, double dx, double dy, double dz,
+                                           double tmax, uint32_t item, float value) {
+  double2 *o = reinterpret_cast<double2 *>(dst);
+  o[0] = make_double2(ox, oy);
+  o[1] = make_double2(oz, dx);
+  o[2] = make_double2(dy, dz);
+  o[3] = make_double2(tmax, __longlong_as_double((long long)(((unsigned long long)__float_as_uint(value) << 32) | item)));
 }
 
-// Plane::intersect (prim-plane.cc:8-44): float vn / on_d / t.
-__device__ __forceinline__ bool plane_intersect(const float pl[4], const RayD &r, double &t_io, double &nx, double &ny,
-                                                double &nz, uint32_t &mat) {
-  double a = (double)pl[0], b = (double)pl[1], c = (double)pl[2];
-  double vx = r.dx, vy = r.dy, vz = r.dz;
-  normalize3(vx, vy, vz);
-  const float vn = (float)(vx * a + vy * b + vz * c);
-  if (fabsf(vn) > 1.1920928955078125e-7f * 1024.0f) {
-    const float on_d = (float)((r.ox * a + r.oy * b + r.oz * c) + (double)pl[3]);
-    const float t = -on_d / vn;
-    if ((t > 0) && ((double)t < t_io)) {
-      t_io = (double)t;
-      normalize3(a, b, c);
-      nx = a, ny = b, nz = c;
-      mat = 0xFFFFFFFFu;
-      return true;
-    }
-  }
-  return false;
-}
-
-// GenerateBasis + SampleDiffuseIS (render.cc:271-339)
-__device__ __forceinline__ void sample_diffuse(Xorshift128 &rng, double nx, double ny, double nz, double &ox,
-                                               double &oy, double &oz) {
-  int index = -1;
-  double minval = 1.0e+6;
-  {
-    double val = (double)fabsf((float)nx);
-    if (val < minval) minval = val, index = 0;
-    val = (double)fabsf((float)ny);
-    if (val < minval) minval = val, index = 1;
-    val = (double)fabsf((float)nz);
-    if (val < minval) minval = val, index = 2;
-  }
-  double tx, ty, tz;
-  if (index == 0) tx = 0.0, ty = -nz, tz = ny;
-  else if (index == 1) tx = -nz, ty = 0.0, tz = nx;
-  else tx = -ny, ty = nx, tz = 0.0;
-  normalize3(tx, ty, tz);
-  double bx = ty * nz - tz * ny, by = tz * nx - tx * nz, bz = tx * ny - ty * nx;
-  normalize3(bx, by, bz);
-  const double theta = acos(sqrt(1.0 - rng.next()));
-  const double phi = 2.0 * 3.14159265358979323846 * rng.next();
-  const double ct = cos(theta), st = sin(theta), cp = cos(phi), sp = sin(phi);
-  ox = ((tx * cp) * st + (bx * sp) * st) + nx * ct;
-  oy = ((ty * cp) * st + (by * sp) * st) + ny * ct;
-  oz = ((tz * cp) * st + (bz * sp) * st) + nz * ct;
-}
-
-struct RenderCounters {
-  unsigned int primary, bounce, shadow, zombie;
-};
-
-constexpr double kRenderEPS = 1.0e-3; // render.cc:51
-constexpr double kFar = 1.0e+30;      // render.cc:50
-
-// One sample of one pixel.  PathTrace (render.cc:381-456) with the post-escape
-// "zombie" segments resolved in closed form (they cannot hit),
-// or the primary+shadow shader.
-template <bool F32, int CAP>
-__device__ __forceinline__ void shade_sample(const SceneView &sc, const mb200_render_params &p, int px, int py,
-                                             uint32_t pass, TravStack<kSmemStack, CAP> &st, RenderCounters &rc,
-                                             double &out_r, double &out_g, double &out_b) {
-  TravCounters tc = {0u, 0u, 0u};
-  Xorshift128 rng;
-  rng_seed_pixel(rng, (uint32_t)((size_t)py * p.width + px), pass);
-  double fu = (double)px, fv = (double)py;
-  if (p.jitter) {
-    const float ju = (float)(rng.next() - 0.5);
-    const float jv = (float)(rng.next() - 0.5);
-    fu = (double)((float)px + ju); // int + float is a float add (render.cc:391)
-    fv = (double)((float)py + jv);
-  }
-  RayD r;
-  {
-    double dx, dy, dz;
-    generate_ray(p.frame, fu, fv, dx, dy, dz);
-    ray_setup(r, p.frame.origin[0], p.frame.origin[1], p.frame.origin[2], dx, dy, dz);
-  }
-  out_r = out_g = out_b = 0.0;
-
-  double thr_r = 1.0, thr_g = 1.0, thr_b = 1.0;
-  uint32_t cur_mat = 0; // Intersection::materialID is zero-initialised in the oracle harness
-  bool escaped = false;
-  const unsigned int max_len = (unsigned int)p.max_path_length;
-
-  for (unsigned int len = 1;; ++len) {
-    bool hit = false;
-    HitD h;
-    double nx = 0.0, ny = 0.0, nz = 0.0;
-    if (!escaped) {
-      h.t = DBL_MAX, h.u = 0.0, h.v = 0.0, h.face = 0xFFFFFFFFu, h.mat = cur_mat;
-      if (len == 1) rc.primary++;
-      else rc.bounce++;
-      hit = traverse<F32, kSmemStack, CAP, false, false>(sc, r, h, st, tc);
-      if (hit) {
-        IsectD d;
-        build_intersection(sc, r, h, d);
-        nx = d.nx, ny = d.ny, nz = d.nz;
-      }
-      if (p.use_plane) hit |= plane_intersect(p.plane, r, h.t, nx, ny, nz, h.mat);
-      cur_mat = h.mat;
-    } else {
-      rc.zombie++;
-    }
-
-    if (p.shader != MB200_SHADER_PATHTRACE) {
-      if (!hit) return;
-      if (p.shader == MB200_SHADER_PRIMARY_ONLY) {
-        out_r = out_g = out_b = 1.0;
-        return;
-      }
-      // primary + shadow: the NEE block the reference leaves empty.
-      const double hx = r.ox + h.t * r.dx, hy = r.oy + h.t * r.dy, hz = r.oz + h.t * r.dz;
-      if ((nx * (-r.dx) + ny * (-r.dy) + nz * (-r.dz)) < 0.0) nx = -nx, ny = -ny, nz = -nz;
-      double lx = p.light[0] - hx, ly = p.light[1] - hy, lz = p.light[2] - hz;
-      const double dist = sqrt(lx * lx + ly * ly + lz * lz);
-      normalize3(lx, ly, lz);
-      RayD sr;
-      ray_setup(sr, hx + lx * kRenderEPS, hy + ly * kRenderEPS, hz + lz * kRenderEPS, lx, ly, lz);
-      HitD sh;
-      sh.t = dist - kRenderEPS, sh.u = 0.0, sh.v = 0.0, sh.face = 0xFFFFFFFFu, sh.mat = 0xFFFFFFFFu;
-      rc.shadow++;
-      const bool occ = traverse<F32, kSmemStack, CAP, true, false>(sc, sr, sh, st, tc);
-      const double ndotl = nx * lx + ny * ly + nz * lz;
-      if (occ || !(ndotl > 0.0)) return;
-      const double kd = (h.mat != 0xFFFFFFFFu) ? 0.5 : 1.0;
-      out_r = out_g = out_b = kd * ndotl;
-      return;
-    }
-
-    if (!hit) {
-      if (len < 2) return; // kMinPathLength: eye ray escaped
-      const double l = (double)len;
-      out_r += thr_r * 0.5 / l, out_g += thr_g * 0.5 / l, out_b += thr_b * 0.5 / l;
-      escaped = true;
-    }
-    if (len >= max_len) return;
-
-    if (escaped) {
-      if (cur_mat != 0xFFFFFFFFu) thr_r *= 0.5, thr_g *= 0.5, thr_b *= 0.5;
-      continue;
-    }
-    const double hx = r.ox + h.t * r.dx, hy = r.oy + h.t * r.dy, hz = r.oz + h.t * r.dz;
-    (void)rng.next(); // drawn, unused (render.cc:430)
-    if ((nx * (-r.dx) + ny * (-r.dy) + nz * (-r.dz)) < 0.0) nx = -nx, ny = -ny, nz = -nz;
-    double sx, sy, sz;
-    sample_diffuse(rng, nx, ny, nz, sx, sy, sz);
-    if (cur_mat != 0xFFFFFFFFu) thr_r *= 0.5, thr_g *= 0.5, thr_b *= 0.5; // default Material::diffuse (scene.h:58-65)
-    ray_setup(r, hx + sx * kRenderEPS, hy + sy * kRenderEPS, hz + sz * kRenderEPS, sx, sy, sz);
-  }
-}
-
-// Rows owned by band `index` of `count` when `rows` scanlines are cut into bands of `band_rows`.
-__host__ __device__ inline int band_local_rows(int rows, int band_rows, int count, int index) {
-  const int nbands = (rows + band_rows - 1) / band_rows;
-  int local = 0;
-  for (int b = index; b < nbands; b += count) {
-    const int lo = b * band_rows, hi = lo + band_rows < rows ? lo + band_rows : rows;
-    local += hi - lo;
-  }
-  return local;
-}
-
-// Persistent warps; each fetch is one 8x4 pixel tile of the render rectangle (coherent
-// primary rays per warp).  num_passes samples per pixel are taken back to back.
-// mode 0: image = last pass, count += passes (one pass: render.cc:673-679)
-// mode 1: image += passes, count += passes   (AccumImage, main_sdl.cc:138-143)
-// mode 2: image = sum of passes, count = passes (fresh frame; nothing read)
-template <bool F32, int CAP>
-__global__ void __launch_bounds__(kBlock)
-    k_render(const __grid_constant__ SceneView sc, const __grid_constant__ mb200_render_params p, int num_passes,
-             int mode, float *__restrict__ image, int *__restrict__ count,
-             unsigned long long *__restrict__ work, unsigned long long *__restrict__ gstats) {
-  extern __shared__ uint4 smem_stack[];
-  TravStack<kSmemStack, CAP> st;
-  st.sm = smem_stack + threadIdx.x;
-  st.stride = kBlock;
-  RenderCounters rc = {0u, 0u, 0u, 0u};
-
-  // rows this call owns: all of [y0,y1), or every band_count-th band of band_rows scanlines
-  const int rows_total = p.y1 - p.y0;
-  int rows_local = rows_total;
-  if (p.band_rows > 0) rows_local = band_local_rows(rows_total, p.band_rows, p.band_count, p.band_index);
-  const int tw = (p.x1 - p.x0 + 7) >> 3, th = (rows_local + 3) >> 2;
-  const unsigned long long ntiles = (unsigned long long)tw * th;
-  for (;;) {
-    const unsigned long long tile = warp_fetch(work, 1u);
-    if (tile >= ntiles) break;
-    const int tx = (int)(tile % tw), ty = (int)(tile / tw);
-    const int x = p.x0 + tx * 8 + (int)(lane_id() & 7u);
-    const int rl = ty * 4 + (int)(lane_id() >> 3); // row among the rows this call owns
-    int y = p.y0 + rl;
-    if (p.band_rows > 0) y = p.y0 + ((rl / p.band_rows) * p.band_count + p.band_index) * p.band_rows + rl % p.band_rows;
-    if (x < p.x1 && rl < rows_local) {
-      const size_t pix = (p.band_rows > 0 && p.band_compact) ? ((size_t)rl * p.width + x) : ((size_t)y * p.width + x);
-      float ar = 0.f, ag = 0.f, ab = 0.f;
-      if (mode == 1) ar = image[3 * pix + 0], ag = image[3 * pix + 1], ab = image[3 * pix + 2];
-      for (int s = 0; s < num_passes; s++) {
-        double r, g, b;
-        shade_sample<F32, CAP>(sc, p, x, y, p.pass + (uint32_t)s, st, rc, r, g, b);
-        if (mode != 0) ar += (float)r, ag += (float)g, ab += (float)b; // AccumImage: float += float
-        else ar = (float)r, ag = (float)g, ab = (float)b;
-      }
-      image[3 * pix + 0] = ar, image[3 * pix + 1] = ag, image[3 * pix + 2] = ab;
-      if (mode == 2) count[pix] = num_passes;
-      else count[pix] += num_passes;
-    }
-  }
-  unsigned long long a = rc.primary, b = rc.bounce, c = rc.shadow, d = rc.zombie;
+__device__ __forceinline__ void warp_add_stats(unsigned long long *g, unsigned int a, unsigned int b) {
   for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_down_sync(0xFFFFFFFFu, a, o);
-    b += __shfl_down_sync(0xFFFFFFFFu, b, o);
-    c += __shfl_down_sync(0xFFFFFFFFu, c, o);
-    d += __shfl_down_sync(0xFFFFFFFFu, d, o);
+    a += __shfl_down_sync(kFullMask, a, o);
+    b += __shfl_down_sync(kFullMask, b, o);
   }
   if (lane_id() == 0) {
-    atomicAdd(&gstats[0], a);
-    atomicAdd(&gstats[1], b);
-    atomicAdd(&gstats[2], c);
-    atomicAdd(&gstats[3], d);
+    if (a) atomicAdd(&g[0], (unsigned long long)a);
+    if (b) atomicAdd(&g[3], (unsigned long long)b);
   }
+}
+
+// The tail of PathTrace after the path escaped at segment `len` (render.cc:407-417 has no break): the
+// remaining segments cannot hit and add throughput*0.5/pathLength each.  Returns the
+// number of those "zombie" segments (not rays).
+__device__ __forceinline__ unsigned int zombie_tail(unsigned int len, unsigned int max_len, uint32_t cur_mat,
+                                                    double &thr, double &radiance) {
+  unsigned int z = 0;
+  for (;;) {
+    if (len >= max_len) return z;
+    if (cur_mat != 0xFFFFFFFFu) thr *= 0.5;
+    ++len;
+    z++;
+    radiance += thr * 0.5 / (double)len;
+  }
+}
+
+// Continuation of a path whose segment `len` hit at (hx,hy,hz) with shading normal n (render.cc:423-449).
+__device__ __forceinline__ void bounce_ray(Xorshift128 &rng, double dx, double dy, double dz, double hx, double hy,
+                                           double hz, double nx, double ny, double nz, double &ox, double &oy,
+                                           double &oz, double &sx, double &sy, double &sz) {
+  (void)rng.next(); // drawn, unused (render.cc:430)
+  if ((nx * (-dx) + ny * (-dy) + nz * (-dz)) < 0.0) nx = -nx, ny = -ny, nz = -nz;
+  sample_diffuse(rng, nx, ny, nz, sx, sy, sz);
+  ox = hx + sx * kRenderEPS, oy = hy + sy * kRenderEPS, oz = hz + sz * kRenderEPS;
+}
+
+__device__ __forceinline__ void load_hit(const mb200_hit *src, double &t, double &u, double &v, uint32_t &face,
+                                         uint32_t &mat) {
+  const double2 *hp = reinterpret_cast<const double2 *>(src);
+  const double2 h0 = __ldg(hp), h1 = __ldg(hp + 1);
+  const unsigned long long ids = (unsigned long long)__double_as_longlong(h1.y);
+  t = h0.x, u = h0.y, v = h1.x, face = (uint32_t)ids, mat = (uint32_t)(ids >> 32);
+}
+
+__device__ __forceinline__ void save_state(PathState *dst, const Xorshift128 &rng, double thr, double radiance,
+                                           uint32_t cur_mat) {
+  uint4 *o = reinterpret_cast<uint4 *>(dst);
+  o[0] = make_uint4(rng.x, rng.y, rng.z, rng.w);
+  reinterpret_cast<double2 *>(dst)[1] = make_double2(thr, radiance);
+  o[2] = make_uint4(cur_mat, 0u, 0u, 0u);
+}
+
+// One thread per work item, after the camera-ray trace.
+__global__ void __launch_bounds__(256)
+    k_shade_primary(const __grid_constant__ SceneView sc, const __grid_constant__ mb200_render_params p,
+                    const __grid_constant__ FrameMap m, uint32_t items, const mb200_hit *__restrict__ hits,
+                    float *__restrict__ contrib, QRay *__restrict__ queue, unsigned int *__restrict__ qcount,
+                    PathState *__restrict__ states, unsigned long long *__restrict__ stats) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; // grid covers whole warps of items
+  int x = 0, y = 0, rl = 0;
+  uint32_t pass = 0;
+  const bool valid = i < items && item_pixel(m, i, x, y, rl, pass);
+  bool push = false;
+  float value = 0.f, out = 0.f;
+  double qox = 0, qoy = 0, qoz = 0, qdx = 0, qdy = 0, qdz = 0, qtmax = 0;
+  unsigned int zombies = 0;
+  if (valid) {
+    Xorshift128 rng;
+    double dx, dy, dz;
+    camera_sample(p, x, y, pass, rng, dx, dy, dz);
+    const double ox = p.frame.origin[0], oy = p.frame.origin[1], oz = p.frame.origin[2];
+    double t, u, v;
+    uint32_t face, mat;
+    load_hit(hits + i, t, u, v, face, mat);
+    bool hit = face != 0xFFFFFFFFu;
+    double nx = 0.0, ny = 0.0, nz = 0.0;
+    uint32_t cur_mat = 0; // Intersection::materialID before the first Trace (zero-initialised isect)
+    if (hit) {
+      IsectD d;
+      build_intersection(sc, ox, oy, oz, dx, dy, dz, t, u, v, face, d);
+      nx = d.nx, ny = d.ny, nz = d.nz;
+      cur_mat = mat;
+    }
+    if (p.use_plane) hit |= plane_intersect(p.plane, ox, oy, oz, dx, dy, dz, t, nx, ny, nz, cur_mat);
+    if (hit) {
+      const double hx = ox + t * dx, hy = oy + t * dy, hz = oz + t * dz;
+      if (p.shader == MB200_SHADER_PRIMARY_ONLY) {
+        out = 1.f;
+      } else if (p.shader == MB200_SHADER_PRIMARY_SHADOW) {
+        // the next-event-estimation block the reference leaves empty (render.cc:425-426)
+        if ((nx * (-dx) + ny * (-dy) + nz * (-dz)) < 0.0) nx = -nx, ny = -ny, nz = -nz;
+        double lx = p.light[0] - hx, ly = p.light[1] - hy, lz = p.light[2] - hz;
+        const double dist = sqrt(lx * lx + ly * ly + lz * lz);
+        normalize3(lx, ly, lz);
+        qox = hx + lx * kRenderEPS, qoy = hy + ly * kRenderEPS, qoz = hz + lz * kRenderEPS;
+        qdx = lx, qdy = ly, qdz = lz;
+        qtmax = dist - kRenderEPS;
+        const double ndotl = nx * lx + ny * ly + nz * lz;
+        const double kd = (cur_mat != 0xFFFFFFFFu) ? 0.5 : 1.0; // default Material::diffuse (scene.h:58-65)
+        value = (ndotl > 0.0) ? (float)(kd * ndotl) : 0.f;
+        push = true;
+      } else if (p.max_path_length > 1) { // PathTrace, segment 1 hit: continue the path
+        double thr = 1.0;
+        bounce_ray(rng, dx, dy, dz, hx, hy, hz, nx, ny, nz, qox, qoy, qoz, qdx, qdy, qdz);
+        if (cur_mat != 0xFFFFFFFFu) thr *= 0.5;
+        qtmax = DBL_MAX;
+        save_state(states + i, rng, thr, 0.0, cur_mat);
+        push = true;
+      }
+    }
+    // a camera ray that escapes contributes nothing (pathLength < kMinPathLength, render.cc:409-412)
+  }
+  const uint32_t slot = queue_slot(qcount, push);
+  if (push) store_qray(queue + slot, qox, qoy, qoz, qdx, qdy, qdz, qtmax, i, value);
+  if (i < items) contrib[i] = out;
+  warp_add_stats(stats, valid ? 1u : 0u, zombies);
+}
+
+// One thread per traced continuation ray of path segment `len` (>= 2): queue slot j, hits[j].
+__global__ void __launch_bounds__(256)
+    k_shade_bounce(const __grid_constant__ SceneView sc, const __grid_constant__ mb200_render_params p,
+                   unsigned int len, const QRay *__restrict__ qin, const unsigned int *__restrict__ qin_count,
+                   const mb200_hit *__restrict__ hits, QRay *__restrict__ qout, unsigned int *__restrict__ qout_count,
+                   PathState *__restrict__ states, float *__restrict__ contrib,
+                   unsigned long long *__restrict__ stats) {
+  const unsigned int n = __ldg(qin_count);
+  const unsigned int max_len = (unsigned int)p.max_path_length;
+  unsigned int zombies = 0, traced = 0;
+  const unsigned int stride = gridDim.x * blockDim.x;
+  for (unsigned int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += stride) {
+    const unsigned int j = base + lane_id();
+    bool push = false;
+    double qox = 0, qoy = 0, qoz = 0, qdx = 0, qdy = 0, qdz = 0;
+    uint32_t item = 0;
+    if (j < n) {
+      traced++;
+      const double2 *qp = reinterpret_cast<const double2 *>(qin + j);
+      const double2 a = __ldg(qp), b = __ldg(qp + 1), c = __ldg(qp + 2), d3 = __ldg(qp + 3);
+      const double ox = a.x, oy = a.y, oz = b.x, dx = b.y, dy = c.x, dz = c.y;
+      item = (uint32_t)(unsigned long long)__double_as_longlong(d3.y);
+      PathState *sp = states + item;
+      const uint4 s0 = *reinterpret_cast<const uint4 *>(sp);
+      const double2 s1 = reinterpret_cast<const double2 *>(sp)[1];
+      uint32_t cur_mat = reinterpret_cast<const uint4 *>(sp)[2].x;
+      Xorshift128 rng{s0.x, s0.y, s0.z, s0.w};
+      double thr = s1.x, radiance = s1.y;
+
+      double t, u, v;
+      uint32_t face, mat;
+      load_hit(hits + j, t, u, v, face, mat);
+      bool hit = face != 0xFFFFFFFFu;
+      double nx = 0.0, ny = 0.0, nz = 0.0;
+      if (hit) {
+        IsectD d;
+        build_intersection(sc, ox, oy, oz, dx, dy, dz, t, u, v, face, d);
+        nx = d.nx, ny = d.ny, nz = d.nz;
+        cur_mat = mat;
+      }
+      if (p.use_plane) hit |= plane_intersect(p.plane, ox, oy, oz, dx, dy, dz, t, nx, ny, nz, cur_mat);
+      if (!hit) { // escaped: this segment and every later one adds throughput*0.5/pathLength
+        radiance += thr * 0.5 / (double)len;
+        zombies += zombie_tail(len, max_len, cur_mat, thr, radiance);
+        contrib[item] = (float)radiance;
+      } else if (len >= max_len) {
+        contrib[item] = (float)radiance;
+      } else {
+        const double hx = ox + t * dx, hy = oy + t * dy, hz = oz + t * dz;
+        bounce_ray(rng, dx, dy, dz, hx, hy, hz, nx, ny, nz, qox, qoy, qoz, qdx, qdy, qdz);
+        if (cur_mat != 0xFFFFFFFFu) thr *= 0.5;
+        save_state(sp, rng, thr, radiance, cur_mat);
+        push = true;
+      }
+    }
+    const uint32_t slot = queue_slot(qout_count, push);
+    if (push) store_qray(qout + slot, qox, qoy, qoz, qdx, qdy, qdz, DBL_MAX, item, 0.f);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    traced += __shfl_down_sync(kFullMask, traced, o);
+    zombies += __shfl_down_sync(kFullMask, zombies, o);
+  }
+  if (lane_id() == 0) {
+    if (traced) atomicAdd(&stats[1], (unsigned long long)traced);
+    if (zombies) atomicAdd(&stats[3], (unsigned long long)zombies);
+  }
+}
+
+// One thread per (tile, lane) pixel: the batch's samples are added in pass order, float += float
+// (AccumImage, main_sdl.cc:138-143), then image / count are written as `mode` says (kernels.h).
+__global__ void __launch_bounds__(256)
+    k_resolve(const __grid_constant__ FrameMap m, uint32_t tiles, int mode, const float *__restrict__ contrib,
+              float *__restrict__ image, int *__restrict__ count) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t tile = g >> 5, lane = g & 31u;
+  if (tile >= tiles) return;
+  int x, y, rl;
+  uint32_t pass;
+  if (!item_pixel(m, (tile * m.passes) * 32u + lane, x, y, rl, pass)) return;
+  const size_t pix = pixel_slot(m, x, y, rl);
+  float ar = 0.f, ag = 0.f, ab = 0.f;
+  if (mode == 1) ar = image[3 * pix + 0], ag = image[3 * pix + 1], ab = image[3 * pix + 2];
+  const float *c = contrib + (size_t)tile * m.passes * 32u + lane;
+  for (uint32_t s = 0; s < m.passes; s++) {
+    const float r = c[(size_t)s * 32u];
+    if (mode != 0) ar += r, ag += r, ab += r;
+    else ar = ag = ab = r;
+  }
+  image[3 * pix + 0] = ar, image[3 * pix + 1] = ag, image[3 * pix + 2] = ab;
+  if (mode == 2) count[pix] = (int)m.passes;
+  else count[pix] += (int)m.passes;
+}
+
+// stats of a batch -> the caller's accumulated stats (shadow rays traced = fill of the shadow queue)
+__global__ void k_add_stats(const unsigned long long *__restrict__ batch, const unsigned int *__restrict__ shadow_count,
+                            unsigned long long *__restrict__ total) {
+  if (threadIdx.x < 4) total[threadIdx.x] += batch[threadIdx.x];
+  if (threadIdx.x == 2 && shadow_count) total[2] += *shadow_count;
 }
 
 // ---------------------------------------------------------------------------
@@ -510,24 +368,101 @@ __global__ void __launch_bounds__(kBlock)
 int g_num_sms = 0;
 int g_launches = 0;
 
-int persistent_grid(const void *kernel, size_t smem) {
+int num_sms() {
   if (g_num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
-  int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem);
-  if (per_sm < 1) per_sm = 1;
-  return g_num_sms * per_sm; // a whole number of CTAs per SM: one persistent wave
+  return g_num_sms;
 }
 
-constexpr size_t kStackSmem = (size_t)kSmemStack * kBlock * sizeof(uint4);
-
-template <typename K> cudaError_t prepare(K kernel) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStackSmem);
+int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v ? atoi(v) : dflt;
 }
+
+// One persistent wave: a whole number of CTAs per SM.
+template <class IO, bool F32, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int POLICY, int S, int MINB, unsigned CHUNK>
+cudaError_t launch_sm(const SceneView &sc, const IO &io, size_t n, const unsigned int *n_dev,
+                      unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
+  auto k = k_trace_sm<IO, F32, CAP, ANYHIT, COUNT, REFILL_MIN, POLICY, S, MINB, CHUNK>;
+  const size_t smem = (size_t)S * kBlock * sizeof(uint4);
+  static int grid = 0; // per instantiation
+  if (grid == 0) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kBlock, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    grid = num_sms() * per_sm;
+  }
+  k<<<grid, kBlock, smem, s>>>(sc, io, (unsigned long long)n, n_dev, work, counters);
+  g_launches++;
+  return cudaGetLastError();
+}
+
+// Picks the kernel instantiation: production parameters, or (development builds, -DMB200_DEV_VARIANTS)
+// the A/B variants selected with MB200_TRACE_POLICY / MB200_TRACE_OCC / MB200_TRACE_CHUNK.
+template <class IO, bool F32, int CAP, bool ANYHIT, bool COUNT>
+cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const unsigned int *n_dev,
+                              unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
+#define MB200_SM(R, P, S, B, C) launch_sm<IO, F32, CAP, ANYHIT, COUNT, R, P, S, B, C>(sc, io, n, n_dev, work, counters, s)
+#ifdef MB200_DEV_VARIANTS
+  if (!COUNT && CAP <= 64) {
+    static const int policy = env_int("MB200_TRACE_POLICY", kPolicy), occ = env_int("MB200_TRACE_OCC", kMinBlocks),
+                     chunk = env_int("MB200_TRACE_CHUNK", (int)kChunk), refill = env_int("MB200_TRACE_REFILL", kRefillMin);
+    if (policy == 0) return MB200_SM(4, 0, 16, 5, 32);
+    if (occ == 4) return MB200_SM(4, 2, 16, 4, 32);
+    if (occ == 6) return MB200_SM(4, 2, 16, 6, 32);
+    if (chunk == 64) return MB200_SM(4, 2, 16, 5, 64);
+    if (refill == 1) return MB200_SM(1, 2, 16, 5, 32);
+    if (refill == 8) return MB200_SM(8, 2, 16, 5, 32);
+  }
+#endif
+  return MB200_SM(kRefillMin, kPolicy, kSmemStack, kMinBlocks, kChunk);
+#undef MB200_SM
+}
+
+// dispatch on the scene's triangle record kind and on the stack capacity the tree needs
+template <class IO, bool ANYHIT>
+cudaError_t launch_trace(const SceneView &sc, int stack_cap, const IO &io, size_t n, const unsigned int *n_dev,
+                         unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
+  if (counters) {
+    if (sc.tri_f32)
+      return stack_cap <= 64 ? launch_sm_variant<IO, true, 64, ANYHIT, true>(sc, io, n, n_dev, work, counters, s)
+                             : launch_sm_variant<IO, true, 512, ANYHIT, true>(sc, io, n, n_dev, work, counters, s);
+    return stack_cap <= 64 ? launch_sm_variant<IO, false, 64, ANYHIT, true>(sc, io, n, n_dev, work, counters, s)
+                           : launch_sm_variant<IO, false, 512, ANYHIT, true>(sc, io, n, n_dev, work, counters, s);
+  }
+  if (sc.tri_f32)
+    return stack_cap <= 64 ? launch_sm_variant<IO, true, 64, ANYHIT, false>(sc, io, n, n_dev, work, counters, s)
+                           : launch_sm_variant<IO, true, 512, ANYHIT, false>(sc, io, n, n_dev, work, counters, s);
+  return stack_cap <= 64 ? launch_sm_variant<IO, false, 64, ANYHIT, false>(sc, io, n, n_dev, work, counters, s)
+                         : launch_sm_variant<IO, false, 512, ANYHIT, false>(sc, io, n, n_dev, work, counters, s);
+}
+
+// frame-internal traces never count
+template <class IO, bool ANYHIT>
+cudaError_t launch_trace_nocount(const SceneView &sc, int stack_cap, const IO &io, size_t n, const unsigned int *n_dev,
+                                 unsigned long long *work, cudaStream_t s) {
+  if (sc.tri_f32)
+    return stack_cap <= 64 ? launch_sm_variant<IO, true, 64, ANYHIT, false>(sc, io, n, n_dev, work, nullptr, s)
+                           : launch_sm_variant<IO, true, 512, ANYHIT, false>(sc, io, n, n_dev, work, nullptr, s);
+  return stack_cap <= 64 ? launch_sm_variant<IO, false, 64, ANYHIT, false>(sc, io, n, n_dev, work, nullptr, s)
+                         : launch_sm_variant<IO, false, 512, ANYHIT, false>(sc, io, n, n_dev, work, nullptr, s);
+}
+
+int flat_grid(size_t n, int block) {
+  const size_t want = (n + block - 1) / block, cap = (size_t)num_sms() * 8;
+  return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 } // namespace
 
@@ -537,54 +472,13 @@ int band_rows_owned(int rows, int band_rows, int count, int index) {
   return band_local_rows(rows, band_rows, count, index);
 }
 
-template <bool F32, int CAP>
-static cudaError_t do_trace_closest(const SceneView &sc, const mb200_ray *rays, size_t n, mb200_hit *hits,
-                                    unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
-  cudaError_t e;
-  if (counters) {
-    auto k = k_trace_closest<F32, CAP, true>;
-    if ((e = prepare(k)) != cudaSuccess) return e;
-    k<<<persistent_grid((const void *)k, kStackSmem), kBlock, kStackSmem, s>>>(sc, rays, n, hits, work, counters);
-  } else {
-    auto k = k_trace_closest<F32, CAP, false>;
-    if ((e = prepare(k)) != cudaSuccess) return e;
-    k<<<persistent_grid((const void *)k, kStackSmem), kBlock, kStackSmem, s>>>(sc, rays, n, hits, work, counters);
-  }
-  g_launches++;
-  return cudaGetLastError();
-}
-
 cudaError_t launch_trace_closest(const SceneView &sc, int stack_cap, const mb200_ray *rays, size_t n,
                                  mb200_hit *hits, unsigned long long *work, unsigned long long *counters,
                                  cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(work, 0, sizeof(unsigned long long), s);
   if (e != cudaSuccess) return e;
-  if (sc.tri_f32) {
-    return stack_cap <= 64 ? do_trace_closest<true, 64>(sc, rays, n, hits, work, counters, s)
-                           : do_trace_closest<true, 512>(sc, rays, n, hits, work, counters, s);
-  }
-  return stack_cap <= 64 ? do_trace_closest<false, 64>(sc, rays, n, hits, work, counters, s)
-                         : do_trace_closest<false, 512>(sc, rays, n, hits, work, counters, s);
-}
-
-template <bool F32, int CAP>
-static cudaError_t do_trace_occluded(const SceneView &sc, const mb200_ray *rays, const double *tmax, size_t n,
-                                     unsigned char *occ, unsigned long long *work, unsigned long long *counters,
-                                     cudaStream_t s) {
-  cudaError_t e;
-  if (counters) {
-    auto k = k_trace_occluded<F32, CAP, true>;
-    if ((e = prepare(k)) != cudaSuccess) return e;
-    k<<<persistent_grid((const void *)k, kStackSmem), kBlock, kStackSmem, s>>>(sc, rays, tmax, n, occ, work,
-                                                                               counters);
-  } else {
-    auto k = k_trace_occluded<F32, CAP, false>;
-    if ((e = prepare(k)) != cudaSuccess) return e;
-    k<<<persistent_grid((const void *)k, kStackSmem), kBlock, kStackSmem, s>>>(sc, rays, tmax, n, occ, work,
-                                                                               counters);
-  }
-  g_launches++;
-  return cudaGetLastError();
+  const IOClosest io{rays, hits};
+  return launch_trace<IOClosest, false>(sc, stack_cap, io, n, nullptr, work, counters, s);
 }
 
 cudaError_t launch_trace_occluded(const SceneView &sc, int stack_cap, const mb200_ray *rays, const double *tmax,
@@ -592,69 +486,22 @@ cudaError_t launch_trace_occluded(const SceneView &sc, int stack_cap, const mb20
                                   unsigned long long *counters, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(work, 0, sizeof(unsigned long long), s);
   if (e != cudaSuccess) return e;
-  if (sc.tri_f32) {
-    return stack_cap <= 64 ? do_trace_occluded<true, 64>(sc, rays, tmax, n, occ, work, counters, s)
-                           : do_trace_occluded<true, 512>(sc, rays, tmax, n, occ, work, counters, s);
-  }
-  return stack_cap <= 64 ? do_trace_occluded<false, 64>(sc, rays, tmax, n, occ, work, counters, s)
-                         : do_trace_occluded<false, 512>(sc, rays, tmax, n, occ, work, counters, s);
+  const IOOccluded io{rays, tmax, occ};
+  return launch_trace<IOOccluded, true>(sc, stack_cap, io, n, nullptr, work, counters, s);
 }
 
-template <bool F32, int CAP>
-static cudaError_t do_trace_full(const SceneView &sc, const mb200_ray *rays, size_t n, mb200_isect *isects,
-                                 unsigned char *mask, unsigned long long *work, cudaStream_t s) {
-  auto k = k_trace_closest_full<F32, CAP>;
-  cudaError_t e = prepare(k);
-  if (e != cudaSuccess) return e;
-  k<<<persistent_grid((const void *)k, kStackSmem), kBlock, kStackSmem, s>>>(sc, rays, n, isects, mask, work);
+cudaError_t launch_build_isects(const SceneView &sc, const mb200_ray *rays, const mb200_hit *hits, size_t n,
+                                mb200_isect *isects, unsigned char *mask, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  k_build_isects<<<flat_grid(n, 256), 256, 0, s>>>(sc, rays, hits, n, isects, mask);
   g_launches++;
   return cudaGetLastError();
-}
-
-cudaError_t launch_trace_closest_full(const SceneView &sc, int stack_cap, const mb200_ray *rays, size_t n,
-                                      mb200_isect *isects, unsigned char *mask, unsigned long long *work,
-                                      cudaStream_t s) {
-  cudaError_t e = cudaMemsetAsync(work, 0, sizeof(unsigned long long), s);
-  if (e != cudaSuccess) return e;
-  if (sc.tri_f32) {
-    return stack_cap <= 64 ? do_trace_full<true, 64>(sc, rays, n, isects, mask, work, s)
-                           : do_trace_full<true, 512>(sc, rays, n, isects, mask, work, s);
-  }
-  return stack_cap <= 64 ? do_trace_full<false, 64>(sc, rays, n, isects, mask, work, s)
-                         : do_trace_full<false, 512>(sc, rays, n, isects, mask, work, s);
-}
-
-template <bool F32, int CAP>
-static cudaError_t do_render(const SceneView &sc, const mb200_render_params &p, int num_passes, int accumulate,
-                             float *image, int *count, unsigned long long *work, unsigned long long *stats,
-                             cudaStream_t s) {
-  auto k = k_render<F32, CAP>;
-  cudaError_t e = prepare(k);
-  if (e != cudaSuccess) return e;
-  k<<<persistent_grid((const void *)k, kStackSmem), kBlock, kStackSmem, s>>>(sc, p, num_passes, accumulate, image,
-                                                                             count, work, stats);
-  g_launches++;
-  return cudaGetLastError();
-}
-
-cudaError_t launch_render(const SceneView &sc, int stack_cap, const mb200_render_params &p, int num_passes,
-                          int accumulate, float *image, int *count, unsigned long long *work,
-                          unsigned long long *stats, cudaStream_t s) {
-  cudaError_t e = cudaMemsetAsync(work, 0, sizeof(unsigned long long), s);
-  if (e != cudaSuccess) return e;
-  if (sc.tri_f32) {
-    return stack_cap <= 64 ? do_render<true, 64>(sc, p, num_passes, accumulate, image, count, work, stats, s)
-                           : do_render<true, 512>(sc, p, num_passes, accumulate, image, count, work, stats, s);
-  }
-  return stack_cap <= 64 ? do_render<false, 64>(sc, p, num_passes, accumulate, image, count, work, stats, s)
-                         : do_render<false, 512>(sc, p, num_passes, accumulate, image, count, work, stats, s);
 }
 
 cudaError_t launch_generate_rays(const mb200_camera_frame &f, const double *px, const double *py, size_t n,
                                  mb200_ray *rays, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
-  const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-  k_generate_rays<<<grid, 256, 0, s>>>(f, px, py, n, rays);
+  k_generate_rays<<<flat_grid(n, 256), 256, 0, s>>>(f, px, py, n, rays);
   g_launches++;
   return cudaGetLastError();
 }
@@ -663,10 +510,119 @@ cudaError_t launch_generate_grid(const mb200_camera_frame &f, int x0, int y0, in
                                  cudaStream_t s) {
   const size_t n = (size_t)w * h;
   if (n == 0) return cudaSuccess;
-  const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-  k_generate_grid<<<grid, 256, 0, s>>>(f, x0, y0, w, h, rays);
+  k_generate_grid<<<flat_grid(n, 256), 256, 0, s>>>(f, x0, y0, w, h, rays);
   g_launches++;
   return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// frame scratch + the wavefront driver
+// ---------------------------------------------------------------------------
+cudaError_t frame_scratch_reserve(FrameScratch &fs, size_t bytes, cudaStream_t s) {
+  if (fs.bytes >= bytes) return cudaSuccess;
+  if (fs.base) {
+    cudaError_t e = cudaStreamSynchronize(s); // earlier work may still use the old block
+    if (e != cudaSuccess) return e;
+    cudaFree(fs.base);
+    fs.base = nullptr, fs.bytes = 0;
+  }
+  const size_t cap = bytes + bytes / 8;
+  cudaError_t e = cudaMalloc(&fs.base, cap);
+  if (e != cudaSuccess) {
+    fs.base = nullptr;
+    return e;
+  }
+  fs.bytes = cap;
+  return cudaSuccess;
+}
+
+void frame_scratch_release(FrameScratch &fs) {
+  if (fs.base) cudaFree(fs.base);
+  fs.base = nullptr, fs.bytes = 0;
+}
+
+// Work items per batch: bounds the scratch (100 B/item for primary+shadow, 212 B/item for PathTrace).
+static size_t batch_item_budget() {
+  static const size_t v = (size_t)env_int("MB200_FRAME_BATCH_ITEMS", 1 << 24);
+  return v < 32 ? 32 : v;
+}
+
+cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_params &p, int num_passes, int mode,
+                         float *image, int *count, FrameScratch &scratch, unsigned long long *stats, cudaStream_t s) {
+  const FrameMap m0 = make_frame_map(p, p.pass, 1);
+  const size_t tiles = frame_map_tiles(m0);
+  if (tiles == 0 || num_passes < 1) return cudaSuccess;
+  if (tiles * 32 > 0xFFFFFFE0ull) return cudaErrorInvalidValue;
+  const bool path = p.shader == MB200_SHADER_PATHTRACE && p.max_path_length > 1;
+  const bool shadow = p.shader == MB200_SHADER_PRIMARY_SHADOW;
+
+  size_t per_batch = batch_item_budget() / (tiles * 32);
+  if (per_batch < 1) per_batch = 1;
+  if (per_batch > (size_t)num_passes) per_batch = (size_t)num_passes;
+  while (per_batch > 1 && tiles * 32 * per_batch > 0xFFFFFFE0ull) per_batch--;
+  const size_t max_items = tiles * 32 * per_batch;
+
+  // scratch carve-up
+  const size_t n_traces = path ? (size_t)p.max_path_length : 2;
+  const size_t ctl_bytes = align_up(sizeof(unsigned long long) * (4 + n_traces) + sizeof(unsigned int) * (n_traces + 1), 256);
+  const size_t hits_bytes = align_up(max_items * sizeof(mb200_hit), 256);
+  const size_t contrib_bytes = align_up(max_items * sizeof(float), 256);
+  const size_t queue_bytes = (path || shadow) ? align_up(max_items * sizeof(QRay), 256) : 0;
+  const size_t state_bytes = path ? align_up(max_items * sizeof(PathState), 256) : 0;
+  const size_t total = ctl_bytes + hits_bytes + contrib_bytes + queue_bytes * (path ? 2 : 1) + state_bytes;
+  cudaError_t e = frame_scratch_reserve(scratch, total, s);
+  if (e != cudaSuccess) return e;
+  char *base = reinterpret_cast<char *>(scratch.base);
+  unsigned long long *bstats = reinterpret_cast<unsigned long long *>(base);           // [4]
+  unsigned long long *work = bstats + 4;                                               // [n_traces]
+  unsigned int *qcount = reinterpret_cast<unsigned int *>(work + n_traces);            // [n_traces + 1]
+  mb200_hit *hits = reinterpret_cast<mb200_hit *>(base + ctl_bytes);
+  float *contrib = reinterpret_cast<float *>(base + ctl_bytes + hits_bytes);
+  QRay *queue[2] = {reinterpret_cast<QRay *>(base + ctl_bytes + hits_bytes + contrib_bytes), nullptr};
+  queue[1] = path ? reinterpret_cast<QRay *>(reinterpret_cast<char *>(queue[0]) + queue_bytes) : queue[0];
+  PathState *states = path ? reinterpret_cast<PathState *>(reinterpret_cast<char *>(queue[0]) + 2 * queue_bytes) : nullptr;
+
+  int done = 0;
+  while (done < num_passes) {
+    const int nb = (int)((size_t)(num_passes - done) < per_batch ? (size_t)(num_passes - done) : per_batch);
+    const FrameMap m = make_frame_map(p, p.pass + (uint32_t)done, (uint32_t)nb);
+    const uint32_t items = (uint32_t)(tiles * 32 * (size_t)nb);
+    if ((e = cudaMemsetAsync(base, 0, ctl_bytes, s)) != cudaSuccess) return e;
+
+    // camera rays: K1 fused into K2
+    const IOCamera cam{p, m, hits};
+    if ((e = launch_trace_nocount<IOCamera, false>(sc, stack_cap, cam, items, nullptr, work + 0, s)) != cudaSuccess) return e;
+    k_shade_primary<<<(items + 255) / 256, 256, 0, s>>>(sc, p, m, items, hits, contrib, queue[0], qcount + 0, states, bstats);
+    g_launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+
+    if (shadow) {
+      const IOQueueShadow io{queue[0], contrib};
+      if ((e = launch_trace_nocount<IOQueueShadow, true>(sc, stack_cap, io, 0, qcount + 0, work + 1, s)) != cudaSuccess) return e;
+    } else if (path) {
+      for (int len = 2; len <= p.max_path_length; len++) {
+        const int qi = len & 1; // segment `len` reads queue[qi], writes queue[qi ^ 1]
+        const IOQueueClosest io{queue[qi], hits};
+        if ((e = launch_trace_nocount<IOQueueClosest, false>(sc, stack_cap, io, 0, qcount + (len - 2), work + (len - 1), s)) != cudaSuccess) return e;
+        k_shade_bounce<<<num_sms() * 8, 256, 0, s>>>(sc, p, (unsigned int)len, queue[qi], qcount + (len - 2), hits, queue[qi ^ 1],
+                                                     qcount + (len - 1), states, contrib, bstats);
+        g_launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      }
+    }
+
+    int bmode = mode;
+    if (mode == 2 && done > 0) bmode = 1;
+    k_resolve<<<(unsigned)((tiles * 32 + 255) / 256), 256, 0, s>>>(m, (uint32_t)tiles, bmode, contrib, image, count);
+    g_launches++;
+    if (stats) {
+      k_add_stats<<<1, 32, 0, s>>>(bstats, shadow ? qcount : nullptr, stats);
+      g_launches++;
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    done += nb;
+  }
+  return cudaSuccess;
 }
 
 } // namespace mb200

@@ -15,21 +15,35 @@ namespace mb200 {
 cudaError_t launch_trace_closest(const SceneView &sc, int stack_cap, const mb200_ray *rays, size_t n,
                                  mb200_hit *hits, unsigned long long *work, unsigned long long *counters,
                                  cudaStream_t s);
-cudaError_t launch_trace_closest_full(const SceneView &sc, int stack_cap, const mb200_ray *rays, size_t n,
-                                      mb200_isect *isects, unsigned char *mask, unsigned long long *work,
-                                      cudaStream_t s);
 cudaError_t launch_trace_occluded(const SceneView &sc, int stack_cap, const mb200_ray *rays, const double *tmax,
                                   size_t n, unsigned char *occluded, unsigned long long *work,
                                   unsigned long long *counters, cudaStream_t s);
-// stats: unsigned long long[4] primary, bounce, shadow, zombie (accumulated).
-// accumulate (mode): 0 = overwrite image / count += passes, 1 = accumulate both, 2 = overwrite both.
-cudaError_t launch_render(const SceneView &sc, int stack_cap, const mb200_render_params &p, int num_passes,
-                          int accumulate, float *image, int *count, unsigned long long *work,
-                          unsigned long long *stats, cudaStream_t s);
+// K3: BuildIntersection for every ray from its 32-byte hit record (mask nullable).
+cudaError_t launch_build_isects(const SceneView &sc, const mb200_ray *rays, const mb200_hit *hits, size_t n,
+                                mb200_isect *isects, unsigned char *mask, cudaStream_t s);
 cudaError_t launch_generate_rays(const mb200_camera_frame &f, const double *px, const double *py, size_t n,
                                  mb200_ray *rays, cudaStream_t s);
 cudaError_t launch_generate_grid(const mb200_camera_frame &f, int x0, int y0, int w, int h, mb200_ray *rays,
                                  cudaStream_t s);
+
+// Device scratch of the frame pipeline (hit records, ray queues, per-sample contributions, path state,
+// counters); owned by the scene, grown on demand by launch_frame.
+struct FrameScratch {
+  void *base = nullptr;
+  size_t bytes = 0;
+};
+cudaError_t frame_scratch_reserve(FrameScratch &fs, size_t bytes, cudaStream_t s);
+void frame_scratch_release(FrameScratch &fs);
+
+// One frame of num_passes samples per pixel (wavefront: primary trace -> shade -> secondary trace ... ->
+// resolve), batched so that a batch's buffers stay within a fixed budget.
+// mode 0: image = last pass, count += passes (one pass: render.cc:673-679)
+// mode 1: image += passes, count += passes    (AccumImage, main_sdl.cc:138-143)
+// mode 2: image = sum of passes, count = passes (fresh frame; nothing read)
+// stats: device unsigned long long[4] primary, bounce, shadow, zombie (accumulated).
+cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_params &p, int num_passes, int mode,
+                         float *image, int *count, FrameScratch &scratch, unsigned long long *stats, cudaStream_t s);
+
 // Rows owned by one band index (see mb200_render_params::band_rows).
 int band_rows_owned(int rows, int band_rows, int count, int index);
 // Number of kernel launches issued by this library in this process (bench.py's gpu_launches).

@@ -20,7 +20,10 @@
 //         (always true for OBJ input with scene_scale 1: positions are parsed as
 //         float, tiny_obj_loader.cc:696-697); values are widened to double
 //         before any arithmetic, so results are unchanged.
-//     f64 variant, 80 B : p0,p1,p2 as doubles | faceID, materialID
+//     f64 variant, 80 B : p0, e1 = p1-p0, e2 = p2-p0 as doubles | faceID, materialID
+//         the edges are rounded on the host exactly as TriangleIsect rounds them
+//         (one IEEE double subtraction each, bvh_accel.cc:600-603), which removes six
+//         subtractions (and, against the f32 variant, nine conversions) per test.
 //   -> one triangle test = 3 (or 5) 16-byte vector loads, no indirection.
 //
 // The original faces/vertices/normals/uvs arrays are also resident (verbatim)
@@ -54,11 +57,37 @@ struct alignas(16) TriRecordF32 {
 static_assert(sizeof(TriRecordF32) == 48, "TriRecordF32");
 
 struct alignas(16) TriRecordF64 {
-  double p[9];
+  double p0[3];
+  double e1[3]; // p1 - p0, rounded as TriangleIsect rounds it (bvh_accel.cc:600-601)
+  double e2[3]; // p2 - p0
   uint32_t face;
   uint32_t mat;
 };
 static_assert(sizeof(TriRecordF64) == 80, "TriRecordF64");
+
+// ---- wavefront buffers of the frame kernels (kernels.cu) ------------------------------------------------
+// A queued secondary ray (shadow ray or path continuation): 64 B = four 16-byte vector loads.
+//   item  = the work item (sample of a pixel) the ray belongs to
+//   value = shadow rays: the radiance the sample receives if the ray is NOT occluded
+struct alignas(16) QRay {
+  double org[3];
+  double dir[3];
+  double tmax;
+  uint32_t item;
+  float value;
+};
+static_assert(sizeof(QRay) == 64, "QRay");
+
+// Per-sample state of PathTrace (render.cc:381-456) between wavefronts.  Radiance and throughput are
+// scalars: every Material the reference can produce is the grey default (scene.h:58-65), so r = g = b.
+struct alignas(16) PathState {
+  uint32_t rng[4];  // xorshift128 state (render.cc:137-168)
+  double throughput;
+  double radiance;
+  uint32_t cur_mat; // Intersection::materialID as PathTrace's isect variable holds it (stale after a miss)
+  uint32_t pad_[3];
+};
+static_assert(sizeof(PathState) == 48, "PathState");
 
 // Everything a kernel needs, passed by value as a __grid_constant__ parameter.
 struct SceneView {

@@ -5,6 +5,7 @@
 #include "scene.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace mb200 {
@@ -100,6 +101,9 @@ int relayout_bvh(Relayout &out, const double *vertices, size_t nverts, const uin
 
   // ---- triangle records in indices_ order
   out.f32 = all_float_exact(vertices, 3 * nverts);
+  if (const char *fmt = getenv("MB200_TRI_FORMAT")) { // development knob: "f64" forces the 80-byte edge records
+    if (!strcmp(fmt, "f64")) out.f32 = false;
+  }
   if (out.f32) {
     out.tris32.resize(nindices);
     for (size_t i = 0; i < nindices; i++) {
@@ -118,10 +122,10 @@ int relayout_bvh(Relayout &out, const double *vertices, size_t nverts, const uin
     for (size_t i = 0; i < nindices; i++) {
       const uint32_t f = indices[i];
       TriRecordF64 &t = out.tris64[i];
-      for (int j = 0; j < 3; j++) {
-        const double *a = vertices + 3 * (size_t)faces[3 * (size_t)f + j];
-        for (int k = 0; k < 3; k++) t.p[3 * j + k] = a[k];
-      }
+      const double *a = vertices + 3 * (size_t)faces[3 * (size_t)f + 0];
+      const double *b = vertices + 3 * (size_t)faces[3 * (size_t)f + 1];
+      const double *c = vertices + 3 * (size_t)faces[3 * (size_t)f + 2];
+      for (int k = 0; k < 3; k++) t.p0[k] = a[k], t.e1[k] = b[k] - a[k], t.e2[k] = c[k] - a[k];
       t.face = f;
       t.mat = material_ids ? material_ids[f] : 0xFFFFFFFFu;
     }
@@ -259,6 +263,8 @@ void scene_destroy(mb200_scene *s) {
     if (st->pinned) cudaFreeHost(st->pinned);
     if (st->dev) cudaFree(st->dev);
   }
+  frame_scratch_release(s->frame_scratch);
+  frame_scratch_release(s->hit_scratch);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }

@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 
+#include "kernels.h"
 #include "layout.h"
 #include "mallie_b200.h"
 
@@ -31,6 +32,9 @@ struct mb200_scene {
     size_t cap = 0;
   };
   Staging in0, in1, out0, out1;
+
+  // device scratch: the frame wavefront's buffers, and hit records of mb200_trace_closest_full
+  mb200::FrameScratch frame_scratch, hit_scratch;
 };
 
 namespace mb200 {

@@ -1,24 +1,24 @@
-// traverse.cuh -- device-side restatement of BVHAccel::Traverse and its helpers
-// (bvh_accel.cc:546-844) for sm_100a.  Compiled with -fmad=false: every multiply
-// and add below rounds separately, in the reference's evaluation order, so the
-// hit record is bit-identical to the CPU reference.
+// traverse.cuh -- device-side primitives of BVHAccel::Traverse (bvh_accel.cc:546-844) for sm_100a:
+// ray set-up, the slab test, the triangle test, triangle-record loaders and the traversal stack.
+// Compiled with -fmad=false: every multiply and add below rounds separately, in the reference's
+// evaluation order, so hit records are bit-identical to the CPU reference.  The traversal loop
+// itself is the state machine in trace_sm.cuh.
 //
-// Equivalence with the reference loop (bvh_accel.cc:805-834), which pops a node,
-// box-tests it against the *current* hitT, and then pushes far/near children:
-//   * here both child boxes are tested when their parent is visited (they sit in
-//     the parent's 128-byte PairNode).  The three slab conditions
-//       (tmax > 0) && (tmin <= tmax) && (tmin <= hitT)
+// Equivalence of the PairNode walk with the reference loop (bvh_accel.cc:805-834), which pops a
+// node, box-tests it against the *current* hitT, and then pushes far/near children:
+//   * here both child boxes are tested when their parent is visited (they sit in the parent's
+//     128-byte PairNode).  The three slab conditions
+//         (tmax > 0) && (tmin <= tmax) && (tmin <= hitT)
 //     are evaluated with the same arithmetic; only the last one depends on hitT.
-//   * hitT never increases, so a child that fails (tmin <= hitT) now also fails it
-//     at the reference's later pop time: dropping it immediately is exact.
-//   * a child that passes is either continued with immediately (near child, hitT
-//     unchanged => the reference's pop-time test passes too) or pushed together
-//     with its tmin; when it is popped the remaining condition (tmin <= hitT_now)
-//     is re-checked -- exactly the reference's pop-time decision.
-//   * near/far order is sign[axis] as in bvh_accel.cc:818-823; triangles are
-//     stored in indices_ order, so "last accepted among equal t wins" is kept.
-// Consequently the sequence of leaves visited, triangles tested and the number
-// of box tests (1 + 2 per accepted branch) are those of the reference.
+//   * hitT never increases, so a child that fails (tmin <= hitT) now also fails it at the
+//     reference's later pop time: dropping it immediately is exact.
+//   * a child that passes is either continued with immediately (near child, hitT unchanged => the
+//     reference's pop-time test passes too) or pushed together with its tmin; when it is popped
+//     the remaining condition (tmin <= hitT_now) is re-checked -- the reference's pop-time decision.
+//   * near/far order is sign[axis] as in bvh_accel.cc:818-823; triangles are stored in indices_
+//     order, so "last accepted among equal t wins" is kept.
+// Consequently the sequence of leaves visited, triangles tested and the number of box tests
+// (1 + 2 per accepted branch) are those of the reference.
 #ifndef MALLIE_B200_TRAVERSE_CUH_
 #define MALLIE_B200_TRAVERSE_CUH_
 
@@ -76,28 +76,66 @@ __device__ __forceinline__ bool slab_test(const double b0, const double b1, cons
   return (tmax > 0.0) && (tmin <= tmax) && (tmin <= max_t);
 }
 
+struct HitD {
+  double t, u, v;
+  uint32_t face, mat;
+};
+
+// ---- triangle records (layout.h) ----------------------------------------------------------------
+// Both record kinds are presented to the triangle test as p0 plus the two edges e1 = p1 - p0,
+// e2 = p2 - p0.  The f64 record stores the edges, rounded once on the host exactly as TriangleIsect
+// rounds them (one IEEE double subtraction each, bvh_accel.cc:600-603); the f32 record stores the
+// float-exact vertices and the edges are formed here after widening to double (same result).
+struct TriEdges {
+  double p0x, p0y, p0z, e1x, e1y, e1z, e2x, e2y, e2z;
+  uint32_t face, mat;
+};
+
+template <bool F32> __device__ __forceinline__ TriEdges load_tri_edges(const void *tris, uint32_t i);
+
+template <> __device__ __forceinline__ TriEdges load_tri_edges<true>(const void *tris, uint32_t i) {
+  const float4 *p = reinterpret_cast<const float4 *>(reinterpret_cast<const TriRecordF32 *>(tris) + i);
+  const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+  TriEdges t;
+  t.p0x = (double)a.x, t.p0y = (double)a.y, t.p0z = (double)a.z;
+  t.e1x = (double)b.x - t.p0x, t.e1y = (double)b.y - t.p0y, t.e1z = (double)b.z - t.p0z;
+  t.e2x = (double)c.x - t.p0x, t.e2y = (double)c.y - t.p0y, t.e2z = (double)c.z - t.p0z;
+  t.face = __float_as_uint(a.w);
+  t.mat = __float_as_uint(b.w);
+  return t;
+}
+
+template <> __device__ __forceinline__ TriEdges load_tri_edges<false>(const void *tris, uint32_t i) {
+  const double2 *p = reinterpret_cast<const double2 *>(reinterpret_cast<const TriRecordF64 *>(tris) + i);
+  const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4);
+  TriEdges t;
+  t.p0x = a.x, t.p0y = a.y, t.p0z = b.x;
+  t.e1x = b.y, t.e1y = c.x, t.e1z = c.y;
+  t.e2x = d.x, t.e2y = d.y, t.e2z = e.x;
+  const unsigned long long w = (unsigned long long)__double_as_longlong(e.y);
+  t.face = (uint32_t)(w & 0xFFFFFFFFull);
+  t.mat = (uint32_t)(w >> 32);
+  return t;
+}
+
 // TriangleIsect (bvh_accel.cc:595-638): Moeller-Trumbore, no culling.
-__device__ __forceinline__ bool tri_test(double &t_io, double &u_out, double &v_out, const double p0x,
-                                         const double p0y, const double p0z, const double p1x, const double p1y,
-                                         const double p1z, const double p2x, const double p2y, const double p2z,
-                                         const RayD &r) {
-  const double e1x = p1x - p0x, e1y = p1y - p0y, e1z = p1z - p0z;
-  const double e2x = p2x - p0x, e2y = p2y - p0y, e2z = p2z - p0z;
+__device__ __forceinline__ bool tri_test_edges(double &t_io, double &u_out, double &v_out, const TriEdges &k,
+                                               const RayD &r) {
   // p = dir x e2
-  const double px = r.dy * e2z - r.dz * e2y;
-  const double py = r.dz * e2x - r.dx * e2z;
-  const double pz = r.dx * e2y - r.dy * e2x;
-  const double det = e1x * px + e1y * py + e1z * pz;
+  const double px = r.dy * k.e2z - r.dz * k.e2y;
+  const double py = r.dz * k.e2x - r.dx * k.e2z;
+  const double pz = r.dx * k.e2y - r.dy * k.e2x;
+  const double det = k.e1x * px + k.e1y * py + k.e1z * pz;
   if (fabs(det) < MB200_TRI_EPS) return false;
   const double inv_det = 1.0 / det;
-  const double sx = r.ox - p0x, sy = r.oy - p0y, sz = r.oz - p0z;
+  const double sx = r.ox - k.p0x, sy = r.oy - k.p0y, sz = r.oz - k.p0z;
   // q = s x e1
-  const double qx = sy * e1z - sz * e1y;
-  const double qy = sz * e1x - sx * e1z;
-  const double qz = sx * e1y - sy * e1x;
+  const double qx = sy * k.e1z - sz * k.e1y;
+  const double qy = sz * k.e1x - sx * k.e1z;
+  const double qz = sx * k.e1y - sy * k.e1x;
   const double u = (sx * px + sy * py + sz * pz) * inv_det;
   const double v = (qx * r.dx + qy * r.dy + qz * r.dz) * inv_det;
-  const double t = (e2x * qx + e2y * qy + e2z * qz) * inv_det;
+  const double t = (k.e2x * qx + k.e2y * qy + k.e2z * qz) * inv_det;
   if (u < 0.0 || u > 1.0) return false;
   if (v < 0.0 || u + v > 1.0) return false;
   if (t < 0.0 || t > t_io) return false;
@@ -107,47 +145,9 @@ __device__ __forceinline__ bool tri_test(double &t_io, double &u_out, double &v_
   return true;
 }
 
-struct HitD {
-  double t, u, v;
-  uint32_t face, mat;
-};
-
-// ---- triangle record loaders ------------------------------------------------
-struct TriVerts {
-  double p0x, p0y, p0z, p1x, p1y, p1z, p2x, p2y, p2z;
-  uint32_t face, mat;
-};
-
-template <bool F32> __device__ __forceinline__ TriVerts load_tri(const void *tris, uint32_t i);
-
-template <> __device__ __forceinline__ TriVerts load_tri<true>(const void *tris, uint32_t i) {
-  const float4 *p = reinterpret_cast<const float4 *>(reinterpret_cast<const TriRecordF32 *>(tris) + i);
-  const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-  TriVerts t;
-  t.p0x = (double)a.x, t.p0y = (double)a.y, t.p0z = (double)a.z;
-  t.face = __float_as_uint(a.w);
-  t.p1x = (double)b.x, t.p1y = (double)b.y, t.p1z = (double)b.z;
-  t.mat = __float_as_uint(b.w);
-  t.p2x = (double)c.x, t.p2y = (double)c.y, t.p2z = (double)c.z;
-  return t;
-}
-
-template <> __device__ __forceinline__ TriVerts load_tri<false>(const void *tris, uint32_t i) {
-  const double2 *p = reinterpret_cast<const double2 *>(reinterpret_cast<const TriRecordF64 *>(tris) + i);
-  const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4);
-  TriVerts t;
-  t.p0x = a.x, t.p0y = a.y, t.p0z = b.x;
-  t.p1x = b.y, t.p1y = c.x, t.p1z = c.y;
-  t.p2x = d.x, t.p2y = d.y, t.p2z = e.x;
-  const unsigned long long w = (unsigned long long)__double_as_longlong(e.y);
-  t.face = (uint32_t)(w & 0xFFFFFFFFull);
-  t.mat = (uint32_t)(w >> 32);
-  return t;
-}
-
-// ---- traversal stack: first S entries per thread in shared memory (column
-// layout: entry k of thread t at [k * blockDim.x + t] -> conflict-free 128-bit
-// accesses), the rest in a per-thread local-memory array.
+// ---- traversal stack: first S entries per thread in shared memory (column layout: entry k of
+// thread t at [k * blockDim.x + t] -> conflict-free 128-bit accesses), the rest in a per-thread
+// local-memory array.  An entry is (tmin of the pushed child, its ref, its cnt).
 template <int S, int CAP> struct TravStack {
   uint4 *sm; // this thread's column base
   int stride;
@@ -169,91 +169,6 @@ template <int S, int CAP> struct TravStack {
 struct TravCounters {
   unsigned int nodes, tris, max_stack;
 };
-
-// Closest hit (ANYHIT = false): on entry hit.t = DBL_MAX, hit.u = hit.v = 0, face = mat = ~0
-// (bvh_accel.cc:783-786); returns true iff something was hit.
-// Any hit (ANYHIT = true): on entry hit.t = tmax; returns true as soon as a triangle is
-// accepted with t < tmax (see kernels.cu, occlusion).
-template <bool F32, int S, int CAP, bool ANYHIT, bool COUNT>
-__device__ __forceinline__ bool traverse(const SceneView &sc, const RayD &r, HitD &hit, TravStack<S, CAP> &st,
-                                         TravCounters &cnt) {
-  if (sc.empty) return false;
-  double hit_t = hit.t;
-  const double tmax_any = hit.t;
-  bool found = false;
-  int sp = 0;
-
-  uint32_t ref = sc.root_ref, rc = sc.root_cnt;
-  {
-    double tm;
-    if (COUNT) cnt.nodes++;
-    if (!slab_test(sc.root_box[0], sc.root_box[1], sc.root_box[2], sc.root_box[3], sc.root_box[4], sc.root_box[5],
-                   r, hit_t, tm))
-      return false;
-  }
-
-  for (;;) {
-    if (rc == kBranch) {
-      // ---- inner node: one 128-byte line, both children tested --------------
-      const double2 *np = reinterpret_cast<const double2 *>(sc.nodes + ref);
-      const double2 a0 = __ldg(np + 0), a1 = __ldg(np + 1), a2 = __ldg(np + 2);
-      const double2 b0 = __ldg(np + 3), b1 = __ldg(np + 4), b2 = __ldg(np + 5);
-      const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(np + 6));
-      const uint32_t axis = __ldg(reinterpret_cast<const uint32_t *>(np + 7));
-      double t0, t1;
-      const bool h0 = slab_test(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, r, hit_t, t0);
-      const bool h1 = slab_test(b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, r, hit_t, t1);
-      if (COUNT) cnt.nodes += 2;
-      const bool sgn = (axis == 0) ? r.sx : ((axis == 1) ? r.sy : r.sz);
-      // near = data[dirSign[axis]] (bvh_accel.cc:818-823)
-      if (h0 && h1) {
-        const uint32_t far_ref = sgn ? meta.x : meta.y, far_cnt = sgn ? meta.z : meta.w;
-        const double far_t = sgn ? t0 : t1;
-        st.put(sp++, far_t, far_ref, far_cnt);
-        if (COUNT) cnt.max_stack = max(cnt.max_stack, (unsigned int)sp + 1u);
-        ref = sgn ? meta.y : meta.x;
-        rc = sgn ? meta.w : meta.z;
-        continue;
-      }
-      if (h0) {
-        ref = meta.x, rc = meta.z;
-        continue;
-      }
-      if (h1) {
-        ref = meta.y, rc = meta.w;
-        continue;
-      }
-    } else {
-      // ---- leaf: TestLeafNode (bvh_accel.cc:640-697) ------------------------
-      if (COUNT) cnt.tris += rc;
-      for (uint32_t i = 0; i < rc; i++) {
-        const TriVerts tv = load_tri<F32>(sc.tris, ref + i);
-        double u, v;
-        if (tri_test(hit_t, u, v, tv.p0x, tv.p0y, tv.p0z, tv.p1x, tv.p1y, tv.p1z, tv.p2x, tv.p2y, tv.p2z, r)) {
-          hit.t = hit_t;
-          hit.u = u;
-          hit.v = v;
-          hit.face = tv.face;
-          hit.mat = tv.mat;
-          found = true;
-          if (ANYHIT && hit_t < tmax_any) return true;
-        }
-      }
-    }
-    // ---- pop: the reference's pop-time (tmin <= hitT) decision ---------------
-    bool got = false;
-    while (sp > 0) {
-      double tm;
-      st.get(--sp, tm, ref, rc);
-      if (tm <= hit_t) {
-        got = true;
-        break;
-      }
-    }
-    if (!got) break;
-  }
-  return ANYHIT ? false : found;
-}
 
 } // namespace mb200
 
