@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Condenses one .ncu-rep (ncu --set full --import-source on) into a short text summary:
 key launch / throughput / stall metrics, an opcode-class table with lane occupancy, and the hottest SASS lines.
-Usage: python tools/ncu_summary.py report.ncu-rep > profiles/<name>.md"""
+Usage: python tools/ncu_summary.py report.ncu-rep [launch-index] > profiles/<name>.md"""
 import collections
 import csv
 import io
@@ -10,6 +10,8 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
+skip = sys.argv[2] if len(sys.argv) > 2 else "0"   # which launch of the report
+SEL = ["--launch-skip", skip, "--launch-count", "1"]
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
         "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "l1tex__t_bytes.sum",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
@@ -23,7 +25,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__warps_eligible.avg.per_cycle_active", "smsp__average_warp_latency_per_inst_issued.ratio",
         "sm__cycles_elapsed.avg", "sm__cycles_active.avg"]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + SEL, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
 print(f"# ncu summary of {rep}\n")
@@ -38,11 +40,11 @@ for k in hdr:
         v = float(m[k][1] or 0)
         if v >= 0.05:
             print(f"| stall {k[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]} | {v:.3f} | warps/issue |")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + SEL, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = rows[1]
 ix = {k: i for i, k in enumerate(h)}
-data = rows[2:]
+data = [r for r in rows[2:] if len(r) >= len(h) and r[0].startswith("0x")]
 cls, thr = collections.Counter(), collections.Counter()
 for r in data:
     ie = int(r[ix["Instructions Executed"]] or 0)
