@@ -132,6 +132,48 @@ int mb200_bvh_stats(const mb200_bvh *bvh, mb200_build_stats *out); /* BVHAccel::
 void mb200_bvh_destroy(mb200_bvh *bvh);
 
 /* -------------------------------------------------------------------------
+ * Mesh ingestion and configuration: what Scene::Init does before the BVH build
+ * (scene.cc:66-170) and LoadJSONConfig (main.cc:98-205).  Host only.
+ * ---------------------------------------------------------------------- */
+typedef struct mb200_mesh mb200_mesh; /* host mesh: the arrays struct Mesh (mesh.h:7-18) points at */
+/* MeshLoader::LoadObj (importers/mesh_loader.cc:26-210 over tiny_obj_loader.cc): same vertex / face
+ * numbering, float-parsed positions, fan triangulation, material ids, face-varying normals and uvs. */
+int mb200_mesh_load_obj(mb200_mesh **out, const char *path);
+/* MeshLoader::LoadESON (importers/mesh_loader.cc:212-310). */
+int mb200_mesh_load_eson(mb200_mesh **out, const char *path);
+/* Scene::Init's vertex transform (scene.cc:112-170): scene_fit != 0 maps the bounding box to [-1,1]^3,
+ * otherwise vertices *= scene_scale. */
+int mb200_mesh_transform(mb200_mesh *mesh, double scene_scale, int scene_fit);
+size_t mb200_mesh_num_vertices(const mb200_mesh *mesh);
+size_t mb200_mesh_num_faces(const mb200_mesh *mesh);
+const double *mb200_mesh_vertices(const mb200_mesh *mesh);       /* [3*nv] */
+const uint32_t *mb200_mesh_faces(const mb200_mesh *mesh);        /* [3*nf] */
+const uint32_t *mb200_mesh_material_ids(const mb200_mesh *mesh); /* [nf]   */
+const double *mb200_mesh_fv_normals(const mb200_mesh *mesh);     /* [9*nf] or NULL */
+const double *mb200_mesh_fv_uvs(const mb200_mesh *mesh);         /* [6*nf] or NULL */
+void mb200_mesh_destroy(mb200_mesh *mesh);
+
+/* struct RenderConfig (render.h:11-49) as a POD; defaults are RenderConfig()'s (render.h:33-48). */
+typedef struct {
+  double fov;
+  int width, height;
+  double eye[3], lookat[3], up[3], quat[4];
+  double scene_scale;
+  int scene_fit, plane;
+  int num_passes, num_photons;
+  char obj_filename[1024], eson_filename[1024], magicavoxel_filename[1024], material_filename[1024];
+  /* additions; absent keys keep the reference's behaviour */
+  int max_path_length; /* "max_path_length", default 16 (kMaxPathLength, render.cc:52) */
+  int shader;          /* "shader": "pathtrace" (default) | "primary_shadow" | "primary"   */
+  double light[3];     /* "light"                                                            */
+  int device, num_gpus; /* "device", "gpus"                                                  */
+} mb200_config;
+void mb200_config_default(mb200_config *cfg);
+/* LoadJSONConfig (main.cc:98-205).  Exactly one of path / json_text is non-NULL.  Keys that are absent
+ * leave *cfg untouched (call mb200_config_default first). */
+int mb200_config_load(mb200_config *cfg, const char *path, const char *json_text);
+
+/* -------------------------------------------------------------------------
  * Device scene: replaces the accel_ member of Scene (scene.h:75) and what
  * Scene::Init does after loading the mesh (scene.cc:224-230).
  * vertices [3*nverts] f64, faces [3*nfaces] u32 as in struct Mesh (mesh.h:7-18);
@@ -212,6 +254,11 @@ typedef struct {
    * b with b % band_count == band_index; with band_compact != 0 the image/count buffers hold just those
    * rows, packed band after band (float[3*width*mb200_band_local_rows()], the NCCL gather send buffer). */
   int band_rows, band_count, band_index, band_compact;
+  /* Render()'s `step` argument (render.cc:657-698).  0 or 1: every pixel.  step > 1 (coarse preview): one
+   * sample at every step-th pixel of every step-th row, copied over its step x step block (clipped to the
+   * tile), and count += 3 for every pixel of the block -- the reference increments it inside the k < 3
+   * colour loop (render.cc:689-693).  Not combinable with band_rows. */
+  int pixel_step;
 } mb200_render_params;
 
 typedef struct {

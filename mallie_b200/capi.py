@@ -38,6 +38,9 @@ EXPORTS = [
     "mb200_camera_frame_build", "mb200_generate_rays", "mb200_generate_rays_grid",
     "mb200_render_params_default", "mb200_plane_from_bounds", "mb200_render_pass", "mb200_render_accumulate",
     "mb200_render_frame", "mb200_band_local_rows",
+    "mb200_mesh_load_obj", "mb200_mesh_load_eson", "mb200_mesh_transform", "mb200_mesh_num_vertices",
+    "mb200_mesh_num_faces", "mb200_mesh_vertices", "mb200_mesh_faces", "mb200_mesh_material_ids",
+    "mb200_mesh_fv_normals", "mb200_mesh_fv_uvs", "mb200_mesh_destroy", "mb200_config_default", "mb200_config_load",
 ]
 
 
@@ -68,7 +71,8 @@ class RenderParams(C.Structure):
                 ("y1", C.c_int), ("frame", CameraFrame), ("use_plane", C.c_int), ("plane", C.c_float * 4),
                 ("max_path_length", C.c_int), ("pass_", C.c_uint32), ("jitter", C.c_int), ("shader", C.c_int),
                 ("light", C.c_double * 3),
-                ("band_rows", C.c_int), ("band_count", C.c_int), ("band_index", C.c_int), ("band_compact", C.c_int)]
+                ("band_rows", C.c_int), ("band_count", C.c_int), ("band_index", C.c_int), ("band_compact", C.c_int),
+                ("pixel_step", C.c_int)]
 
 
 class RenderStats(C.Structure):
@@ -77,6 +81,17 @@ class RenderStats(C.Structure):
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class Config(C.Structure):
+    """mb200_config: struct RenderConfig (render.h:11-49) as a POD."""
+    _fields_ = [("fov", C.c_double), ("width", C.c_int), ("height", C.c_int), ("eye", C.c_double * 3),
+                ("lookat", C.c_double * 3), ("up", C.c_double * 3), ("quat", C.c_double * 4),
+                ("scene_scale", C.c_double), ("scene_fit", C.c_int), ("plane", C.c_int), ("num_passes", C.c_int),
+                ("num_photons", C.c_int), ("obj_filename", C.c_char * 1024), ("eson_filename", C.c_char * 1024),
+                ("magicavoxel_filename", C.c_char * 1024), ("material_filename", C.c_char * 1024),
+                ("max_path_length", C.c_int), ("shader", C.c_int), ("light", C.c_double * 3), ("device", C.c_int),
+                ("num_gpus", C.c_int)]
 
 
 class MallieB200Error(RuntimeError):
@@ -137,6 +152,18 @@ def lib():
         L.mb200_render_accumulate.argtypes = [vp, C.POINTER(RenderParams), i32, vp, vp, C.POINTER(RenderStats)]
         L.mb200_render_frame.argtypes = [vp, C.POINTER(RenderParams), i32, vp, vp, C.POINTER(RenderStats)]
         L.mb200_band_local_rows.argtypes = [C.POINTER(RenderParams)]
+        L.mb200_mesh_load_obj.argtypes = [C.POINTER(vp), C.c_char_p]
+        L.mb200_mesh_load_eson.argtypes = [C.POINTER(vp), C.c_char_p]
+        L.mb200_mesh_transform.argtypes = [vp, dbl, i32]
+        for fn in ("num_vertices", "num_faces"):
+            getattr(L, "mb200_mesh_" + fn).restype = sz
+            getattr(L, "mb200_mesh_" + fn).argtypes = [vp]
+        for fn in ("vertices", "faces", "material_ids", "fv_normals", "fv_uvs"):
+            getattr(L, "mb200_mesh_" + fn).restype = vp
+            getattr(L, "mb200_mesh_" + fn).argtypes = [vp]
+        L.mb200_mesh_destroy.argtypes = [vp]
+        L.mb200_config_default.argtypes = [C.POINTER(Config)]
+        L.mb200_config_load.argtypes = [C.POINTER(Config), C.c_char_p, C.c_char_p]
         _lib = L
     return _lib
 
@@ -161,6 +188,40 @@ def device_count():
 
 def launches_issued():
     return int(lib().mb200_launches_issued())
+
+
+def load_config(path=None, text=None):
+    """LoadJSONConfig (main.cc:98-205) -> Config; raises MallieB200Error when the file is unreadable / malformed."""
+    cfg = Config()
+    lib().mb200_config_default(C.byref(cfg))
+    check(lib().mb200_config_load(C.byref(cfg), path.encode() if path is not None else None,
+                                  text.encode() if text is not None else None))
+    return cfg
+
+
+def load_mesh(path, kind=None, scene_scale=1.0, scene_fit=False):
+    """MeshLoader::LoadObj / LoadESON + Scene::Init's scale / fit.  Returns dict(vertices, faces, material_ids,
+    normals, uvs) of numpy arrays (normals / uvs None when the loader leaves them NULL)."""
+    L = lib()
+    kind = kind or ("eson" if path.endswith(".eson") else "obj")
+    h = C.c_void_p()
+    check((L.mb200_mesh_load_eson if kind == "eson" else L.mb200_mesh_load_obj)(C.byref(h), path.encode()))
+    try:
+        check(L.mb200_mesh_transform(h, float(scene_scale), int(bool(scene_fit))))
+        nv, nf = L.mb200_mesh_num_vertices(h), L.mb200_mesh_num_faces(h)
+
+        def grab(fn, dtype, count):
+            ptr = getattr(L, "mb200_mesh_" + fn)(h)
+            if not ptr or count == 0:
+                return None if fn.startswith("fv_") else np.zeros(0, dtype)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), (count,)).copy()
+
+        return dict(vertices=grab("vertices", np.float64, 3 * nv).reshape(-1, 3),
+                    faces=grab("faces", np.uint32, 3 * nf).reshape(-1, 3),
+                    material_ids=grab("material_ids", np.uint32, nf),
+                    normals=grab("fv_normals", np.float64, 9 * nf), uvs=grab("fv_uvs", np.float64, 6 * nf))
+    finally:
+        L.mb200_mesh_destroy(h)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -338,8 +399,9 @@ class Scene:
 
     # -- frame
     def render_params(self, frame, width, height, tile=None, plane=None, max_path_length=16, pass_index=0,
-                      jitter=True, shader=SHADER_PATHTRACE, light=(0.0, 20.0, 0.0), bands=None, compact=False):
-        """bands = (band_rows, band_count, band_index) enables the multi-GPU row-band interleave."""
+                      jitter=True, shader=SHADER_PATHTRACE, light=(0.0, 20.0, 0.0), bands=None, compact=False, step=1):
+        """bands = (band_rows, band_count, band_index) enables the multi-GPU row-band interleave; step is
+        Render()'s coarse-preview step (render.cc:657-698)."""
         p = RenderParams()
         lib().mb200_render_params_default(C.byref(p), width, height)
         p.frame = frame
@@ -355,6 +417,7 @@ class Scene:
         if bands is not None:
             p.band_rows, p.band_count, p.band_index = bands
             p.band_compact = int(compact)
+        p.pixel_step = int(step)
         return p
 
     @staticmethod

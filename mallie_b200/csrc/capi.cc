@@ -7,11 +7,14 @@
 
 #include <cstdio>
 #include <cstring>
+#include <new>
 #include <string>
 
 #include "device/kernels.h"
 #include "device/scene.h"
 #include "host/bvh_build.h"
+#include "host/mallie_api.h"
+#include "host/mesh_data.h"
 #include "mallie_b200.h"
 
 namespace {
@@ -178,6 +181,86 @@ int mb200_bvh_stats(const mb200_bvh *bvh, mb200_build_stats *out) {
   return MB200_OK;
 }
 void mb200_bvh_destroy(mb200_bvh *bvh) { delete bvh; }
+
+// ---------------------------------------------------------------------------- mesh + config
+static int load_mesh(mb200_mesh **out, const char *path, bool eson) {
+  if (!out || !path) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  mb200_mesh *m = new (std::nothrow) mb200_mesh();
+  if (!m) return set_err(MB200_ERR_OUT_OF_MEMORY, "out of host memory");
+  std::string err;
+  const bool ok = eson ? mb200::load_eson(m->mesh, path, &err) : mb200::load_obj(m->mesh, path, &err);
+  if (!ok) {
+    delete m;
+    return set_err(MB200_ERR_IO, err);
+  }
+  *out = m;
+  return MB200_OK;
+}
+int mb200_mesh_load_obj(mb200_mesh **out, const char *path) { return load_mesh(out, path, false); }
+int mb200_mesh_load_eson(mb200_mesh **out, const char *path) { return load_mesh(out, path, true); }
+int mb200_mesh_transform(mb200_mesh *mesh, double scene_scale, int scene_fit) {
+  if (!mesh) return set_err(MB200_ERR_INVALID_ARG, "null mesh");
+  mb200::apply_scene_transform(mesh->mesh.vertices.data(), mesh->mesh.vertices.size() / 3, scene_scale,
+                               scene_fit != 0, false);
+  return MB200_OK;
+}
+size_t mb200_mesh_num_vertices(const mb200_mesh *m) { return m ? m->mesh.vertices.size() / 3 : 0; }
+size_t mb200_mesh_num_faces(const mb200_mesh *m) { return m ? m->mesh.faces.size() / 3 : 0; }
+const double *mb200_mesh_vertices(const mb200_mesh *m) { return m ? m->mesh.vertices.data() : nullptr; }
+const uint32_t *mb200_mesh_faces(const mb200_mesh *m) { return m ? m->mesh.faces.data() : nullptr; }
+const uint32_t *mb200_mesh_material_ids(const mb200_mesh *m) { return m ? m->mesh.material_ids.data() : nullptr; }
+const double *mb200_mesh_fv_normals(const mb200_mesh *m) {
+  return (m && !m->mesh.normals.empty()) ? m->mesh.normals.data() : nullptr;
+}
+const double *mb200_mesh_fv_uvs(const mb200_mesh *m) {
+  return (m && !m->mesh.uvs.empty()) ? m->mesh.uvs.data() : nullptr;
+}
+void mb200_mesh_destroy(mb200_mesh *m) { delete m; }
+
+static void config_to_pod(const mallie::RenderConfig &c, mb200_config *o) {
+  o->fov = c.fov, o->width = c.width, o->height = c.height;
+  for (int k = 0; k < 3; k++)
+    o->eye[k] = c.eye[k], o->lookat[k] = c.lookat[k], o->up[k] = c.up[k], o->light[k] = c.light[k];
+  for (int k = 0; k < 4; k++) o->quat[k] = c.quat[k];
+  o->scene_scale = c.scene_scale, o->scene_fit = c.scene_fit, o->plane = c.plane;
+  o->num_passes = c.num_passes, o->num_photons = c.num_photons;
+  snprintf(o->obj_filename, sizeof(o->obj_filename), "%s", c.obj_filename.c_str());
+  snprintf(o->eson_filename, sizeof(o->eson_filename), "%s", c.eson_filename.c_str());
+  snprintf(o->magicavoxel_filename, sizeof(o->magicavoxel_filename), "%s", c.magicavoxel_filename.c_str());
+  snprintf(o->material_filename, sizeof(o->material_filename), "%s", c.material_filename.c_str());
+  o->max_path_length = c.max_path_length, o->shader = c.shader, o->device = c.device, o->num_gpus = c.num_gpus;
+}
+static void pod_to_config(const mb200_config *o, mallie::RenderConfig &c) {
+  c.fov = o->fov, c.width = o->width, c.height = o->height;
+  for (int k = 0; k < 3; k++)
+    c.eye[k] = o->eye[k], c.lookat[k] = o->lookat[k], c.up[k] = o->up[k], c.light[k] = o->light[k];
+  for (int k = 0; k < 4; k++) c.quat[k] = o->quat[k];
+  c.scene_scale = o->scene_scale, c.scene_fit = o->scene_fit != 0, c.plane = o->plane != 0;
+  c.num_passes = o->num_passes, c.num_photons = o->num_photons;
+  c.obj_filename = o->obj_filename, c.eson_filename = o->eson_filename;
+  c.magicavoxel_filename = o->magicavoxel_filename, c.material_filename = o->material_filename;
+  c.max_path_length = o->max_path_length, c.shader = o->shader, c.device = o->device, c.num_gpus = o->num_gpus;
+}
+void mb200_config_default(mb200_config *cfg) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof(*cfg));
+  config_to_pod(mallie::RenderConfig(), cfg);
+}
+int mb200_config_load(mb200_config *cfg, const char *path, const char *json_text) {
+  if (!cfg || (path == nullptr) == (json_text == nullptr))
+    return set_err(MB200_ERR_INVALID_ARG, "need a config and exactly one of path / json_text");
+  cfg->obj_filename[sizeof(cfg->obj_filename) - 1] = cfg->eson_filename[sizeof(cfg->eson_filename) - 1] = 0;
+  cfg->magicavoxel_filename[sizeof(cfg->magicavoxel_filename) - 1] = 0;
+  cfg->material_filename[sizeof(cfg->material_filename) - 1] = 0;
+  mallie::RenderConfig c;
+  pod_to_config(cfg, c);
+  const bool ok = path ? mallie::LoadJSONConfig(c, path) : mallie::LoadJSONConfigFromString(c, json_text);
+  if (!ok)
+    return set_err(MB200_ERR_IO, path ? std::string("cannot read or parse ") + path : std::string("malformed JSON"));
+  config_to_pod(c, cfg);
+  return MB200_OK;
+}
 
 // ---------------------------------------------------------------------------- scene
 int mb200_scene_create(mb200_scene **out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
@@ -370,6 +453,8 @@ static int render_common(mb200_scene *s, const mb200_render_params *p, int num_p
   if (p->band_rows < 0 || (p->band_rows > 0 && (p->band_rows % 4 != 0 || p->band_count < 1 || p->band_index < 0 ||
                                                  p->band_index >= p->band_count)))
     return set_err(MB200_ERR_INVALID_ARG, "bad band parameters (band_rows must be a multiple of 4)");
+  if (p->pixel_step < 0 || (p->pixel_step > 1 && p->band_rows > 0))
+    return set_err(MB200_ERR_INVALID_ARG, "pixel_step must be >= 0 and cannot be combined with row bands");
   if (stats) memset(stats, 0, sizeof(*stats));
   CU(cudaSetDevice(s->device));
   const bool compact = p->band_rows > 0 && p->band_compact;

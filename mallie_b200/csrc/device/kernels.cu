@@ -350,6 +350,19 @@ __global__ void __launch_bounds__(256)
     if (mode != 0) ar += r, ag += r, ab += r;
     else ar = ag = ab = r;
   }
+  if (m.step > 1) {
+    // coarse preview (render.cc:684-696): the sample fills its step x step block, clipped to the
+    // rectangle; count++ sits inside the reference's k < 3 colour loop, hence += 3 per pass.
+    const int bx = min(m.step, m.x1 - x), by = min(m.step, m.y1 - y);
+    for (int v = 0; v < by; v++)
+      for (int u = 0; u < bx; u++) {
+        const size_t q = (size_t)(y + v) * m.width + (x + u);
+        image[3 * q + 0] = ar, image[3 * q + 1] = ag, image[3 * q + 2] = ab;
+        if (mode == 2) count[q] = 3 * (int)m.passes;
+        else count[q] += 3 * (int)m.passes;
+      }
+    return;
+  }
   image[3 * pix + 0] = ar, image[3 * pix + 1] = ag, image[3 * pix + 2] = ab;
   if (mode == 2) count[pix] = (int)m.passes;
   else count[pix] += (int)m.passes;

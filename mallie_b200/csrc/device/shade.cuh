@@ -174,7 +174,8 @@ __device__ __forceinline__ void sample_diffuse(Xorshift128 &rng, double nx, doub
 }
 
 // ---- work items of a frame ---------------------------------------------------------------------------
-// The pixels a render call owns (its rectangle, or its row bands of it) are cut into 8x4 tiles; one work
+// The pixels a render call samples (its rectangle, or its row bands of it; every step-th pixel of every
+// step-th row when Render()'s step > 1) are cut into 8x4 tiles; one work
 // item is one sample of one pixel, numbered   item = (tile * passes + pass) * 32 + lane   so that 32
 // consecutive items are one tile (coherent rays for a warp) and the samples of a tile are adjacent (the
 // same BVH region stays in L1/L2).  Items of lanes that fall outside the rectangle are "invalid".
@@ -186,6 +187,8 @@ struct FrameMap {
   int band_rows, band_count, band_index, compact;
   uint32_t passes;      // samples per pixel in this batch
   uint32_t pass0;       // first pass index of the batch
+  int step;             // Render()'s step (>= 1): sampled pixels are step apart in x and y
+  int y1;               // end row of the rectangle (block fill clipping)
 };
 
 __host__ __device__ inline int band_local_rows(int rows, int band_rows, int count, int index) {
@@ -201,9 +204,11 @@ __host__ __device__ inline int band_local_rows(int rows, int band_rows, int coun
 __host__ inline FrameMap make_frame_map(const mb200_render_params &p, uint32_t pass0, uint32_t passes) {
   FrameMap m;
   m.x0 = p.x0, m.x1 = p.x1, m.y0 = p.y0;
-  m.rows_local = p.y1 - p.y0;
+  m.step = p.pixel_step > 1 ? p.pixel_step : 1;
+  m.y1 = p.y1;
+  m.rows_local = (p.y1 - p.y0 + m.step - 1) / m.step; // sampled rows
   if (p.band_rows > 0) m.rows_local = band_local_rows(p.y1 - p.y0, p.band_rows, p.band_count, p.band_index);
-  m.tiles_x = (p.x1 - p.x0 + 7) >> 3;
+  m.tiles_x = ((p.x1 - p.x0 + m.step - 1) / m.step + 7) >> 3;
   m.width = p.width;
   m.band_rows = p.band_rows, m.band_count = p.band_count, m.band_index = p.band_index, m.compact = p.band_compact;
   m.passes = passes, m.pass0 = pass0;
@@ -220,9 +225,9 @@ __device__ __forceinline__ bool item_pixel(const FrameMap &m, uint32_t item, int
   const uint32_t tile = g / m.passes;
   pass = m.pass0 + (g - tile * m.passes);
   const int tx = (int)(tile % (uint32_t)m.tiles_x), ty = (int)(tile / (uint32_t)m.tiles_x);
-  x = m.x0 + tx * 8 + (int)(lane & 7u);
+  x = m.x0 + (tx * 8 + (int)(lane & 7u)) * m.step;
   rl = ty * 4 + (int)(lane >> 3);
-  y = m.y0 + rl;
+  y = m.y0 + rl * m.step;
   if (m.band_rows > 0) y = m.y0 + ((rl / m.band_rows) * m.band_count + m.band_index) * m.band_rows + rl % m.band_rows;
   return x < m.x1 && rl < m.rows_local;
 }

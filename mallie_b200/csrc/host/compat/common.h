@@ -1,0 +1,2 @@
+// common.h -- forwarding header: code written against the reference's common.h builds against mallie_b200.
+#include "../mallie_api.h"

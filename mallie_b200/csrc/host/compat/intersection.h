@@ -1,0 +1,2 @@
+// intersection.h -- forwarding header: code written against the reference's intersection.h builds against mallie_b200.
+#include "../mallie_api.h"

@@ -1,0 +1,2 @@
+// mesh.h -- forwarding header: code written against the reference's mesh.h builds against mallie_b200.
+#include "../mallie_api.h"

@@ -1,0 +1,2 @@
+// render.h -- forwarding header: code written against the reference's render.h builds against mallie_b200.
+#include "../mallie_api.h"

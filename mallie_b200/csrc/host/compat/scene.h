@@ -1,0 +1,2 @@
+// scene.h -- forwarding header: code written against the reference's scene.h builds against mallie_b200.
+#include "../mallie_api.h"

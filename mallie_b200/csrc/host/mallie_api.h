@@ -317,6 +317,15 @@ double RenderAccumulate(Scene &scene, const RenderConfig &config, std::vector<fl
 
 // config.json -> RenderConfig (main.cc:98-205): same keys, unknown keys ignored.
 bool LoadJSONConfig(RenderConfig &config, const std::string &filename);
+bool LoadJSONConfigFromString(RenderConfig &config, const std::string &json_text);
+
+// DoMainConsole (main_console.cc:57-75): one Render() pass -> 8-bit image -> file.  The reference
+// writes output.jpg through jpge; this writes a binary PPM with the same quantisation
+// (x / count * 255.5, clamped, main_console.cc:25-43).  `passes` > 1 accumulates that many passes on
+// the GPU first (what the SDL front end's render thread does).  Returns false on failure.
+bool DoMainConsole(Scene &scene, const RenderConfig &config, const char *output = "output.ppm", int passes = 1);
+void HDRToLDR(std::vector<unsigned char> &out, const std::vector<float> &in, const std::vector<int> &in_count,
+              int width, int height);
 
 } // namespace mallie
 

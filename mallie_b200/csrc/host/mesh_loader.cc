@@ -23,7 +23,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cstdint>
 #include <fstream>
+#include <iterator>
 #include <map>
 #include <string>
 #include <tuple>
@@ -328,6 +330,102 @@ bool load_obj(MeshData &out, const char *filename, std::string *err) {
   return true;
 }
 
+
+// ---- ESON -----------------------------------------------------------------------------------------
+// LTE's binary container (importers/eson.cc:131-313): i64 total size, then elements
+//   u8 tag | NUL-terminated key | payload
+// with payload f64 (tag 1), i64 (tag 2), i64 n + n bytes (string 4, binary 6), i64 n + nested element
+// (object 7).  MeshLoader::LoadESON (mesh_loader.cc:212-310) reads num_vertices, num_faces (i64),
+// vertices (f32[3nv]), faces (i32[3nf]) and optional material_ids (u16[nf]); face-varying normals and
+// uvs are left NULL even when present.
+namespace {
+struct EsonField {
+  int tag = 0;
+  int64_t i64 = 0;
+  const unsigned char *ptr = nullptr;
+  int64_t size = 0;
+};
+
+bool eson_scan(const std::vector<unsigned char> &buf, std::map<std::string, EsonField> &out, std::string *err) {
+  auto fail = [&](const char *m) {
+    if (err) *err = m;
+    return false;
+  };
+  if (buf.size() < 8) return fail("ESON: file too short");
+  int64_t total;
+  memcpy(&total, buf.data(), 8);
+  if (total <= 0 || (size_t)total > buf.size()) return fail("ESON: bad total size");
+  size_t at = 8;
+  while (at < (size_t)total) {
+    EsonField f;
+    f.tag = buf[at++];
+    const void *nul = memchr(buf.data() + at, 0, (size_t)total - at);
+    if (!nul) return fail("ESON: unterminated key");
+    const std::string key(reinterpret_cast<const char *>(buf.data() + at));
+    at += key.size() + 1;
+    if (f.tag == 1 || f.tag == 2) {
+      if (at + 8 > buf.size()) return fail("ESON: truncated scalar");
+      memcpy(&f.i64, buf.data() + at, 8);
+      at += 8;
+    } else if (f.tag == 4 || f.tag == 6 || f.tag == 7) {
+      if (at + 8 > buf.size()) return fail("ESON: truncated length");
+      memcpy(&f.size, buf.data() + at, 8);
+      at += 8;
+      if (f.size < 0 || at + (size_t)f.size > buf.size()) return fail("ESON: truncated payload");
+      f.ptr = buf.data() + at;
+      at += (size_t)f.size;
+    } else {
+      return fail("ESON: unsupported element type");
+    }
+    out[key] = f;
+  }
+  return true;
+}
+} // namespace
+
+bool load_eson(MeshData &out, const char *filename, std::string *err) {
+  std::ifstream in(filename, std::ios::binary);
+  if (!in) {
+    if (err) *err = std::string("Failed to load file: ") + filename;
+    return false;
+  }
+  std::vector<unsigned char> buf((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+  std::map<std::string, EsonField> f;
+  if (!eson_scan(buf, f, err)) return false;
+  auto need = [&](const char *k, int tag) { return f.count(k) && f[k].tag == tag; };
+  if (!need("num_vertices", 2) || !need("num_faces", 2) || !need("vertices", 6) || !need("faces", 6)) {
+    if (err) *err = "ESON: missing num_vertices / num_faces / vertices / faces";
+    return false;
+  }
+  const int64_t nv = f["num_vertices"].i64, nf = f["num_faces"].i64;
+  if (nv < 0 || nf < 0 || f["vertices"].size < nv * 12 || f["faces"].size < nf * 12) {
+    if (err) *err = "ESON: array sizes do not match the counts";
+    return false;
+  }
+  out = MeshData();
+  out.num_shapes = 1;
+  out.vertices.resize(3 * (size_t)nv);
+  out.faces.resize(3 * (size_t)nf);
+  out.material_ids.assign((size_t)nf, 0u);
+  for (size_t i = 0; i < 3 * (size_t)nv; i++) {
+    float v;
+    memcpy(&v, f["vertices"].ptr + 4 * i, 4);
+    out.vertices[i] = (double)v;
+  }
+  for (size_t i = 0; i < 3 * (size_t)nf; i++) {
+    int v;
+    memcpy(&v, f["faces"].ptr + 4 * i, 4);
+    out.faces[i] = (unsigned int)v;
+  }
+  if (need("material_ids", 6) && f["material_ids"].size >= nf * 2)
+    for (size_t i = 0; i < (size_t)nf; i++) {
+      unsigned short v;
+      memcpy(&v, f["material_ids"].ptr + 2 * i, 2);
+      out.material_ids[i] = v;
+    }
+  return true;
+}
+
 } // namespace mb200
 
 // ---- the reference-facing entry (importers/mesh_loader.h) ---------------------------------------------
@@ -358,4 +456,26 @@ bool MeshLoader::LoadObj(Mesh &mesh, const char *filename) {
   if (!d.normals.empty()) memcpy(mesh.facevarying_normals, d.normals.data(), d.normals.size() * sizeof(real));
   if (!d.uvs.empty()) memcpy(mesh.facevarying_uvs, d.uvs.data(), d.uvs.size() * sizeof(real));
   return true;
+}
+
+bool MeshLoader::LoadESON(Mesh &mesh, const char *filename) {
+  printf("[LoadESON] %s\n", filename);
+  mb200::MeshData d;
+  std::string err;
+  if (!mb200::load_eson(d, filename, &err)) {
+    fprintf(stderr, "%s\n", err.c_str());
+    return false;
+  }
+  printf("# of vertices: %zu\n# of faces   : %zu\n", d.vertices.size() / 3, d.faces.size() / 3);
+  memset(&mesh, 0, sizeof(mesh));
+  mesh.numVertices = d.vertices.size() / 3;
+  mesh.numFaces = d.faces.size() / 3;
+  mesh.vertices = new real[d.vertices.size() + 1];
+  mesh.faces = new unsigned int[d.faces.size() + 1];
+  mesh.materialIDs = new unsigned int[d.material_ids.size() + 1];
+  if (!d.vertices.empty()) memcpy(mesh.vertices, d.vertices.data(), d.vertices.size() * sizeof(real));
+  if (!d.faces.empty()) memcpy(mesh.faces, d.faces.data(), d.faces.size() * sizeof(unsigned int));
+  if (!d.material_ids.empty())
+    memcpy(mesh.materialIDs, d.material_ids.data(), d.material_ids.size() * sizeof(unsigned int));
+  return true; // face-varying normals / uvs stay NULL (mesh_loader.cc:303-307)
 }

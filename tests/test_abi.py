@@ -49,13 +49,35 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(capi.CameraFrame) == 96
     assert C.sizeof(capi.Counters) == 32 and C.sizeof(capi.RenderStats) == 32
     assert C.sizeof(capi.BuildOptions) == 24 and C.sizeof(capi.BuildStats) == 12
-    # mb200_render_params: 6 ints, frame (96, 8-aligned), int, float[4], int, u32, int, int, double[3], 4 ints
-    assert C.sizeof(capi.RenderParams) == 200
+    # mb200_render_params: 6 ints, frame (96, 8-aligned), int, float[4], int, u32, int, int, double[3], 5 ints
+    assert C.sizeof(capi.RenderParams) == 208
     assert capi.RAY_DTYPE.itemsize == 48 and capi.HIT_DTYPE.itemsize == 32
     assert capi.ISECT_DTYPE.itemsize == 184 and capi.NODE_DTYPE.itemsize == 64
     assert capi.ISECT_DTYPE.fields["position"][1] == 48 and capi.ISECT_DTYPE.fields["normal"][1] == 96
     assert capi.ISECT_DTYPE.fields["texcoord"][1] == 168
     assert capi.lib().mb200_version().decode().startswith("mallie_b200")
+
+
+def test_header_is_plain_c_and_ctypes_mirrors_agree(tmp_path):
+    """include/mallie_b200.h compiles as C (gcc -std=c99) and its struct sizes are the ctypes mirrors' sizes."""
+    import subprocess
+    names = {"mb200_ray": capi.RAY_DTYPE.itemsize, "mb200_hit": capi.HIT_DTYPE.itemsize,
+             "mb200_isect": capi.ISECT_DTYPE.itemsize, "mb200_bvh_node": capi.NODE_DTYPE.itemsize,
+             "mb200_build_options": C.sizeof(capi.BuildOptions), "mb200_build_stats": C.sizeof(capi.BuildStats),
+             "mb200_counters": C.sizeof(capi.Counters), "mb200_camera_frame": C.sizeof(capi.CameraFrame),
+             "mb200_render_params": C.sizeof(capi.RenderParams), "mb200_render_stats": C.sizeof(capi.RenderStats),
+             "mb200_config": C.sizeof(capi.Config)}
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "mallie_b200.h"\nint main(void){\n' +
+                   "".join('printf("%s %%zu\\n", sizeof(%s));\n' % (n, n) for n in names) +
+                   'printf("pixel_step %zu\\n", offsetof(mb200_render_params, pixel_step));return 0;}\n')
+    exe = tmp_path / "sizes"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, "-o", str(exe), str(src)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for n, want in names.items():
+        assert int(got[n]) == want, (n, got[n], want)
+    assert int(got["pixel_step"]) == capi.RenderParams.pixel_step.offset
 
 
 @pytest.mark.parametrize("mesh,entry", [("cornellbox", "cornellbox_512"), ("teapot", "teapot_1080p"),
