@@ -13,9 +13,13 @@ A "step" is one 16-spp frame: 33.2 M primary rays + ~11.4 M shadow rays.
           frame is fixed), each rank renders its bands, one NCCL all-gather of the framebuffer per frame.
 * e2e   : the same frame through the C-ABI call a Mallie host makes (mb200_render_frame) with pinned HOST
           image / count buffers; the device->host copy of the framebuffer is inside the timed region.
-* roofline : algorithmic bytes (64 B/node popped + 88 B/triangle tested + 48 B ray + 32 B hit record,
-          counted by the CPU oracle in reference traversal order for the exact ray set) / render-kernel time,
-          against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+* roofline : the traversal kernel k_trace_sm (closest-hit launches over camera rays + any-hit launches over shadow
+          rays; per-instantiation breakdown under roofline.kernels).  achieved = algorithmic bytes per launch
+          (64 B/node popped + 88 B/triangle tested + 48 B ray + 32 B hit record, counted by the CPU oracle in
+          reference traversal order for the exact ray set; a shadow ray counts as the closest-hit Traverse that
+          defines its oracle) / average launch duration, timed with CUDA events around every launch on the
+          scene's stream inside the timed region (mb200_scene_timing), against the measured HBM copy bandwidth
+          in MEASURED_PEAKS.json.  traffic = ncu dram read+write bytes per launch (profiles/r1_traffic.json).
 * cpu_baseline : the unmodified reference (oracle/_ref) tracing a sample of the same ray set on the host cores.
 * --impl reference : times the reference's own OpenMP CPU path on the same workload (rank 0 only).
 """
@@ -136,14 +140,16 @@ class CpuSide:
 
     def algorithmic_bytes(self, passes):
         """sum over all rays of 64*N_node + 88*N_tri + 48 + 32 (SURVEY.md §8d / BASELINE.md §3)."""
-        tot = dict(rays=0, n_node=0, n_tri=0, shadow=0)
+        tot = dict(rays=0, n_node=0, n_tri=0, shadow=0, shadow_n_node=0, shadow_n_tri=0)
         for k in passes:
             _, _, info = self.bvh.render_pass(self.frame, W, H, rng_mode=1, pass_index=k, shader=1, light=LIGHT)
             tot["rays"] += info["trace_calls"] + info["shadow_rays"]
             tot["shadow"] += info["shadow_rays"]
-            tot["n_node"] += info["n_node"]
-            tot["n_tri"] += info["n_tri"]
+            for key in ("n_node", "n_tri", "shadow_n_node", "shadow_n_tri"):
+                tot[key] += info[key]
         tot["bytes"] = 64 * tot["n_node"] + 88 * tot["n_tri"] + 80 * tot["rays"]
+        tot["shadow_bytes"] = 64 * tot["shadow_n_node"] + 88 * tot["shadow_n_tri"] + 80 * tot["shadow"]
+        tot["camera_bytes"] = tot["bytes"] - tot["shadow_bytes"]
         return tot
 
     def trace_seconds(self, rays, repeat=1):
@@ -191,7 +197,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the oracle legs (roofline bytes + cpu_baseline)")
@@ -264,6 +270,7 @@ def main():
     for _ in range(args.warmup):
         step_device()
     barrier()
+    sc.timing(True)                        # CUDA events around every kernel the scene launches
     launches0 = M.capi.launches_issued()
     sampler = ClockSampler(local_rank)
     evs = []
@@ -280,12 +287,17 @@ def main():
     barrier()
     clocks = sampler.stop()
     launches = M.capi.launches_issued() - launches0
+    kt = sc.kernel_times()
+    sc.timing(False)
     step_ms = [a.elapsed_time(c) for a, _, c in evs]
     kern_ms = [a.elapsed_time(b) for a, b, _ in evs]
-    total_ms = torch.tensor([sum(step_ms), float(np.mean(kern_ms))], dtype=torch.float64, device="cuda")
+    total_ms = torch.tensor([sum(step_ms), float(np.mean(kern_ms)), kt["camera_trace_ms"], kt["shadow_trace_ms"],
+                             kt["shade_ms"], kt["resolve_ms"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms_max, kern_ms_max = float(total_ms[0]), float(total_ms[1])
+    cam_ms, shd_ms, shade_ms, resolve_ms = (float(x) for x in total_ms[2:6])       # totals over the timed steps
+    cam_n, shd_n = int(kt["camera_trace_launches"]), int(kt["shadow_trace_launches"])
     value = rays_frame * args.steps / (total_ms_max * 1e-3) / 1e6
 
     # ------------------------------------------------------------------ e2e: host buffers through the C ABI
@@ -331,13 +343,43 @@ def main():
         cpu = CpuSide(v, f)
         alg = cpu.algorithmic_bytes(range(SPP))
         assert alg["rays"] == rays_frame, (alg["rays"], rays_frame)
-        bytes_launch = alg["bytes"] / world        # one render launch per rank covers 1/world of the bands
-        achieved = bytes_launch / (kern_ms_max * 1e-3) / 1e9
+        # every rank renders 1/world of the row bands; per-launch bytes = the frame's bytes / launches per frame
+        per_frame = {"camera": alg["camera_bytes"] / world, "shadow": alg["shadow_bytes"] / world}
+        traffic = {}
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tp) and world == 1:
+            with open(tp) as fp:
+                traffic = json.load(fp)
+        kernels = []
+        for name, ms, n, inst in (("camera", cam_ms, cam_n, "k_trace_sm<IOCamera, closest-hit> (raygen fused)"),
+                                  ("shadow", shd_ms, shd_n, "k_trace_sm<IOQueueShadow, any-hit>")):
+            if n == 0:
+                continue
+            b = per_frame[name] * args.steps / n
+            a = b / (ms / n * 1e-3) / 1e9
+            kernels.append({"kernel": inst, "launches_per_step": n / args.steps, "ms_per_launch": ms / n,
+                            "algorithmic_bytes_per_launch": b, "achieved": a, "frac": a / peak,
+                            "traffic": traffic.get(name + "_trace_dram_bytes_per_launch")})
+        trace_ms, trace_n = cam_ms + shd_ms, cam_n + shd_n
+        bytes_launch = (per_frame["camera"] + per_frame["shadow"]) * args.steps / trace_n
+        achieved = bytes_launch / (trace_ms / trace_n * 1e-3) / 1e9
+        tr = [k["traffic"] for k in kernels]
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "kernel": "k_render (raygen + closest-hit + shadow + shade)",
-                    "kernel_ms": kern_ms_max, "algorithmic_bytes_per_launch": bytes_launch,
+                    "traffic": (sum(t * k["launches_per_step"] for t, k in zip(tr, kernels)) /
+                                sum(k["launches_per_step"] for k in kernels)) if all(tr) and tr else None,
+                    "peak_source": peak_src,
+                    "kernel": "k_trace_sm (persistent-warp BVH traversal state machine): all launches of a step",
+                    "launches_per_step": trace_n / args.steps, "ms_per_launch": trace_ms / trace_n,
+                    "algorithmic_bytes_per_launch": bytes_launch, "kernels": kernels,
+                    "step_share": {"trace": trace_ms / args.steps / (total_ms_max / args.steps),
+                                   "shade": shade_ms / args.steps / (total_ms_max / args.steps),
+                                   "resolve": resolve_ms / args.steps / (total_ms_max / args.steps)},
                     "bytes_per_ray": alg["bytes"] / alg["rays"],
-                    "nodes_per_ray": alg["n_node"] / alg["rays"], "tris_per_ray": alg["n_tri"] / alg["rays"]}
+                    "nodes_per_ray": alg["n_node"] / alg["rays"], "tris_per_ray": alg["n_tri"] / alg["rays"],
+                    "camera_nodes_per_ray": (alg["n_node"] - alg["shadow_n_node"]) / (alg["rays"] - alg["shadow"]),
+                    "camera_tris_per_ray": (alg["n_tri"] - alg["shadow_n_tri"]) / (alg["rays"] - alg["shadow"]),
+                    "shadow_nodes_per_ray": alg["shadow_n_node"] / max(1, alg["shadow"]),
+                    "shadow_tris_per_ray": alg["shadow_n_tri"] / max(1, alg["shadow"])}
         if world == 1:
             sample_passes = 4
             rays = np.concatenate([cpu.pass_rays(k)[0] for k in range(sample_passes)], axis=0)

@@ -196,6 +196,18 @@ int mb200_scene_device(const mb200_scene *scene);
  * fp32 triangle records are in use (still widened to double before any arithmetic). */
 int mb200_scene_uses_f32_vertices(const mb200_scene *scene);
 
+/* Per-kernel device timing (monitoring; what the reference's timerutil around Render() is to the CPU path,
+ * render.cc:630-707, at kernel granularity).  While enabled, every kernel the scene launches is bracketed by
+ * CUDA events on the scene's stream.  mb200_scene_kernel_times synchronises the stream, returns the
+ * milliseconds and launch counts accumulated since the last call (per kernel class) and resets them. */
+typedef struct {
+  double camera_trace_ms, shadow_trace_ms, bounce_trace_ms, shade_ms, resolve_ms, query_trace_ms;
+  uint64_t camera_trace_launches, shadow_trace_launches, bounce_trace_launches, shade_launches, resolve_launches,
+      query_trace_launches;
+} mb200_kernel_times;
+int mb200_scene_timing(mb200_scene *scene, int enable);
+int mb200_scene_kernel_times(mb200_scene *scene, mb200_kernel_times *out);
+
 /* -------------------------------------------------------------------------
  * Queries: replace bool Scene::Trace(Intersection&, Ray&) (scene.cc:253-315) ->
  * BVHAccel::Traverse (bvh_accel.cc:773-844), batched.

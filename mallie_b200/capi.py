@@ -34,6 +34,7 @@ EXPORTS = [
     "mb200_bvh_stats", "mb200_bvh_destroy",
     "mb200_scene_create", "mb200_scene_destroy", "mb200_scene_bounds", "mb200_scene_device_bytes",
     "mb200_scene_stream", "mb200_scene_device", "mb200_scene_uses_f32_vertices", "mb200_scene_synchronize",
+    "mb200_scene_timing", "mb200_scene_kernel_times",
     "mb200_trace_closest", "mb200_trace_closest_full", "mb200_trace_occluded", "mb200_trace_closest_async",
     "mb200_camera_frame_build", "mb200_generate_rays", "mb200_generate_rays_grid",
     "mb200_render_params_default", "mb200_plane_from_bounds", "mb200_render_pass", "mb200_render_accumulate",
@@ -94,6 +95,16 @@ class Config(C.Structure):
                 ("num_gpus", C.c_int)]
 
 
+class KernelTimes(C.Structure):
+    _fields_ = [(k + "_ms", C.c_double) for k in ("camera_trace", "shadow_trace", "bounce_trace", "shade", "resolve",
+                                                  "query_trace")] + \
+               [(k + "_launches", C.c_uint64) for k in ("camera_trace", "shadow_trace", "bounce_trace", "shade",
+                                                        "resolve", "query_trace")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class MallieB200Error(RuntimeError):
     pass
 
@@ -139,6 +150,8 @@ def lib():
         L.mb200_scene_device.argtypes = [vp]
         L.mb200_scene_uses_f32_vertices.argtypes = [vp]
         L.mb200_scene_synchronize.argtypes = [vp]
+        L.mb200_scene_timing.argtypes = [vp, i32]
+        L.mb200_scene_kernel_times.argtypes = [vp, C.POINTER(KernelTimes)]
         L.mb200_trace_closest.argtypes = [vp, vp, sz, vp, C.POINTER(Counters)]
         L.mb200_trace_closest_full.argtypes = [vp, vp, sz, vp, vp]
         L.mb200_trace_occluded.argtypes = [vp, vp, vp, sz, vp, C.POINTER(Counters)]
@@ -344,6 +357,16 @@ class Scene:
 
     def synchronize(self):
         check(lib().mb200_scene_synchronize(self.h))
+
+    def timing(self, enable=True):
+        """Bracket every kernel this scene launches with CUDA events (mb200_scene_timing)."""
+        check(lib().mb200_scene_timing(self.h, int(enable)))
+
+    def kernel_times(self):
+        """ms and launch counts per kernel class since the last call (synchronises the stream)."""
+        kt = KernelTimes()
+        check(lib().mb200_scene_kernel_times(self.h, C.byref(kt)))
+        return kt.as_dict()
 
     # -- queries (numpy in / numpy out, or raw device pointers as ints)
     @staticmethod

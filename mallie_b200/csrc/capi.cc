@@ -288,6 +288,33 @@ void *mb200_scene_stream(const mb200_scene *scene) { return scene ? (void *)scen
 int mb200_scene_device(const mb200_scene *scene) { return scene ? scene->device : -1; }
 int mb200_scene_uses_f32_vertices(const mb200_scene *scene) { return scene ? scene->view.tri_f32 : 0; }
 
+int mb200_scene_timing(mb200_scene *scene, int enable) {
+  if (!scene) return set_err(MB200_ERR_INVALID_ARG, "null scene");
+  CU(cudaSetDevice(scene->device));
+  CU(cudaStreamSynchronize(scene->stream));
+  double ms[mb200::kKClasses] = {0};
+  unsigned long long n[mb200::kKClasses] = {0};
+  scene->timer.collect(ms, n); // drop what was pending
+  scene->timer.enabled = enable != 0;
+  return MB200_OK;
+}
+
+int mb200_scene_kernel_times(mb200_scene *scene, mb200_kernel_times *out) {
+  if (!scene || !out) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  CU(cudaSetDevice(scene->device));
+  CU(cudaStreamSynchronize(scene->stream));
+  double ms[mb200::kKClasses] = {0};
+  unsigned long long n[mb200::kKClasses] = {0};
+  scene->timer.collect(ms, n);
+  out->camera_trace_ms = ms[mb200::kKCameraTrace], out->camera_trace_launches = n[mb200::kKCameraTrace];
+  out->shadow_trace_ms = ms[mb200::kKShadowTrace], out->shadow_trace_launches = n[mb200::kKShadowTrace];
+  out->bounce_trace_ms = ms[mb200::kKBounceTrace], out->bounce_trace_launches = n[mb200::kKBounceTrace];
+  out->shade_ms = ms[mb200::kKShade], out->shade_launches = n[mb200::kKShade];
+  out->resolve_ms = ms[mb200::kKResolve], out->resolve_launches = n[mb200::kKResolve];
+  out->query_trace_ms = ms[mb200::kKQueryTrace], out->query_trace_launches = n[mb200::kKQueryTrace];
+  return MB200_OK;
+}
+
 int mb200_scene_synchronize(mb200_scene *scene) {
   if (!scene) return set_err(MB200_ERR_INVALID_ARG, "scene is null");
   CU(cudaSetDevice(scene->device));
@@ -300,7 +327,7 @@ int mb200_trace_closest_async(mb200_scene *s, const mb200_ray *d_rays, size_t n,
   if (!s || (n && (!d_rays || !d_hits))) return set_err(MB200_ERR_INVALID_ARG, "null argument");
   if (n == 0) return MB200_OK;
   CU(cudaSetDevice(s->device));
-  CU(mb200::launch_trace_closest(s->view, s->stack_cap, d_rays, n, d_hits, s->d_work, nullptr, s->stream));
+  CU(mb200::launch_trace_closest(s->view, s->stack_cap, d_rays, n, d_hits, s->d_work, nullptr, s->stream, &s->timer));
   return MB200_OK;
 }
 
@@ -317,7 +344,7 @@ int mb200_trace_closest(mb200_scene *s, const mb200_ray *rays, size_t n, mb200_h
   if ((rc = stage_out_begin(s->out0, hits, n * sizeof(mb200_hit), &d_hits, &staged)) != MB200_OK) return rc;
   if (counters) CU(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream));
   CU(mb200::launch_trace_closest(s->view, s->stack_cap, (const mb200_ray *)d_rays, n, (mb200_hit *)d_hits, s->d_work,
-                                 counters ? s->d_counters : nullptr, s->stream));
+                                 counters ? s->d_counters : nullptr, s->stream, &s->timer));
   if (staged && (rc = stage_out_enqueue(s, s->out0, n * sizeof(mb200_hit))) != MB200_OK) return rc;
   if (counters) {
     unsigned long long c[4];
@@ -345,7 +372,7 @@ int mb200_trace_closest_full(mb200_scene *s, const mb200_ray *rays, size_t n, mb
   CU(mb200::frame_scratch_reserve(s->hit_scratch, n * sizeof(mb200_hit), s->stream));
   mb200_hit *d_hits = (mb200_hit *)s->hit_scratch.base;
   CU(mb200::launch_trace_closest(s->view, s->stack_cap, (const mb200_ray *)d_rays, n, d_hits, s->d_work, nullptr,
-                                 s->stream));
+                                 s->stream, &s->timer));
   CU(mb200::launch_build_isects(s->view, (const mb200_ray *)d_rays, d_hits, n, (mb200_isect *)d_is,
                                 (unsigned char *)d_mask, s->stream));
   if (st_is && (rc = stage_out_enqueue(s, s->out0, n * sizeof(mb200_isect))) != MB200_OK) return rc;
@@ -371,7 +398,8 @@ int mb200_trace_occluded(mb200_scene *s, const mb200_ray *rays, const double *tm
   if ((rc = stage_out_begin(s->out0, occluded, n, &d_occ, &staged)) != MB200_OK) return rc;
   if (counters) CU(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream));
   CU(mb200::launch_trace_occluded(s->view, s->stack_cap, (const mb200_ray *)d_rays, (const double *)d_tmax, n,
-                                  (unsigned char *)d_occ, s->d_work, counters ? s->d_counters : nullptr, s->stream));
+                                  (unsigned char *)d_occ, s->d_work, counters ? s->d_counters : nullptr, s->stream,
+                                  &s->timer));
   if (staged && (rc = stage_out_enqueue(s, s->out0, n)) != MB200_OK) return rc;
   if (counters) {
     unsigned long long c[4];
@@ -491,7 +519,7 @@ static int render_common(mb200_scene *s, const mb200_render_params *p, int num_p
   }
   if (stats) CU(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream));
   CU(mb200::launch_frame(s->view, s->stack_cap, *p, num_passes, mode, d_img, d_cnt, s->frame_scratch,
-                         stats ? s->d_counters : nullptr, s->stream));
+                         stats ? s->d_counters : nullptr, s->stream, &s->timer));
   if (img_kind != kDevice)
     CU(cudaMemcpyAsync(img_kind == kPinned ? (void *)image : s->out0.pinned, d_img, img_bytes, cudaMemcpyDeviceToHost,
                        s->stream));

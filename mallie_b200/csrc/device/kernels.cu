@@ -481,25 +481,85 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int launches_issued() { return g_launches; }
 
+// ---------------------------------------------------------------------------
+// KernelTimer
+// ---------------------------------------------------------------------------
+void KernelTimer::begin(int cls, cudaStream_t s) {
+  if (!enabled) return;
+  Span sp;
+  sp.cls = cls;
+  for (cudaEvent_t *e : {&sp.a, &sp.b}) {
+    if (!pool.empty()) {
+      *e = pool.back();
+      pool.pop_back();
+    } else if (cudaEventCreate(e) != cudaSuccess) {
+      enabled = false;
+      return;
+    }
+  }
+  cudaEventRecord(sp.a, s);
+  spans.push_back(sp);
+}
+
+void KernelTimer::end(cudaStream_t s) {
+  if (!enabled || spans.empty()) return;
+  cudaEventRecord(spans.back().b, s);
+}
+
+void KernelTimer::collect(double ms[kKClasses], unsigned long long launches[kKClasses]) {
+  for (const Span &sp : spans) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess && sp.cls >= 0 && sp.cls < kKClasses) {
+      ms[sp.cls] += (double)t;
+      launches[sp.cls]++;
+    }
+    pool.push_back(sp.a);
+    pool.push_back(sp.b);
+  }
+  spans.clear();
+}
+
+void KernelTimer::release() {
+  for (const Span &sp : spans) cudaEventDestroy(sp.a), cudaEventDestroy(sp.b);
+  for (cudaEvent_t e : pool) cudaEventDestroy(e);
+  spans.clear();
+  pool.clear();
+}
+
+namespace {
+struct TimedScope { // brackets one kernel launch
+  KernelTimer *t;
+  cudaStream_t s;
+  TimedScope(KernelTimer *timer, int cls, cudaStream_t stream) : t(timer), s(stream) {
+    if (t) t->begin(cls, s);
+  }
+  ~TimedScope() {
+    if (t) t->end(s);
+  }
+};
+} // namespace
+
 int band_rows_owned(int rows, int band_rows, int count, int index) {
   return band_local_rows(rows, band_rows, count, index);
 }
 
 cudaError_t launch_trace_closest(const SceneView &sc, int stack_cap, const mb200_ray *rays, size_t n,
                                  mb200_hit *hits, unsigned long long *work, unsigned long long *counters,
-                                 cudaStream_t s) {
+                                 cudaStream_t s, KernelTimer *timer) {
   cudaError_t e = cudaMemsetAsync(work, 0, sizeof(unsigned long long), s);
   if (e != cudaSuccess) return e;
   const IOClosest io{rays, hits};
+  TimedScope ts(timer, kKQueryTrace, s);
   return launch_trace<IOClosest, false>(sc, stack_cap, io, n, nullptr, work, counters, s);
 }
 
 cudaError_t launch_trace_occluded(const SceneView &sc, int stack_cap, const mb200_ray *rays, const double *tmax,
                                   size_t n, unsigned char *occ, unsigned long long *work,
-                                  unsigned long long *counters, cudaStream_t s) {
+                                  unsigned long long *counters, cudaStream_t s, KernelTimer *timer) {
   cudaError_t e = cudaMemsetAsync(work, 0, sizeof(unsigned long long), s);
   if (e != cudaSuccess) return e;
   const IOOccluded io{rays, tmax, occ};
+  TimedScope ts(timer, kKQueryTrace, s);
   return launch_trace<IOOccluded, true>(sc, stack_cap, io, n, nullptr, work, counters, s);
 }
 
@@ -561,7 +621,8 @@ static size_t batch_item_budget() {
 }
 
 cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_params &p, int num_passes, int mode,
-                         float *image, int *count, FrameScratch &scratch, unsigned long long *stats, cudaStream_t s) {
+                         float *image, int *count, FrameScratch &scratch, unsigned long long *stats, cudaStream_t s,
+                         KernelTimer *timer) {
   const FrameMap m0 = make_frame_map(p, p.pass, 1);
   const size_t tiles = frame_map_tiles(m0);
   if (tiles == 0 || num_passes < 1) return cudaSuccess;
@@ -604,19 +665,32 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
 
     // camera rays: K1 fused into K2
     const IOCamera cam{p, m, hits};
-    if ((e = launch_trace_nocount<IOCamera, false>(sc, stack_cap, cam, items, nullptr, work + 0, s)) != cudaSuccess) return e;
-    k_shade_primary<<<(items + 255) / 256, 256, 0, s>>>(sc, p, m, items, hits, contrib, queue[0], qcount + 0, states, bstats);
+    {
+      TimedScope ts(timer, kKCameraTrace, s);
+      e = launch_trace_nocount<IOCamera, false>(sc, stack_cap, cam, items, nullptr, work + 0, s);
+    }
+    if (e != cudaSuccess) return e;
+    {
+      TimedScope ts(timer, kKShade, s);
+      k_shade_primary<<<(items + 255) / 256, 256, 0, s>>>(sc, p, m, items, hits, contrib, queue[0], qcount + 0, states, bstats);
+    }
     g_launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
     if (shadow) {
       const IOQueueShadow io{queue[0], contrib};
+      TimedScope ts(timer, kKShadowTrace, s);
       if ((e = launch_trace_nocount<IOQueueShadow, true>(sc, stack_cap, io, 0, qcount + 0, work + 1, s)) != cudaSuccess) return e;
     } else if (path) {
       for (int len = 2; len <= p.max_path_length; len++) {
         const int qi = len & 1; // segment `len` reads queue[qi], writes queue[qi ^ 1]
         const IOQueueClosest io{queue[qi], hits};
-        if ((e = launch_trace_nocount<IOQueueClosest, false>(sc, stack_cap, io, 0, qcount + (len - 2), work + (len - 1), s)) != cudaSuccess) return e;
+        {
+          TimedScope ts(timer, kKBounceTrace, s);
+          e = launch_trace_nocount<IOQueueClosest, false>(sc, stack_cap, io, 0, qcount + (len - 2), work + (len - 1), s);
+        }
+        if (e != cudaSuccess) return e;
+        TimedScope ts(timer, kKShade, s);
         k_shade_bounce<<<num_sms() * 8, 256, 0, s>>>(sc, p, (unsigned int)len, queue[qi], qcount + (len - 2), hits, queue[qi ^ 1],
                                                      qcount + (len - 1), states, contrib, bstats);
         g_launches++;
@@ -626,7 +700,10 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
 
     int bmode = mode;
     if (mode == 2 && done > 0) bmode = 1;
-    k_resolve<<<(unsigned)((tiles * 32 + 255) / 256), 256, 0, s>>>(m, (uint32_t)tiles, bmode, contrib, image, count);
+    {
+      TimedScope ts(timer, kKResolve, s);
+      k_resolve<<<(unsigned)((tiles * 32 + 255) / 256), 256, 0, s>>>(m, (uint32_t)tiles, bmode, contrib, image, count);
+    }
     g_launches++;
     if (stats) {
       k_add_stats<<<1, 32, 0, s>>>(bstats, shadow ? qcount : nullptr, stats);

@@ -5,19 +5,39 @@
 
 #include <cuda_runtime_api.h>
 
+#include <vector>
+
 #include "layout.h"
 #include "mallie_b200.h"
 
 namespace mb200 {
 
+// Optional per-kernel timing: CUDA events recorded on the launching stream around every kernel of a
+// class (bench.py's roofline leg: the duration of the traversal kernels inside the timed region).
+enum KernelClass { kKCameraTrace = 0, kKShadowTrace, kKBounceTrace, kKShade, kKResolve, kKQueryTrace, kKClasses };
+struct KernelTimer {
+  bool enabled = false;
+  struct Span {
+    int cls;
+    cudaEvent_t a, b;
+  };
+  std::vector<Span> spans;        // recorded, not yet collected
+  std::vector<cudaEvent_t> pool;  // recycled events
+  void begin(int cls, cudaStream_t s);
+  void end(cudaStream_t s);
+  // After the stream has been synchronised: adds every span's elapsed ms / launch to the arrays, recycles events.
+  void collect(double ms[kKClasses], unsigned long long launches[kKClasses]);
+  void release();
+};
+
 // `work` is an 8-byte device scratch word (persistent-warp work counter, reset by the launcher);
 // `counters` (nullable) is unsigned long long[4]: nodes, tris, rays, max stack (accumulated).
 cudaError_t launch_trace_closest(const SceneView &sc, int stack_cap, const mb200_ray *rays, size_t n,
                                  mb200_hit *hits, unsigned long long *work, unsigned long long *counters,
-                                 cudaStream_t s);
+                                 cudaStream_t s, KernelTimer *timer = nullptr);
 cudaError_t launch_trace_occluded(const SceneView &sc, int stack_cap, const mb200_ray *rays, const double *tmax,
                                   size_t n, unsigned char *occluded, unsigned long long *work,
-                                  unsigned long long *counters, cudaStream_t s);
+                                  unsigned long long *counters, cudaStream_t s, KernelTimer *timer = nullptr);
 // K3: BuildIntersection for every ray from its 32-byte hit record (mask nullable).
 cudaError_t launch_build_isects(const SceneView &sc, const mb200_ray *rays, const mb200_hit *hits, size_t n,
                                 mb200_isect *isects, unsigned char *mask, cudaStream_t s);
@@ -42,7 +62,8 @@ void frame_scratch_release(FrameScratch &fs);
 // mode 2: image = sum of passes, count = passes (fresh frame; nothing read)
 // stats: device unsigned long long[4] primary, bounce, shadow, zombie (accumulated).
 cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_params &p, int num_passes, int mode,
-                         float *image, int *count, FrameScratch &scratch, unsigned long long *stats, cudaStream_t s);
+                         float *image, int *count, FrameScratch &scratch, unsigned long long *stats, cudaStream_t s,
+                         KernelTimer *timer = nullptr);
 
 // Rows owned by one band index (see mb200_render_params::band_rows).
 int band_rows_owned(int rows, int band_rows, int count, int index);

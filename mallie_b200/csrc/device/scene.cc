@@ -263,6 +263,7 @@ void scene_destroy(mb200_scene *s) {
     if (st->pinned) cudaFreeHost(st->pinned);
     if (st->dev) cudaFree(st->dev);
   }
+  s->timer.release();
   frame_scratch_release(s->frame_scratch);
   frame_scratch_release(s->hit_scratch);
   if (s->stream) cudaStreamDestroy(s->stream);

@@ -35,6 +35,9 @@ struct mb200_scene {
 
   // device scratch: the frame wavefront's buffers, and hit records of mb200_trace_closest_full
   mb200::FrameScratch frame_scratch, hit_scratch;
+
+  // per-kernel timing (mb200_scene_timing / mb200_scene_kernel_times)
+  mb200::KernelTimer timer;
 };
 
 namespace mb200 {

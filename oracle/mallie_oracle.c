@@ -884,7 +884,7 @@ static const double kFar = 1.0e+30;      /* render.cc:50 */
  * post-escape segments -- which can never hit -- are not traced; their
  * contribution throughput*0.5/pathLength is accumulated in the same order. */
 static v3 path_trace(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, ora_rng *rng, int px,
-                     int py, uint64_t cnt[5]) {
+                     int py, uint64_t cnt[7]) {
   float ju = (float)(ora_randomreal(rng) - 0.5);
   float jv = (float)(ora_randomreal(rng) - 0.5);
   double ray[6];
@@ -947,7 +947,7 @@ static v3 path_trace(const ora_bvh *b, const ora_mesh *mesh, const ora_render_pa
  * empty (render.cc:425-426), defined in DESIGN.md §"primary+shadow".  One closest-hit
  * primary ray; on a hit, one occlusion ray towards the point light. */
 static v3 primary_shadow(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, ora_rng *rng, int px,
-                         int py, uint64_t cnt[5], double *primary_out, double *shadow_out) {
+                         int py, uint64_t cnt[7], double *primary_out, double *shadow_out) {
   float ju = (float)(ora_randomreal(rng) - 0.5);
   float jv = (float)(ora_randomreal(rng) - 0.5);
   double ray[6];
@@ -979,9 +979,12 @@ static v3 primary_shadow(const ora_bvh *b, const ora_mesh *mesh, const ora_rende
   memset(&sh, 0, sizeof(sh));
   cnt[2]++;
   if (shadow_out) { memcpy(shadow_out, sray, sizeof(sray)); shadow_out[6] = tmax; }
+  const uint64_t pn = tc[0], pt = tc[1]; /* the camera ray's share */
   int occ = ora_traverse(b, mesh, sray, sray + 3, &sh, tc) && sh.t < tmax;
   cnt[3] += tc[0];
   cnt[4] += tc[1];
+  cnt[5] += tc[0] - pn; /* the shadow ray's own node / triangle counts */
+  cnt[6] += tc[1] - pt;
   double ndotl = v3_dot(n, ld);
   if (occ || !(ndotl > 0.0)) return v3_make(0.0, 0.0, 0.0);
   double kd = (is.material_id != (uint32_t)-1) ? 0.5 : 1.0;
@@ -991,7 +994,7 @@ static v3 primary_shadow(const ora_bvh *b, const ora_mesh *mesh, const ora_rende
 
 /* One pixel sample with either shader. */
 static v3 shade_pixel(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, ora_rng *rng, int x, int y,
-                      uint64_t c[5], double *primary_out, double *shadow_out) {
+                      uint64_t c[7], double *primary_out, double *shadow_out) {
   if (p->shader == 0) return path_trace(b, mesh, p, rng, x, y, c);
   return primary_shadow(b, mesh, p, rng, x, y, c, primary_out, shadow_out);
 }
@@ -1000,10 +1003,10 @@ static v3 shade_pixel(const ora_bvh *b, const ora_mesh *mesh, const ora_render_p
  * primary_rays_out (nullable, shader 1): [6*W*H] the jittered camera rays; shadow_rays_out (nullable):
  * [7*W*H] org, dir, tmax of each shadow ray (NaN-filled where the primary ray missed). */
 void ora_render_pass_ex(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, int x0, int y0, int x1,
-                        int y1, float *image, int *count, uint64_t ray_counts[5], int nthreads,
+                        int y1, float *image, int *count, uint64_t ray_counts[7], int nthreads,
                         double *primary_rays_out, double *shadow_rays_out) {
   const int W = p->width;
-  uint64_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+  uint64_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0;
   if (shadow_rays_out)
     for (size_t i = 0; i < (size_t)7 * W * p->height; i++) shadow_rays_out[i] = NAN;
   if (p->rng_mode == 0) {
@@ -1014,7 +1017,7 @@ void ora_render_pass_ex(const ora_bvh *b, const ora_mesh *mesh, const ora_render
     ora_rng_seed_reference(&rng, 0);
     for (int y = y0; y < y1; y++)
       for (int x = x0; x < x1; x++) {
-        uint64_t c[5] = {0, 0, 0, 0, 0};
+        uint64_t c[7] = {0, 0, 0, 0, 0, 0, 0};
         size_t pix = (size_t)y * W + x;
         v3 r = shade_pixel(b, mesh, p, &rng, x, y, c, primary_rays_out ? primary_rays_out + 6 * pix : NULL,
                            shadow_rays_out ? shadow_rays_out + 7 * pix : NULL);
@@ -1022,35 +1025,36 @@ void ora_render_pass_ex(const ora_bvh *b, const ora_mesh *mesh, const ora_render
         image[3 * pix + 1] = (float)r.y;
         image[3 * pix + 2] = (float)r.z;
         count[pix]++;
-        c0 += c[0]; c1 += c[1]; c2 += c[2]; c3 += c[3]; c4 += c[4];
+        c0 += c[0]; c1 += c[1]; c2 += c[2]; c3 += c[3]; c4 += c[4]; c5 += c[5]; c6 += c[6];
       }
   } else {
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
-#pragma omp parallel for schedule(dynamic, 1) reduction(+ : c0, c1, c2, c3, c4)
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : c0, c1, c2, c3, c4, c5, c6)
     for (int y = y0; y < y1; y++)
       for (int x = x0; x < x1; x++) {
         ora_rng rng;
         size_t pix = (size_t)y * W + x;
         ora_rng_seed_pixel(&rng, (uint32_t)pix, p->pass);
-        uint64_t c[5] = {0, 0, 0, 0, 0};
+        uint64_t c[7] = {0, 0, 0, 0, 0, 0, 0};
         v3 r = shade_pixel(b, mesh, p, &rng, x, y, c, primary_rays_out ? primary_rays_out + 6 * pix : NULL,
                            shadow_rays_out ? shadow_rays_out + 7 * pix : NULL);
         image[3 * pix + 0] = (float)r.x;
         image[3 * pix + 1] = (float)r.y;
         image[3 * pix + 2] = (float)r.z;
         count[pix]++;
-        c0 += c[0]; c1 += c[1]; c2 += c[2]; c3 += c[3]; c4 += c[4];
+        c0 += c[0]; c1 += c[1]; c2 += c[2]; c3 += c[3]; c4 += c[4]; c5 += c[5]; c6 += c[6];
       }
   }
   if (ray_counts) {
     ray_counts[0] += c0; ray_counts[1] += c1; ray_counts[2] += c2; ray_counts[3] += c3; ray_counts[4] += c4;
+    ray_counts[5] += c5; ray_counts[6] += c6;
   }
 }
 
 void ora_render_pass(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, int x0, int y0, int x1,
-                     int y1, float *image, int *count, uint64_t ray_counts[5], int nthreads) {
+                     int y1, float *image, int *count, uint64_t ray_counts[7], int nthreads) {
   ora_render_pass_ex(b, mesh, p, x0, y0, x1, y1, image, count, ray_counts, nthreads, NULL, NULL);
 }
 

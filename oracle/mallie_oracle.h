@@ -122,13 +122,14 @@ typedef struct {
 /* image: float[3*W*H] overwritten; count[W*H] incremented; x0..x1,y0..y1 tile (whole image: 0,0,W,H).
  * ray_counts (nullable, accumulated): [0] Trace calls for camera/bounce rays, [1] zombie segments,
  * [2] shadow rays, [3] nodes popped, [4] triangles tested over all those rays (reference traversal order;
- * shadow rays counted as the closest-hit Traverse that defines the occlusion oracle). */
+ * shadow rays counted as the closest-hit Traverse that defines the occlusion oracle), [5] / [6] the share
+ * of [3] / [4] that belongs to the shadow rays. */
 void ora_render_pass(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, int x0, int y0, int x1,
-                     int y1, float *image, int *count, uint64_t ray_counts[5], int nthreads);
+                     int y1, float *image, int *count, uint64_t ray_counts[7], int nthreads);
 /* Same, also emitting the exact ray set of the pass for the CPU-baseline timing (shader 1 only):
  * primary_rays_out [6*W*H]; shadow_rays_out [7*W*H] = org, dir, tmax (NaN where the camera ray missed). */
 void ora_render_pass_ex(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, int x0, int y0, int x1,
-                        int y1, float *image, int *count, uint64_t ray_counts[5], int nthreads,
+                        int y1, float *image, int *count, uint64_t ray_counts[7], int nthreads,
                         double *primary_rays_out, double *shadow_rays_out);
 
 /* --- misc ---------------------------------------------------------------- */

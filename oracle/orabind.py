@@ -206,13 +206,13 @@ class BVH:
         if count is None:
             count = np.zeros((height, width), np.int32)
         x0, y0, x1, y1 = tile if tile is not None else (0, 0, width, height)
-        rc = np.zeros(5, np.uint64)
+        rc = np.zeros(7, np.uint64)
         prim = np.zeros((height * width, 6)) if emit_rays else None
         shad = np.zeros((height * width, 7)) if emit_rays else None
         lib().ora_render_pass_ex(self.h, C.byref(self.mesh.c), C.byref(p), x0, y0, x1, y1, _p(image), _p(count),
                                  _p(rc), nthreads, _p(prim), _p(shad))
         info = dict(trace_calls=int(rc[0]), zombies=int(rc[1]), shadow_rays=int(rc[2]), n_node=int(rc[3]),
-                    n_tri=int(rc[4]))
+                    n_tri=int(rc[4]), shadow_n_node=int(rc[5]), shadow_n_tri=int(rc[6]))
         if emit_rays:
             info["primary_rays"] = prim
             ok = ~np.isnan(shad[:, 0])
