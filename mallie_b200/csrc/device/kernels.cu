@@ -25,11 +25,14 @@ namespace {
 constexpr int kBlock = 128; // threads per CTA of the traversal kernels
 
 // production configuration of the traversal state machine (A/B history: DESIGN.md §5)
-constexpr int kRefillMin = 4;   // idle lanes that trigger a refill
+// (measured on B200, 1 M-triangle scene, 1080p 16 spp primary+shadow frame; history in DESIGN.md §5:
+//  4/2/16/5/32/0 = 28.98 ms -> 8 CTAs per SM at 64 registers 26.98 -> + refill 8 26.08 -> + no prefetch 23.05)
+constexpr int kRefillMin = 8;   // idle lanes that trigger a refill
 constexpr int kPolicy = 2;      // both step bodies every iteration
-constexpr int kSmemStack = 16;  // stack entries per thread kept in shared memory
-constexpr int kMinBlocks = 5;   // resident CTAs per SM the register allocation targets
+constexpr int kSmemStack = 12;  // stack entries per thread kept in shared memory (24 KB per CTA)
+constexpr int kMinBlocks = 8;   // resident CTAs per SM the register allocation targets (64 registers)
 constexpr unsigned kChunk = 32; // ray indices per atomicAdd
+constexpr int kVar = 1 + 2 + 8; // wide node loads, sign mask, no software prefetch (trace_sm.cuh)
 
 __device__ __forceinline__ unsigned int lane_id() { return threadIdx.x & 31u; }
 
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(256) k_generate_grid(const __grid_constant__ m
 // K2 / K4: the persistent-warp traversal state machine (trace_sm.cuh) as a kernel.
 // n_dev (nullable): the ray count lives in device memory (a queue filled by the previous kernel).
 // ---------------------------------------------------------------------------
-template <class IO, bool F32, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int POLICY, int S, int MINB, unsigned CHUNK>
+template <class IO, bool F32, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int POLICY, int S, int MINB, unsigned CHUNK, int VAR>
 __global__ void __launch_bounds__(kBlock, MINB)
     k_trace_sm(const __grid_constant__ SceneView sc, const __grid_constant__ IO io, unsigned long long n,
                const unsigned int *__restrict__ n_dev, unsigned long long *__restrict__ work,
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__(kBlock, MINB)
   st.sm = smem_stack + threadIdx.x;
   st.stride = kBlock;
   if (n_dev) n = __ldg(n_dev);
-  trace_state_machine<IO, F32, S, CAP, ANYHIT, COUNT, REFILL_MIN, POLICY, CHUNK>(sc, io, n, work, st, gcounters);
+  trace_state_machine<IO, F32, S, CAP, ANYHIT, COUNT, REFILL_MIN, POLICY, CHUNK, VAR>(sc, io, n, work, st, gcounters);
 }
 
 // ---------------------------------------------------------------------------
@@ -397,21 +400,26 @@ int env_int(const char *name, int dflt) {
 }
 
 // One persistent wave: a whole number of CTAs per SM.
-template <class IO, bool F32, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int POLICY, int S, int MINB, unsigned CHUNK>
+template <class IO, bool F32, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int POLICY, int S, int MINB, unsigned CHUNK, int VAR>
 cudaError_t launch_sm(const SceneView &sc, const IO &io, size_t n, const unsigned int *n_dev,
                       unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
-  auto k = k_trace_sm<IO, F32, CAP, ANYHIT, COUNT, REFILL_MIN, POLICY, S, MINB, CHUNK>;
+  auto k = k_trace_sm<IO, F32, CAP, ANYHIT, COUNT, REFILL_MIN, POLICY, S, MINB, CHUNK, VAR>;
   const size_t smem = (size_t)S * kBlock * sizeof(uint4);
   static int grid = 0; // per instantiation
   if (grid == 0) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    // shared memory for MINB resident CTAs and no more: what is left of the SM's 256 KB stays L1, which
+    // is what the node / triangle fetches hit in
+    int carve = (int)((smem + 1024) * MINB * 100 / (228 * 1024)) + 1;
+    if (carve > 100) carve = 100;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kBlock, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
+    if (per_sm > MINB) per_sm = MINB;
     grid = num_sms() * per_sm;
   }
   k<<<grid, kBlock, smem, s>>>(sc, io, (unsigned long long)n, n_dev, work, counters);
@@ -424,20 +432,49 @@ cudaError_t launch_sm(const SceneView &sc, const IO &io, size_t n, const unsigne
 template <class IO, bool F32, int CAP, bool ANYHIT, bool COUNT>
 cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const unsigned int *n_dev,
                               unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
-#define MB200_SM(R, P, S, B, C) launch_sm<IO, F32, CAP, ANYHIT, COUNT, R, P, S, B, C>(sc, io, n, n_dev, work, counters, s)
+#define MB200_SM(R, P, S, B, C, V) launch_sm<IO, F32, CAP, ANYHIT, COUNT, R, P, S, B, C, V>(sc, io, n, n_dev, work, counters, s)
 #ifdef MB200_DEV_VARIANTS
   if (!COUNT && CAP <= 64) {
     static const int policy = env_int("MB200_TRACE_POLICY", kPolicy), occ = env_int("MB200_TRACE_OCC", kMinBlocks),
-                     chunk = env_int("MB200_TRACE_CHUNK", (int)kChunk), refill = env_int("MB200_TRACE_REFILL", kRefillMin);
-    if (policy == 0) return MB200_SM(4, 0, 16, 5, 32);
-    if (occ == 4) return MB200_SM(4, 2, 16, 4, 32);
-    if (occ == 6) return MB200_SM(4, 2, 16, 6, 32);
-    if (chunk == 64) return MB200_SM(4, 2, 16, 5, 64);
-    if (refill == 1) return MB200_SM(1, 2, 16, 5, 32);
-    if (refill == 8) return MB200_SM(8, 2, 16, 5, 32);
+                     chunk = env_int("MB200_TRACE_CHUNK", (int)kChunk), refill = env_int("MB200_TRACE_REFILL", kRefillMin),
+                     var = env_int("MB200_TRACE_VAR", kVar);
+    if (policy == 0) return MB200_SM(4, 0, 16, 5, 32, 0);
+    if (occ == 4) return MB200_SM(4, 2, 16, 4, 32, 0);
+    if (occ == 6) return MB200_SM(4, 2, 16, 6, 32, 0);
+    if (occ == 8) return MB200_SM(4, 2, 12, 8, 32, 0);
+    if (occ == 83) return MB200_SM(4, 2, 12, 8, 32, 3);
+    if (occ == 88) return MB200_SM(8, 2, 12, 8, 32, 3);
+    if (occ == 9) return MB200_SM(4, 2, 12, 9, 32, 3);
+    if (occ == 10) return MB200_SM(4, 2, 10, 10, 32, 3);
+    if (occ == 108) return MB200_SM(8, 2, 10, 10, 32, 3);
+    if (occ == 12) return MB200_SM(4, 2, 8, 12, 32, 3);
+    if (chunk == 64) return MB200_SM(4, 2, 16, 5, 64, 0);
+    if (refill == 1) return MB200_SM(1, 2, 16, 5, 32, 0);
+    if (refill == 8) return MB200_SM(8, 2, 16, 5, 32, 0);
+    // on top of refill 8 / 12 smem stack entries / 8 CTAs per SM / wide nodes + sign mask:
+    if (var == 3) return MB200_SM(8, 2, 12, 8, 32, 3);
+    if (var == 7) return MB200_SM(8, 2, 12, 8, 32, 3 + 4);
+    if (var == 11) return MB200_SM(8, 2, 12, 8, 32, 3 + 8);
+    if (var == 19) return MB200_SM(8, 2, 12, 8, 32, 3 + 16);
+    if (var == 35) return MB200_SM(8, 2, 12, 8, 32, 3 + 32);
+    if (var == 67) return MB200_SM(8, 2, 12, 8, 32, 3 + 64);
+    if (var == 87) return MB200_SM(8, 2, 12, 8, 32, 3 + 4 + 16 + 64);
+    if (var == 119) return MB200_SM(8, 2, 12, 8, 32, 3 + 4 + 16 + 32 + 64);
+    if (var == 123) return MB200_SM(8, 2, 12, 8, 32, 3 + 8 + 16 + 32 + 64);
+    // stack split between shared memory and (L1-cached) local memory, no prefetch
+    if (var == 1100) return MB200_SM(8, 2, 0, 8, 32, 11);
+    if (var == 1104) return MB200_SM(8, 2, 4, 8, 32, 11);
+    if (var == 1108) return MB200_SM(8, 2, 8, 8, 32, 11);
+    if (var == 1116) return MB200_SM(8, 2, 16, 8, 32, 11);
+    if (var == 1109) return MB200_SM(8, 2, 8, 9, 32, 11);
+    if (var == 1110) return MB200_SM(8, 2, 8, 10, 32, 11);
+    if (var == 1143) return MB200_SM(8, 2, 12, 8, 32, 11 + 32);
+    if (var == 1127) return MB200_SM(8, 2, 12, 8, 32, 11 + 16);
+    if (var == 1112) return MB200_SM(12, 2, 12, 8, 32, 11);
+    if (var == 1164) return MB200_SM(8, 2, 12, 8, 64, 11);
   }
 #endif
-  return MB200_SM(kRefillMin, kPolicy, kSmemStack, kMinBlocks, kChunk);
+  return MB200_SM(kRefillMin, kPolicy, kSmemStack, kMinBlocks, kChunk, kVar);
 #undef MB200_SM
 }
 

@@ -58,8 +58,18 @@ __device__ __forceinline__ void store_miss(mb200_hit *dst) { store_hit(dst, DBL_
 // ray: traversal is front to back) and overwrites the result in place, so u, v, faceID and
 // materialID never occupy registers between steps.  finish() ends the ray.
 
+// Every source also has a per-thread chunk context (empty unless the source can share work between the
+// rays of one 32-item chunk): prepare(ctx, base) is called by all lanes when the warp takes a new chunk.
+struct NoChunk {};
+
 // K2 over a caller's ray buffer (mb200_trace_closest).
 struct IOClosest {
+  typedef NoChunk Chunk;
+  __device__ __forceinline__ void prepare(Chunk &, uint32_t) const {}
+  __device__ __forceinline__ bool load(const Chunk &, uint32_t i, double &ox, double &oy, double &oz, double &dx,
+                                       double &dy, double &dz, double &t0) const {
+    return load(i, ox, oy, oz, dx, dy, dz, t0);
+  }
   const mb200_ray *rays;
   mb200_hit *hits;
   __device__ __forceinline__ bool load(uint32_t i, double &ox, double &oy, double &oz, double &dx, double &dy,
@@ -79,6 +89,12 @@ struct IOClosest {
 
 // K4 over a caller's ray buffer (mb200_trace_occluded).
 struct IOOccluded {
+  typedef NoChunk Chunk;
+  __device__ __forceinline__ void prepare(Chunk &, uint32_t) const {}
+  __device__ __forceinline__ bool load(const Chunk &, uint32_t i, double &ox, double &oy, double &oz, double &dx,
+                                       double &dy, double &dz, double &t0) const {
+    return load(i, ox, oy, oz, dx, dy, dz, t0);
+  }
   const mb200_ray *rays;
   const double *tmax;
   unsigned char *occluded;
@@ -98,6 +114,32 @@ struct IOOccluded {
 // the refill step -- Camera::GenerateRay (camera.cc:222-240) after PathTrace's jitter (render.cc:386-393)
 // -- and never stored; hits[i] receives the 32-byte record.
 struct IOCamera {
+  // (tile, pass) of the chunk the warp is drawing from: one decode (three integer divisions) per 32 rays
+  struct Chunk {
+    uint32_t group; // item >> 5 the fields below belong to (0xFFFFFFFF: none)
+    int x_tile, y_tile, rows_valid;
+    uint32_t pass;
+  };
+  __device__ __forceinline__ void prepare(Chunk &c, uint32_t base) const {
+    int x, y, rl;
+    item_pixel(m, base & ~31u, x, y, rl, c.pass); // lane 0 of the tile
+    c.group = base >> 5;
+    c.x_tile = x, c.y_tile = y;
+    c.rows_valid = m.rows_local - rl; // rows of this tile that exist (>= 1)
+  }
+  __device__ __forceinline__ bool load(const Chunk &c, uint32_t i, double &ox, double &oy, double &oz, double &dx,
+                                       double &dy, double &dz, double &t0) const {
+    if ((i >> 5) != c.group) return load(i, ox, oy, oz, dx, dy, dz, t0);
+    store_miss(hits + i);
+    const int lx = (int)(i & 7u), ly = (int)((i >> 3) & 3u);
+    const int x = c.x_tile + lx * m.step, y = c.y_tile + ly * m.step;
+    if (!(x < m.x1 && ly < c.rows_valid)) return false;
+    Xorshift128 rng;
+    camera_sample(p, x, y, c.pass, rng, dx, dy, dz);
+    ox = p.frame.origin[0], oy = p.frame.origin[1], oz = p.frame.origin[2];
+    t0 = DBL_MAX;
+    return true;
+  }
   mb200_render_params p;
   FrameMap m;
   mb200_hit *hits;
@@ -121,6 +163,12 @@ struct IOCamera {
 
 // K2 over a queue of path-continuation rays: hits[i] for queue slot i.
 struct IOQueueClosest {
+  typedef NoChunk Chunk;
+  __device__ __forceinline__ void prepare(Chunk &, uint32_t) const {}
+  __device__ __forceinline__ bool load(const Chunk &, uint32_t i, double &ox, double &oy, double &oz, double &dx,
+                                       double &dy, double &dz, double &t0) const {
+    return load(i, ox, oy, oz, dx, dy, dz, t0);
+  }
   const QRay *q;
   mb200_hit *hits;
   __device__ __forceinline__ bool load(uint32_t i, double &ox, double &oy, double &oz, double &dx, double &dy,
@@ -140,6 +188,12 @@ struct IOQueueClosest {
 
 // K4 over the queue of shadow rays: an unoccluded ray deposits its `value` into its sample's slot.
 struct IOQueueShadow {
+  typedef NoChunk Chunk;
+  __device__ __forceinline__ void prepare(Chunk &, uint32_t) const {}
+  __device__ __forceinline__ bool load(const Chunk &, uint32_t i, double &ox, double &oy, double &oz, double &dx,
+                                       double &dy, double &dz, double &t0) const {
+    return load(i, ox, oy, oz, dx, dy, dz, t0);
+  }
   const QRay *q;
   float *contrib; // [items]
   __device__ __forceinline__ bool load(uint32_t i, double &ox, double &oy, double &oz, double &dx, double &dy,
@@ -162,7 +216,65 @@ struct IOQueueShadow {
 // ---- the state machine ------------------------------------------------------------------------------
 // REFILL_MIN: idle lanes that trigger a refill; CHUNK: ray indices taken from the global counter per
 // atomicAdd (32 keeps the end-of-launch imbalance small: a launch of 2 M rays is only ~18 per lane).
-template <class IO, bool F32, int S, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int POLICY, unsigned CHUNK>
+// VAR: bit set of code-generation variants kept for A/B runs (development builds pick them with
+// MB200_TRACE_VAR; production value kVar in kernels.cu):
+//   1  PairNode fetched with four 256-bit loads (LDG.E.256) instead of seven 128-bit + one 32-bit
+//   2  near/far order from a 3-bit sign mask ((mask >> axis) & 1) instead of a select chain
+//   4  leaf prefetch touches only the first 128-byte line of the leaf's records (no per-lane loop)
+//   8  no software prefetch at all
+//  16  branch-free triangle test (one predicate at the end instead of early returns)
+//  32  at most one stack pop per warp iteration (no inner pop loop)
+//  64  camera rays: the (tile, pass) decode of a 32-item chunk is done once per chunk, not per ray
+constexpr int kVarWideNode = 1, kVarSignMask = 2, kVarLeafPrefetch1 = 4, kVarNoPrefetch = 8, kVarTriBranchFree = 16,
+              kVarSinglePop = 32, kVarChunkDecode = 64;
+
+template <bool F32, int VAR> __device__ __forceinline__ void prefetch_next(const SceneView &sc, uint32_t ref, uint32_t rc) {
+  if (VAR & kVarNoPrefetch) return;
+  if (rc == kBranch) {
+    prefetch_l1(sc.nodes + ref);
+  } else if (VAR & kVarLeafPrefetch1) {
+    const size_t rec = F32 ? sizeof(TriRecordF32) : sizeof(TriRecordF64);
+    prefetch_l1(reinterpret_cast<const char *>(sc.tris) + (size_t)ref * rec);
+  } else {
+    prefetch_leaf<F32>(sc.tris, ref, rc);
+  }
+}
+
+struct NodeWords { // one PairNode as loaded
+  double b[2][6];
+  uint32_t ref0, ref1, cnt0, cnt1, axis;
+};
+
+template <bool WIDE> __device__ __forceinline__ NodeWords load_pair_node(const PairNode *n) {
+  NodeWords w;
+  if (WIDE) {
+    const char *p = reinterpret_cast<const char *>(n);
+    double a0, a1, a2, a3;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3) : "l"(p + 32 * k));
+      (&w.b[0][0])[4 * k + 0] = a0, (&w.b[0][0])[4 * k + 1] = a1, (&w.b[0][0])[4 * k + 2] = a2, (&w.b[0][0])[4 * k + 3] = a3;
+    }
+    uint32_t m0, m1, m2, m3, m4, m5, m6, m7;
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3), "=r"(m4), "=r"(m5), "=r"(m6), "=r"(m7)
+                 : "l"(p + 96));
+    w.ref0 = m0, w.ref1 = m1, w.cnt0 = m2, w.cnt1 = m3, w.axis = m4;
+  } else {
+    const double2 *np = reinterpret_cast<const double2 *>(n);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const double2 v = __ldg(np + k);
+      (&w.b[0][0])[2 * k] = v.x, (&w.b[0][0])[2 * k + 1] = v.y;
+    }
+    const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(np + 6));
+    w.ref0 = meta.x, w.ref1 = meta.y, w.cnt0 = meta.z, w.cnt1 = meta.w;
+    w.axis = __ldg(reinterpret_cast<const uint32_t *>(np + 7));
+  }
+  return w;
+}
+
+template <class IO, bool F32, int S, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int POLICY, unsigned CHUNK, int VAR>
 __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const IO &io, unsigned long long n,
                                                     unsigned long long *work, TravStack<S, CAP> &st,
                                                     unsigned long long *gcounters) {
@@ -175,6 +287,7 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
   int sp = 0;
   uint32_t pool_next = 0, pool_end = 0;
   bool exhausted = false;
+  typename IO::Chunk chunk;
   TravCounters cnt = {0u, 0u, 0u};
   unsigned int nrays = 0;
   r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = r.ix = r.iy = r.iz = 0.0;
@@ -194,6 +307,7 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
           } else {
             pool_next = (uint32_t)base;
             pool_end = (uint32_t)((base + CHUNK < n) ? base + CHUNK : n);
+            if (VAR & kVarChunkDecode) io.prepare(chunk, pool_next);
           }
         }
         if (!exhausted) {
@@ -202,7 +316,8 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
           if (rc == kIdle && rank < avail) {
             item = pool_next + rank;
             double ox, oy, oz, dx, dy, dz, t0;
-            if (io.load(item, ox, oy, oz, dx, dy, dz, t0)) {
+            if ((VAR & kVarChunkDecode) ? io.load(chunk, item, ox, oy, oz, dx, dy, dz, t0)
+                                        : io.load(item, ox, oy, oz, dx, dy, dz, t0)) {
               ray_setup(r, ox, oy, oz, dx, dy, dz);
               hit_t = t0;
               if (ANYHIT) tmax_any = t0;
@@ -244,40 +359,38 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
 
     if (run_inner && at_inner) {
       // ---- INNER: one 128-byte PairNode, both children tested (equivalence: traverse.cuh) -------------
-      const double2 *np = reinterpret_cast<const double2 *>(sc.nodes + ref);
-      const double2 a0 = __ldg(np + 0), a1 = __ldg(np + 1), a2 = __ldg(np + 2);
-      const double2 b0 = __ldg(np + 3), b1 = __ldg(np + 4), b2 = __ldg(np + 5);
-      const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(np + 6));
-      const uint32_t axis = __ldg(reinterpret_cast<const uint32_t *>(np + 7));
+      const NodeWords nw = load_pair_node<(VAR & kVarWideNode) != 0>(sc.nodes + ref);
       double t0, t1;
-      const bool h0 = slab_test(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, r, hit_t, t0);
-      const bool h1 = slab_test(b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, r, hit_t, t1);
+      const bool h0 = slab_test(nw.b[0][0], nw.b[0][1], nw.b[0][2], nw.b[0][3], nw.b[0][4], nw.b[0][5], r, hit_t, t0);
+      const bool h1 = slab_test(nw.b[1][0], nw.b[1][1], nw.b[1][2], nw.b[1][3], nw.b[1][4], nw.b[1][5], r, hit_t, t1);
       if (COUNT) cnt.nodes += 2;
-      const bool sgn = (axis == 0) ? r.sx : ((axis == 1) ? r.sy : r.sz);
+      bool sgn;
+      if (VAR & kVarSignMask) {
+        const uint32_t smask = (r.sx ? 1u : 0u) | (r.sy ? 2u : 0u) | (r.sz ? 4u : 0u);
+        sgn = ((smask >> nw.axis) & 1u) != 0u;
+      } else {
+        sgn = (nw.axis == 0) ? r.sx : ((nw.axis == 1) ? r.sy : r.sz);
+      }
       if (h0 && h1) { // near = data[dirSign[axis]] first, far pushed with its tmin (bvh_accel.cc:818-823)
-        st.put(sp++, sgn ? t0 : t1, sgn ? meta.x : meta.y, sgn ? meta.z : meta.w);
+        st.put(sp++, sgn ? t0 : t1, sgn ? nw.ref0 : nw.ref1, sgn ? nw.cnt0 : nw.cnt1);
         if (COUNT) cnt.max_stack = max(cnt.max_stack, (unsigned int)sp + 1u);
-        ref = sgn ? meta.y : meta.x, rc = sgn ? meta.w : meta.z;
+        ref = sgn ? nw.ref1 : nw.ref0, rc = sgn ? nw.cnt1 : nw.cnt0;
       } else if (h0) {
-        ref = meta.x, rc = meta.z;
+        ref = nw.ref0, rc = nw.cnt0;
       } else if (h1) {
-        ref = meta.y, rc = meta.w;
+        ref = nw.ref1, rc = nw.cnt1;
       } else {
         rc = 0u;
       }
       if (rc != 0u) {
-        if (rc == kBranch) {
-          prefetch_l1(sc.nodes + ref);
-        } else {
-          if (COUNT) cnt.tris += rc;
-          prefetch_leaf<F32>(sc.tris, ref, rc);
-        }
+        if (COUNT && rc != kBranch) cnt.tris += rc;
+        prefetch_next<F32, VAR>(sc, ref, rc);
       }
     } else if (run_leaf && at_leaf) {
       // ---- LEAF: one triangle of TestLeafNode (bvh_accel.cc:640-697), in indices_ order -----------------
       const TriEdges tv = load_tri_edges<F32>(sc.tris, ref);
       double u, v;
-      if (tri_test_edges(hit_t, u, v, tv, r)) {
+      if (tri_test_edges<(VAR & kVarTriBranchFree) != 0>(hit_t, u, v, tv, r)) {
         io.accept(item, hit_t, u, v, tv.face, tv.mat);
         if (ANYHIT && hit_t < tmax_any) { // occluded: closest-hit Traverse would return t < tmax
           io.finish(item, true);
@@ -292,24 +405,36 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
 
     // ---- C. pop: the reference's pop-time (tmin <= hitT) decision; empty stack = ray finished ----------
     if (rc == 0u) {
-      for (;;) {
+      if (VAR & kVarSinglePop) {
         if (sp == 0) {
           io.finish(item, false);
           rc = kIdle;
-          break;
-        }
-        double tm;
-        st.get(--sp, tm, ref, rc);
-        if (tm <= hit_t && rc != 0u) {
-          if (rc == kBranch) {
-            prefetch_l1(sc.nodes + ref);
+        } else {
+          double tm;
+          st.get(--sp, tm, ref, rc);
+          if (tm <= hit_t && rc != 0u) {
+            if (COUNT && rc != kBranch) cnt.tris += rc;
+            prefetch_next<F32, VAR>(sc, ref, rc);
           } else {
-            if (COUNT) cnt.tris += rc;
-            prefetch_leaf<F32>(sc.tris, ref, rc);
+            rc = 0u; // culled at pop time: pops again next iteration
           }
-          break;
         }
-        rc = 0u;
+      } else {
+        for (;;) {
+          if (sp == 0) {
+            io.finish(item, false);
+            rc = kIdle;
+            break;
+          }
+          double tm;
+          st.get(--sp, tm, ref, rc);
+          if (tm <= hit_t && rc != 0u) {
+            if (COUNT && rc != kBranch) cnt.tris += rc;
+            prefetch_next<F32, VAR>(sc, ref, rc);
+            break;
+          }
+          rc = 0u;
+        }
       }
     }
   }

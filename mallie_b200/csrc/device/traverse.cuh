@@ -119,6 +119,11 @@ template <> __device__ __forceinline__ TriEdges load_tri_edges<false>(const void
 }
 
 // TriangleIsect (bvh_accel.cc:595-638): Moeller-Trumbore, no culling.
+// BRANCH_FREE: the same arithmetic with every rejection test folded into one predicate.  Each test is
+// written as the negation of the reference's rejecting comparison, so NaNs fall through exactly as they
+// do there (a NaN u, v or t is NOT rejected by `u < 0.0 || u > 1.0` and friends); a near-zero det still
+// rejects first, whatever 1.0 / det produced.
+template <bool BRANCH_FREE>
 __device__ __forceinline__ bool tri_test_edges(double &t_io, double &u_out, double &v_out, const TriEdges &k,
                                                const RayD &r) {
   // p = dir x e2
@@ -126,7 +131,7 @@ __device__ __forceinline__ bool tri_test_edges(double &t_io, double &u_out, doub
   const double py = r.dz * k.e2x - r.dx * k.e2z;
   const double pz = r.dx * k.e2y - r.dy * k.e2x;
   const double det = k.e1x * px + k.e1y * py + k.e1z * pz;
-  if (fabs(det) < MB200_TRI_EPS) return false;
+  if (!BRANCH_FREE && fabs(det) < MB200_TRI_EPS) return false;
   const double inv_det = 1.0 / det;
   const double sx = r.ox - k.p0x, sy = r.oy - k.p0y, sz = r.oz - k.p0z;
   // q = s x e1
@@ -136,9 +141,15 @@ __device__ __forceinline__ bool tri_test_edges(double &t_io, double &u_out, doub
   const double u = (sx * px + sy * py + sz * pz) * inv_det;
   const double v = (qx * r.dx + qy * r.dy + qz * r.dz) * inv_det;
   const double t = (k.e2x * qx + k.e2y * qy + k.e2z * qz) * inv_det;
-  if (u < 0.0 || u > 1.0) return false;
-  if (v < 0.0 || u + v > 1.0) return false;
-  if (t < 0.0 || t > t_io) return false;
+  if (BRANCH_FREE) {
+    const bool ok = !(fabs(det) < MB200_TRI_EPS) & !(u < 0.0) & !(u > 1.0) & !(v < 0.0) & !(u + v > 1.0) & !(t < 0.0) &
+                    !(t > t_io);
+    if (!ok) return false;
+  } else {
+    if (u < 0.0 || u > 1.0) return false;
+    if (v < 0.0 || u + v > 1.0) return false;
+    if (t < 0.0 || t > t_io) return false;
+  }
   t_io = t;
   u_out = u;
   v_out = v;
@@ -155,11 +166,11 @@ template <int S, int CAP> struct TravStack {
   __device__ __forceinline__ void put(int k, double tmin, uint32_t ref, uint32_t cnt) {
     const unsigned long long tb = (unsigned long long)__double_as_longlong(tmin);
     const uint4 e = make_uint4((uint32_t)tb, (uint32_t)(tb >> 32), ref, cnt);
-    if (k < S) sm[k * stride] = e;
+    if (S > 0 && k < S) sm[k * stride] = e;
     else ovf[k - S] = e;
   }
   __device__ __forceinline__ void get(int k, double &tmin, uint32_t &ref, uint32_t &cnt) const {
-    const uint4 e = (k < S) ? sm[k * stride] : ovf[k - S];
+    const uint4 e = (S > 0 && k < S) ? sm[k * stride] : ovf[k - S];
     tmin = __longlong_as_double((long long)(((unsigned long long)e.y << 32) | e.x));
     ref = e.z;
     cnt = e.w;
