@@ -400,6 +400,11 @@ def main():
             "rays_per_step": rays_frame, "shadow_rays_per_step": shadow_frame, "scene_build_upload_s": build_s,
         }
         print(json.dumps(line), flush=True)
+    # tensors that were used on the scene's stream must be released before the stream is destroyed
+    # (torch's caching allocator records an event on that stream when it frees them)
+    del d_img, d_cnt, flush, gather, h_img, h_cnt, evs
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

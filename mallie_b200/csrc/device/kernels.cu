@@ -438,7 +438,10 @@ cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const
     static const int policy = env_int("MB200_TRACE_POLICY", kPolicy), occ = env_int("MB200_TRACE_OCC", kMinBlocks),
                      chunk = env_int("MB200_TRACE_CHUNK", (int)kChunk), refill = env_int("MB200_TRACE_REFILL", kRefillMin),
                      var = env_int("MB200_TRACE_VAR", kVar);
-    if (policy == 0) return MB200_SM(4, 0, 16, 5, 32, 0);
+    if (policy == 0) return MB200_SM(8, 0, 12, 8, 32, 11);
+    if (policy == 3) return MB200_SM(8, 3, 12, 8, 32, 11);
+    if (policy == 4) return MB200_SM(8, 4, 12, 8, 32, 11);
+    if (policy == 6) return MB200_SM(8, 6, 12, 8, 32, 11);
     if (occ == 4) return MB200_SM(4, 2, 16, 4, 32, 0);
     if (occ == 6) return MB200_SM(4, 2, 16, 6, 32, 0);
     if (occ == 8) return MB200_SM(4, 2, 12, 8, 32, 0);

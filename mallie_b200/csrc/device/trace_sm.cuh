@@ -355,6 +355,18 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
       if (!(m_inner | m_leaf)) continue;
       run_inner = __popc(m_inner) > __popc(m_leaf);
       run_leaf = !run_inner;
+    } else if (POLICY >= 3) {
+      // threshold vote (A/B): a body runs only when at least POLICY * 2 lanes wait for it, unless the
+      // other body does not qualify either (then the fuller one runs); the skipped lanes wait one iteration
+      const int n_inner = __popc(__ballot_sync(kFullMask, at_inner));
+      const int n_leaf = __popc(__ballot_sync(kFullMask, at_leaf));
+      constexpr int T = POLICY * 2;
+      run_inner = n_inner >= T;
+      run_leaf = n_leaf >= T;
+      if (!run_inner && !run_leaf) {
+        run_inner = n_inner >= n_leaf;
+        run_leaf = !run_inner;
+      }
     }
 
     if (run_inner && at_inner) {

@@ -1,13 +1,7 @@
 mkdir -p gpurun_out
 run() { env "$@" python tools/ab_frame.py 2>&1 | tail -1; }
 run MB200_TRACE_VAR=11
-run MB200_TRACE_VAR=1100
-run MB200_TRACE_VAR=1104
-run MB200_TRACE_VAR=1108
-run MB200_TRACE_VAR=1116
-run MB200_TRACE_VAR=1109
-run MB200_TRACE_VAR=1110
-run MB200_TRACE_VAR=1143
-run MB200_TRACE_VAR=1127
-run MB200_TRACE_VAR=1112
-run MB200_TRACE_VAR=1164
+run MB200_TRACE_POLICY=0
+run MB200_TRACE_POLICY=3
+run MB200_TRACE_POLICY=4
+run MB200_TRACE_POLICY=6
