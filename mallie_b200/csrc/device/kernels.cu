@@ -15,6 +15,7 @@
 #include <cstdlib>
 
 #include "shade.cuh"
+#include "trace_mr.cuh"
 #include "trace_sm.cuh"
 #include "traverse.cuh"
 
@@ -82,6 +83,20 @@ __global__ void __launch_bounds__(kBlock, MINB)
   st.stride = kBlock;
   if (n_dev) n = __ldg(n_dev);
   trace_state_machine<IO, F32, S, CAP, ANYHIT, COUNT, REFILL_MIN, POLICY, CHUNK, VAR>(sc, io, n, work, st, gcounters);
+}
+
+// The K-rays-per-lane machine (trace_mr.cuh): ray slots in dynamic shared memory, MINB CTAs per SM.
+template <class IO, bool F32, int K, bool ANYHIT, bool COUNT, int REFILL_MIN, int MINB, unsigned CHUNK>
+__global__ void __launch_bounds__(kBlock, MINB)
+    k_trace_mr(const __grid_constant__ SceneView sc, const __grid_constant__ IO io, unsigned long long n,
+               const unsigned int *__restrict__ n_dev, unsigned long long *__restrict__ work,
+               unsigned long long *__restrict__ gcounters) {
+  extern __shared__ uint4 smem_slots[];
+  SlotMem<K> sm;
+  sm.base = smem_slots + threadIdx.x;
+  sm.stride = kBlock;
+  if (n_dev) n = __ldg(n_dev);
+  trace_multi_ray<IO, F32, K, 64, ANYHIT, COUNT, REFILL_MIN, CHUNK>(sc, io, n, work, sm, gcounters);
 }
 
 // ---------------------------------------------------------------------------
@@ -427,6 +442,31 @@ cudaError_t launch_sm(const SceneView &sc, const IO &io, size_t n, const unsigne
   return cudaGetLastError();
 }
 
+template <class IO, bool F32, int K, bool ANYHIT, bool COUNT, int REFILL_MIN, int MINB, unsigned CHUNK>
+cudaError_t launch_mr(const SceneView &sc, const IO &io, size_t n, const unsigned int *n_dev,
+                      unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
+  auto k = k_trace_mr<IO, F32, K, ANYHIT, COUNT, REFILL_MIN, MINB, CHUNK>;
+  const size_t smem = (size_t)K * kSlotUnits * kBlock * sizeof(uint4);
+  static int grid = 0; // per instantiation
+  if (grid == 0) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int carve = (int)((smem + 1024) * MINB * 100 / (228 * 1024)) + 1;
+    if (carve > 100) carve = 100;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kBlock, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > MINB) per_sm = MINB;
+    grid = num_sms() * per_sm;
+  }
+  k<<<grid, kBlock, smem, s>>>(sc, io, (unsigned long long)n, n_dev, work, counters);
+  g_launches++;
+  return cudaGetLastError();
+}
+
 // Picks the kernel instantiation: production parameters, or (development builds, -DMB200_DEV_VARIANTS)
 // the A/B variants selected with MB200_TRACE_POLICY / MB200_TRACE_OCC / MB200_TRACE_CHUNK.
 template <class IO, bool F32, int CAP, bool ANYHIT, bool COUNT>
@@ -434,6 +474,18 @@ cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const
                               unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
 #define MB200_SM(R, P, S, B, C, V) launch_sm<IO, F32, CAP, ANYHIT, COUNT, R, P, S, B, C, V>(sc, io, n, n_dev, work, counters, s)
 #ifdef MB200_DEV_VARIANTS
+  if (CAP <= 64) {
+    static const int mr = env_int("MB200_TRACE_MR", 0); // K * 100 + CTAs per SM * 10 + (refill >= 16 ? 1 : 0)
+#define MB200_MR(K, R, B) launch_mr<IO, F32, K, ANYHIT, COUNT, R, B, 32>(sc, io, n, n_dev, work, counters, s)
+    if (mr == 440) return MB200_MR(4, 8, 4);
+    if (mr == 441) return MB200_MR(4, 16, 4);
+    if (mr == 340) return MB200_MR(3, 8, 4);
+    if (mr == 350) return MB200_MR(3, 8, 5);
+    if (mr == 260) return MB200_MR(2, 8, 6);
+    if (mr == 280) return MB200_MR(2, 8, 8);
+    if (mr == 430) return MB200_MR(4, 8, 3);
+#undef MB200_MR
+  }
   if (!COUNT && CAP <= 64) {
     static const int policy = env_int("MB200_TRACE_POLICY", kPolicy), occ = env_int("MB200_TRACE_OCC", kMinBlocks),
                      chunk = env_int("MB200_TRACE_CHUNK", (int)kChunk), refill = env_int("MB200_TRACE_REFILL", kRefillMin),

@@ -108,6 +108,7 @@ struct IOOccluded {
   }
   __device__ __forceinline__ void accept(uint32_t, double, double, double, uint32_t, uint32_t) const {}
   __device__ __forceinline__ void finish(uint32_t i, bool occ) const { occluded[i] = occ ? 1 : 0; }
+  __device__ __forceinline__ double tmax_of(uint32_t i) const { return __ldg(tmax + i); }
 };
 
 // K1 fused into K2: the camera ray of work item i (one jittered sample of one pixel) is generated in
@@ -211,6 +212,7 @@ struct IOQueueShadow {
       contrib[w.x] = __uint_as_float(w.y);
     }
   }
+  __device__ __forceinline__ double tmax_of(uint32_t i) const { return __ldg(&q[i].tmax); }
 };
 
 // ---- the state machine ------------------------------------------------------------------------------

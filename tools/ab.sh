@@ -1,7 +1,11 @@
 mkdir -p gpurun_out
 run() { env "$@" python tools/ab_frame.py 2>&1 | tail -1; }
-run MB200_TRACE_VAR=11
-run MB200_TRACE_POLICY=0
-run MB200_TRACE_POLICY=3
-run MB200_TRACE_POLICY=4
-run MB200_TRACE_POLICY=6
+MB200_TRACE_MR=440 python -m pytest tests/test_gpu_parity.py tests/test_gpu_render.py -x -q 2>&1 | tail -3
+run A=1
+run MB200_TRACE_MR=440
+run MB200_TRACE_MR=441
+run MB200_TRACE_MR=430
+run MB200_TRACE_MR=340
+run MB200_TRACE_MR=350
+run MB200_TRACE_MR=260
+run MB200_TRACE_MR=280
