@@ -86,17 +86,17 @@ __global__ void __launch_bounds__(kBlock, MINB)
 }
 
 // The K-rays-per-lane machine (trace_mr.cuh): ray slots in dynamic shared memory, MINB CTAs per SM.
-template <class IO, bool F32, int K, bool ANYHIT, bool COUNT, int REFILL_MIN, int MINB, unsigned CHUNK>
+template <class IO, bool F32, int K, int S, bool ANYHIT, bool COUNT, int REFILL_MIN, int MINB, unsigned CHUNK>
 __global__ void __launch_bounds__(kBlock, MINB)
     k_trace_mr(const __grid_constant__ SceneView sc, const __grid_constant__ IO io, unsigned long long n,
                const unsigned int *__restrict__ n_dev, unsigned long long *__restrict__ work,
                unsigned long long *__restrict__ gcounters) {
   extern __shared__ uint4 smem_slots[];
-  SlotMem<K> sm;
+  SlotMem<K, S> sm;
   sm.base = smem_slots + threadIdx.x;
   sm.stride = kBlock;
   if (n_dev) n = __ldg(n_dev);
-  trace_multi_ray<IO, F32, K, 64, ANYHIT, COUNT, REFILL_MIN, CHUNK>(sc, io, n, work, sm, gcounters);
+  trace_multi_ray<IO, F32, K, S, 64, ANYHIT, COUNT, REFILL_MIN, CHUNK>(sc, io, n, work, sm, gcounters);
 }
 
 // ---------------------------------------------------------------------------
@@ -442,11 +442,11 @@ cudaError_t launch_sm(const SceneView &sc, const IO &io, size_t n, const unsigne
   return cudaGetLastError();
 }
 
-template <class IO, bool F32, int K, bool ANYHIT, bool COUNT, int REFILL_MIN, int MINB, unsigned CHUNK>
+template <class IO, bool F32, int K, int S, bool ANYHIT, bool COUNT, int REFILL_MIN, int MINB, unsigned CHUNK>
 cudaError_t launch_mr(const SceneView &sc, const IO &io, size_t n, const unsigned int *n_dev,
                       unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
-  auto k = k_trace_mr<IO, F32, K, ANYHIT, COUNT, REFILL_MIN, MINB, CHUNK>;
-  const size_t smem = (size_t)K * kSlotUnits * kBlock * sizeof(uint4);
+  auto k = k_trace_mr<IO, F32, K, S, ANYHIT, COUNT, REFILL_MIN, MINB, CHUNK>;
+  const size_t smem = (size_t)K * (kSlotUnits + S) * kBlock * sizeof(uint4);
   static int grid = 0; // per instantiation
   if (grid == 0) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -476,14 +476,13 @@ cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const
 #ifdef MB200_DEV_VARIANTS
   if (CAP <= 64) {
     static const int mr = env_int("MB200_TRACE_MR", 0); // K * 100 + CTAs per SM * 10 + (refill >= 16 ? 1 : 0)
-#define MB200_MR(K, R, B) launch_mr<IO, F32, K, ANYHIT, COUNT, R, B, 32>(sc, io, n, n_dev, work, counters, s)
-    if (mr == 440) return MB200_MR(4, 8, 4);
-    if (mr == 441) return MB200_MR(4, 16, 4);
-    if (mr == 340) return MB200_MR(3, 8, 4);
-    if (mr == 350) return MB200_MR(3, 8, 5);
-    if (mr == 260) return MB200_MR(2, 8, 6);
-    if (mr == 280) return MB200_MR(2, 8, 8);
-    if (mr == 430) return MB200_MR(4, 8, 3);
+#define MB200_MR(K, S, R, B) launch_mr<IO, F32, K, S, ANYHIT, COUNT, R, B, 32>(sc, io, n, n_dev, work, counters, s)
+    if (mr == 440) return MB200_MR(4, 0, 16, 4);
+    if (mr == 333) return MB200_MR(3, 3, 16, 4);
+    if (mr == 327) return MB200_MR(2, 7, 16, 4);
+    if (mr == 325) return MB200_MR(2, 5, 16, 5);
+    if (mr == 336) return MB200_MR(3, 6, 16, 3);
+    if (mr == 248) return MB200_MR(4, 8, 16, 2);
 #undef MB200_MR
   }
   if (!COUNT && CAP <= 64) {

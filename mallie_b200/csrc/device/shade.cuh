@@ -189,7 +189,15 @@ struct FrameMap {
   uint32_t pass0;       // first pass index of the batch
   int step;             // Render()'s step (>= 1): sampled pixels are step apart in x and y
   int y1;               // end row of the rectangle (block fill clipping)
+  // exact division by the launch constants passes / tiles_x as one 64-bit high multiply (0 means d == 1)
+  unsigned long long magic_passes, magic_tiles_x;
 };
+
+// M = ceil(2^64 / d) = (2^64 + e) / d with 0 <= e < d.  For n < 2^32: n * M / 2^64 = n / d + n * e / (d * 2^64),
+// and n * e < 2^64, so the extra term is below 1 / d and floor(n * M / 2^64) == floor(n / d): exact.
+__host__ __device__ inline unsigned long long div_magic(uint32_t d) {
+  return d <= 1u ? 0ull : (0xFFFFFFFFFFFFFFFFull / d) + 1ull;
+}
 
 __host__ __device__ inline int band_local_rows(int rows, int band_rows, int count, int index) {
   const int nbands = (rows + band_rows - 1) / band_rows;
@@ -212,6 +220,7 @@ __host__ inline FrameMap make_frame_map(const mb200_render_params &p, uint32_t p
   m.width = p.width;
   m.band_rows = p.band_rows, m.band_count = p.band_count, m.band_index = p.band_index, m.compact = p.band_compact;
   m.passes = passes, m.pass0 = pass0;
+  m.magic_passes = div_magic(passes), m.magic_tiles_x = div_magic((uint32_t)m.tiles_x);
   return m;
 }
 
@@ -222,9 +231,10 @@ __host__ inline size_t frame_map_tiles(const FrameMap &m) {
 // item -> pixel; returns false for padding lanes.  rl = row among the rows this call owns.
 __device__ __forceinline__ bool item_pixel(const FrameMap &m, uint32_t item, int &x, int &y, int &rl, uint32_t &pass) {
   const uint32_t lane = item & 31u, g = item >> 5;
-  const uint32_t tile = g / m.passes;
+  const uint32_t tile = m.magic_passes ? (uint32_t)__umul64hi((unsigned long long)g, m.magic_passes) : g;
   pass = m.pass0 + (g - tile * m.passes);
-  const int tx = (int)(tile % (uint32_t)m.tiles_x), ty = (int)(tile / (uint32_t)m.tiles_x);
+  const uint32_t tyu = m.magic_tiles_x ? (uint32_t)__umul64hi((unsigned long long)tile, m.magic_tiles_x) : tile;
+  const int ty = (int)tyu, tx = (int)(tile - tyu * (uint32_t)m.tiles_x);
   x = m.x0 + (tx * 8 + (int)(lane & 7u)) * m.step;
   rl = ty * 4 + (int)(lane >> 3);
   y = m.y0 + rl * m.step;

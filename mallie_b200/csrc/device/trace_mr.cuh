@@ -29,10 +29,11 @@ namespace mb200 {
 
 constexpr int kSlotUnits = 6; // 16-byte units per ray slot
 
-template <int K> struct SlotMem {
+// S: stack entries per slot kept in shared memory right behind the slot's six units
+template <int K, int S = 0> struct SlotMem {
   uint4 *base; // this thread's column
   int stride;  // blockDim.x
-  __device__ __forceinline__ uint4 *unit(int s, int u) const { return base + (s * kSlotUnits + u) * stride; }
+  __device__ __forceinline__ uint4 *unit(int s, int u) const { return base + (s * (kSlotUnits + S) + u) * stride; }
   __device__ __forceinline__ double2 ld2(int s, int u) const {
     const uint4 v = *unit(s, u);
     return make_double2(__longlong_as_double((long long)(((unsigned long long)v.y << 32) | v.x)),
@@ -50,15 +51,23 @@ template <int K> struct SlotMem {
 
 // K rays per lane.  CAP: stack entries per ray (local memory).  The IO policies are those of trace_sm.cuh;
 // any-hit sources must provide tmax_of(item) (the occlusion distance, re-read on the rare accepted hit).
-template <class IO, bool F32, int K, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, unsigned CHUNK>
+template <class IO, bool F32, int K, int S, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, unsigned CHUNK>
 __device__ __forceinline__ void trace_multi_ray(const SceneView &sc, const IO &io, unsigned long long n,
-                                                unsigned long long *work, const SlotMem<K> sm,
+                                                unsigned long long *work, const SlotMem<K, S> sm,
                                                 unsigned long long *gcounters) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
   constexpr uint32_t kAll = (1u << K) - 1u;
 
-  uint4 stk[K * CAP]; // (tmin, ref, cnt) entries, per slot; L1-cached local memory
+  // (tmin, ref, cnt) stack entries per slot: the first S in shared memory, the rest in L1-cached local memory
+  uint4 stk[K * ((CAP > S) ? (CAP - S) : 1)];
+  auto stk_put = [&](int s, uint32_t k, const uint4 &e) {
+    if (S > 0 && k < (uint32_t)S) *sm.unit(s, kSlotUnits + (int)k) = e;
+    else stk[s * (CAP - S) + (int)k - S] = e;
+  };
+  auto stk_get = [&](int s, uint32_t k) -> uint4 {
+    return (S > 0 && k < (uint32_t)S) ? *sm.unit(s, kSlotUnits + (int)k) : stk[s * (CAP - S) + (int)k - S];
+  };
   uint32_t m_inner = 0u, m_leaf = 0u, m_pop = 0u;
   uint32_t pool_next = 0, pool_end = 0;
   bool exhausted = false;
@@ -169,7 +178,7 @@ __device__ __forceinline__ void trace_multi_ray(const SceneView &sc, const IO &i
       if (h0 && h1) { // near = data[dirSign[axis]] first, far pushed with its tmin (bvh_accel.cc:818-823)
         const double tf = sgn ? t0 : t1;
         const unsigned long long tb = (unsigned long long)__double_as_longlong(tf);
-        stk[si * CAP + sp] = make_uint4((uint32_t)tb, (uint32_t)(tb >> 32), sgn ? nw.ref0 : nw.ref1, sgn ? nw.cnt0 : nw.cnt1);
+        stk_put(si, sp, make_uint4((uint32_t)tb, (uint32_t)(tb >> 32), sgn ? nw.ref0 : nw.ref1, sgn ? nw.cnt0 : nw.cnt1));
         sp++;
         if (COUNT) cnt.max_stack = max(cnt.max_stack, sp + 1u);
         ref = sgn ? nw.ref1 : nw.ref0, rc = sgn ? nw.cnt1 : nw.cnt0;
@@ -227,7 +236,7 @@ __device__ __forceinline__ void trace_multi_ray(const SceneView &sc, const IO &i
       uint32_t sp = w.z & 0xFFFFu, ref = 0u, rc = 0u;
       for (;;) {
         if (sp == 0u) break;
-        const uint4 e = stk[s * CAP + (--sp)];
+        const uint4 e = stk_get(s, --sp);
         const double tm = __longlong_as_double((long long)(((unsigned long long)e.y << 32) | e.x));
         if (tm <= hit_t && e.w != 0u) {
           ref = e.z, rc = e.w;

@@ -185,3 +185,31 @@ def test_device_buffers_and_pinned_host():
     om, ob = T.oracle_scene("sphere40")
     T.assert_hits_equal(hits, ob.trace(d_rays.cpu().numpy().reshape(-1, 6), row=W)["hits"], "device buffers")
     sc.close()
+
+
+def test_kernel_timing_hooks():
+    """mb200_scene_timing / mb200_scene_kernel_times: launches and milliseconds per kernel class."""
+    W, H = 320, 200
+    m = T.load_mesh("sphere40")
+    sc = M.Scene(m["vertices"], m["faces"])
+    fg = M.camera_frame((0.2, 0.1, 3.0), (0, 0, 0), width=W, height=H)
+    p = sc.render_params(fg, W, H, shader=M.SHADER_PRIMARY_SHADOW, light=(2, 4, 3))
+    sc.render_pass(p)
+    assert all(v == 0 for v in sc.kernel_times().values())          # disabled: nothing recorded
+    sc.timing(True)
+    sc.render_frame(p, 3)
+    rays = sc.generate_rays_grid(fg, 0, 0, W, H)
+    sc.trace_closest(rays)
+    kt = sc.kernel_times()
+    assert kt["camera_trace_launches"] == 1 and kt["shadow_trace_launches"] == 1 and kt["shade_launches"] == 1
+    assert kt["resolve_launches"] == 1 and kt["query_trace_launches"] == 1 and kt["bounce_trace_launches"] == 0
+    assert 0 < kt["camera_trace_ms"] < 1000 and 0 < kt["shadow_trace_ms"] < 1000 and kt["query_trace_ms"] > 0
+    assert all(v == 0 for v in sc.kernel_times().values())          # reading resets
+    pp = sc.render_params(fg, W, H, shader=M.SHADER_PATHTRACE, max_path_length=4)
+    sc.render_pass(pp)
+    kt = sc.kernel_times()
+    assert kt["bounce_trace_launches"] == 3 and kt["shade_launches"] == 4
+    sc.timing(False)
+    sc.render_pass(p)
+    assert all(v == 0 for v in sc.kernel_times().values())
+    sc.close()
