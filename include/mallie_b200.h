@@ -297,6 +297,16 @@ int mb200_render_accumulate(mb200_scene *scene, const mb200_render_params *param
  * buffers cost one device->host copy only. */
 int mb200_render_frame(mb200_scene *scene, const mb200_render_params *params, int num_passes, float *image,
                        int *count, mb200_render_stats *stats);
+/* One frame over several GPUs from ONE host thread (the single-process form of SURVEY.md §8e; one process per
+ * GPU uses mb200_render_frame with band_* and an NCCL gather instead, bench.py).  scenes[g] is a replica of the
+ * same scene on its own GPU; the image rows are cut into bands of band_rows scanlines (a multiple of 4), band b
+ * is rendered by scenes[b % num_scenes], and the frame is assembled in scenes[0]'s GPU: with peer access every
+ * GPU's resolve kernel stores its rows straight into that framebuffer over NVLink (no copy, no collective);
+ * without it each GPU renders into a local band buffer that is copied peer-to-peer afterwards.  params must
+ * describe the whole image (x0 = y0 = 0, x1 = width, y1 = height, band_rows = 0, pixel_step <= 1).
+ * image / count: as mb200_render_frame (device pointers must belong to scenes[0]'s GPU).  stats: sums. */
+int mb200_render_frame_multi(mb200_scene *const *scenes, int num_scenes, const mb200_render_params *params,
+                             int num_passes, int band_rows, float *image, int *count, mb200_render_stats *stats);
 /* Rows of the image a banded call owns (== y1-y0 when bands are disabled). */
 int mb200_band_local_rows(const mb200_render_params *params);
 

@@ -38,7 +38,7 @@ EXPORTS = [
     "mb200_trace_closest", "mb200_trace_closest_full", "mb200_trace_occluded", "mb200_trace_closest_async",
     "mb200_camera_frame_build", "mb200_generate_rays", "mb200_generate_rays_grid",
     "mb200_render_params_default", "mb200_plane_from_bounds", "mb200_render_pass", "mb200_render_accumulate",
-    "mb200_render_frame", "mb200_band_local_rows",
+    "mb200_render_frame", "mb200_render_frame_multi", "mb200_band_local_rows",
     "mb200_mesh_load_obj", "mb200_mesh_load_eson", "mb200_mesh_transform", "mb200_mesh_num_vertices",
     "mb200_mesh_num_faces", "mb200_mesh_vertices", "mb200_mesh_faces", "mb200_mesh_material_ids",
     "mb200_mesh_fv_normals", "mb200_mesh_fv_uvs", "mb200_mesh_destroy", "mb200_config_default", "mb200_config_load",
@@ -165,6 +165,8 @@ def lib():
         L.mb200_render_accumulate.argtypes = [vp, C.POINTER(RenderParams), i32, vp, vp, C.POINTER(RenderStats)]
         L.mb200_render_frame.argtypes = [vp, C.POINTER(RenderParams), i32, vp, vp, C.POINTER(RenderStats)]
         L.mb200_band_local_rows.argtypes = [C.POINTER(RenderParams)]
+        L.mb200_render_frame_multi.argtypes = [C.POINTER(vp), i32, C.POINTER(RenderParams), i32, i32, vp, vp,
+                                               C.POINTER(RenderStats)]
         L.mb200_mesh_load_obj.argtypes = [C.POINTER(vp), C.c_char_p]
         L.mb200_mesh_load_eson.argtypes = [C.POINTER(vp), C.c_char_p]
         L.mb200_mesh_transform.argtypes = [vp, dbl, i32]
@@ -201,6 +203,19 @@ def device_count():
 
 def launches_issued():
     return int(lib().mb200_launches_issued())
+
+
+def render_frame_multi(scenes, params, num_passes, band_rows=8, image=None, count=None, stats=True):
+    """mb200_render_frame_multi: one frame over several single-GPU Scene replicas from one host thread."""
+    if image is None:
+        image = np.zeros((params.height, params.width, 3), np.float32)
+    if count is None:
+        count = np.zeros((params.height, params.width), np.int32)
+    arr = (C.c_void_p * len(scenes))(*[s.h for s in scenes])
+    st = RenderStats()
+    check(lib().mb200_render_frame_multi(arr, len(scenes), C.byref(params), num_passes, band_rows, _p(image), _p(count),
+                                         C.byref(st) if stats else None))
+    return image, count, (st.as_dict() if stats else None)
 
 
 def load_config(path=None, text=None):

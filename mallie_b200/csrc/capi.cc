@@ -539,6 +539,131 @@ static int render_common(mb200_scene *s, const mb200_render_params *p, int num_p
   return MB200_OK;
 }
 
+// Can `dev` address memory of `root`?  Enables peer access on first use.
+static bool peer_ok(int dev, int root) {
+  static int state[64][64]; // 0 unknown, 1 yes, 2 no
+  if (dev == root) return true;
+  if (dev < 0 || root < 0 || dev >= 64 || root >= 64) return false;
+  if (state[dev][root] == 0) {
+    int can = 0;
+    state[dev][root] = 2;
+    if (cudaDeviceCanAccessPeer(&can, dev, root) == cudaSuccess && can) {
+      int cur = 0;
+      cudaGetDevice(&cur);
+      cudaSetDevice(dev);
+      const cudaError_t e = cudaDeviceEnablePeerAccess(root, 0);
+      if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) state[dev][root] = 1;
+      cudaGetLastError();
+      cudaSetDevice(cur);
+    }
+  }
+  return state[dev][root] == 1;
+}
+
+int mb200_render_frame_multi(mb200_scene *const *scenes, int n, const mb200_render_params *p, int num_passes,
+                             int band_rows, float *image, int *count, mb200_render_stats *stats) {
+  if (!scenes || n < 1 || !p || !image || !count) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  for (int g = 0; g < n; g++)
+    if (!scenes[g]) return set_err(MB200_ERR_INVALID_ARG, "null scene");
+  if (n == 1) return render_common(scenes[0], p, num_passes, 2, image, count, stats);
+  if (p->width <= 0 || p->height <= 0 || p->x0 != 0 || p->y0 != 0 || p->x1 != p->width || p->y1 != p->height ||
+      p->band_rows != 0 || p->pixel_step > 1 || p->max_path_length < 1 || num_passes < 1 || band_rows < 4 ||
+      band_rows % 4 != 0 || p->shader < 0 || p->shader > MB200_SHADER_PRIMARY_ONLY)
+    return set_err(MB200_ERR_INVALID_ARG,
+                   "multi-GPU frames need whole-image parameters without bands / step and band_rows = 4k");
+  if (n > 64) return set_err(MB200_ERR_INVALID_ARG, "too many scenes");
+  for (int g = 0; g < n; g++)
+    for (int h = 0; h < g; h++)
+      if (scenes[g]->device == scenes[h]->device)
+        return set_err(MB200_ERR_INVALID_ARG, "every scene must live on its own GPU");
+  if (stats) memset(stats, 0, sizeof(*stats));
+  mb200_scene *root = scenes[0];
+  const size_t W = (size_t)p->width, H = (size_t)p->height;
+  const size_t img_bytes = W * H * 3 * sizeof(float), cnt_bytes = W * H * sizeof(int);
+  const HostKind img_kind = classify(image), cnt_kind = classify(count);
+  CU(cudaSetDevice(root->device));
+  float *d_img = image;
+  int *d_cnt = count;
+  int rc;
+  if (img_kind != kDevice) {
+    if ((rc = ensure(root->out0, img_bytes, img_kind == kPageable)) != MB200_OK) return rc;
+    d_img = (float *)root->out0.dev;
+  }
+  if (cnt_kind != kDevice) {
+    if ((rc = ensure(root->out1, cnt_bytes, cnt_kind == kPageable)) != MB200_OK) return rc;
+    d_cnt = (int *)root->out1.dev;
+  }
+  cudaEvent_t done[64];
+  int ndone = 0;
+  auto cleanup = [&]() {
+    for (int k = 0; k < ndone; k++) cudaEventDestroy(done[k]);
+  };
+  for (int g = 0; g < n; g++) {
+    mb200_scene *s = scenes[g];
+    cudaError_t e = cudaSetDevice(s->device);
+    mb200_render_params pg = *p;
+    pg.band_rows = band_rows, pg.band_count = n, pg.band_index = g, pg.band_compact = 0;
+    float *t_img = d_img;
+    int *t_cnt = d_cnt;
+    const bool direct = peer_ok(s->device, root->device);
+    size_t rows = 0;
+    if (e == cudaSuccess && !direct) { // local compact band buffer, copied to the root afterwards
+      pg.band_compact = 1;
+      rows = (size_t)mb200_band_local_rows(&pg);
+      if (ensure(s->in0, rows * W * 3 * sizeof(float), false) != MB200_OK || ensure(s->in1, rows * W * sizeof(int), false) != MB200_OK) {
+        cleanup();
+        return MB200_ERR_OUT_OF_MEMORY;
+      }
+      t_img = (float *)s->in0.dev, t_cnt = (int *)s->in1.dev;
+    }
+    if (e == cudaSuccess && stats) e = cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream);
+    if (e == cudaSuccess)
+      e = mb200::launch_frame(s->view, s->stack_cap, pg, num_passes, 2, t_img, t_cnt, s->frame_scratch,
+                              stats ? s->d_counters : nullptr, s->stream, &s->timer);
+    if (e == cudaSuccess && !direct) {
+      size_t local = 0;
+      const size_t nbands = (H + band_rows - 1) / band_rows;
+      for (size_t b = (size_t)g; b < nbands && e == cudaSuccess; b += (size_t)n) {
+        const size_t y = b * band_rows, r = (y + band_rows <= H) ? (size_t)band_rows : H - y;
+        e = cudaMemcpyPeerAsync(d_img + y * W * 3, root->device, t_img + local * W * 3, s->device, r * W * 3 * sizeof(float), s->stream);
+        if (e == cudaSuccess)
+          e = cudaMemcpyPeerAsync(d_cnt + y * W, root->device, t_cnt + local * W, s->device, r * W * sizeof(int), s->stream);
+        local += r;
+      }
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[ndone], cudaEventDisableTiming);
+    if (e == cudaSuccess) {
+      ndone++;
+      e = cudaEventRecord(done[ndone - 1], s->stream);
+    }
+    if (e != cudaSuccess) {
+      cleanup();
+      return cuda_err(e, "mb200_render_frame_multi: enqueue");
+    }
+  }
+  cudaError_t e = cudaSetDevice(root->device);
+  for (int k = 0; k < ndone && e == cudaSuccess; k++) e = cudaStreamWaitEvent(root->stream, done[k], 0);
+  if (e == cudaSuccess && img_kind != kDevice)
+    e = cudaMemcpyAsync(img_kind == kPinned ? (void *)image : root->out0.pinned, d_img, img_bytes, cudaMemcpyDeviceToHost, root->stream);
+  if (e == cudaSuccess && cnt_kind != kDevice)
+    e = cudaMemcpyAsync(cnt_kind == kPinned ? (void *)count : root->out1.pinned, d_cnt, cnt_bytes, cudaMemcpyDeviceToHost, root->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(root->stream);
+  cleanup();
+  if (e != cudaSuccess) return cuda_err(e, "mb200_render_frame_multi: gather");
+  if (img_kind == kPageable) memcpy(image, root->out0.pinned, img_bytes);
+  if (cnt_kind == kPageable) memcpy(count, root->out1.pinned, cnt_bytes);
+  if (stats) {
+    for (int g = 0; g < n; g++) {
+      unsigned long long c[4] = {0, 0, 0, 0};
+      CU(cudaSetDevice(scenes[g]->device));
+      CU(cudaMemcpy(c, scenes[g]->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+      stats->primary_rays += c[0], stats->bounce_rays += c[1], stats->shadow_rays += c[2], stats->zombie_segments += c[3];
+    }
+    CU(cudaSetDevice(root->device));
+  }
+  return MB200_OK;
+}
+
 int mb200_band_local_rows(const mb200_render_params *p) {
   if (!p) return 0;
   if (p->band_rows <= 0) return p->y1 - p->y0;

@@ -24,9 +24,33 @@ BVHAccel::BVHAccel() : device_(0), dev_(nullptr), devMesh_(nullptr) {}
 BVHAccel::~BVHAccel() { ReleaseDevice(); }
 
 void BVHAccel::ReleaseDevice() {
+  for (mb200_scene *r : replicas_) mb200_scene_destroy(r);
+  replicas_.clear();
   if (dev_) mb200_scene_destroy(dev_);
   dev_ = nullptr;
   devMesh_ = nullptr;
+}
+
+bool BVHAccel::DeviceScenes(const Mesh *mesh, int count, std::vector<mb200_scene *> &out) {
+  out.clear();
+  mb200_scene *first = DeviceScene(mesh);
+  if (!first || count < 1) return false;
+  out.push_back(first);
+  while ((int)replicas_.size() < count - 1) {
+    mb200_scene *r = nullptr;
+    const int rc = mb200_scene_create(&r, device_ + 1 + (int)replicas_.size(), mesh->vertices, mesh->numVertices,
+                                      mesh->faces, mesh->numFaces, mesh->materialIDs, mesh->facevarying_normals,
+                                      mesh->facevarying_uvs, reinterpret_cast<const mb200_bvh_node *>(nodes_.data()),
+                                      nodes_.size(), indices_.data(), indices_.size());
+    if (rc != MB200_OK) {
+      printf("Mallie:err\tmsg:cannot create the scene replica on GPU %d: %s\n", device_ + 1 + (int)replicas_.size(),
+             mb200_last_error());
+      return false;
+    }
+    replicas_.push_back(r);
+  }
+  for (int g = 1; g < count; g++) out.push_back(replicas_[g - 1]);
+  return true;
 }
 
 // BVHAccel::Build (bvh_accel.cc:445-482): binned SAH on the host; the tree is bit-identical to the
@@ -364,8 +388,17 @@ void Render(Scene &scene, const RenderConfig &config, std::vector<float> &image,
   p.pass = g_render.pass++;
   p.pixel_step = step < 1 ? 1 : step;
   memset(image.data(), 0, sizeof(float) * (size_t)width * height * 3); // render.cc:639
-  if (mb200_render_pass(s, &p, image.data(), count.data(), nullptr) != MB200_OK)
+  std::vector<mb200_scene *> gpus;
+  if (config.num_gpus > 1 && p.pixel_step == 1 && scene.DeviceScenes(config.num_gpus, gpus)) {
+    // rows interleaved over the GPUs in bands of 8 scanlines; the frame is assembled on the first GPU
+    std::vector<int> one((size_t)width * height);
+    if (mb200_render_frame_multi(gpus.data(), (int)gpus.size(), &p, 1, 8, image.data(), one.data(), nullptr) != MB200_OK)
+      printf("Mallie:err\tmsg:Render failed: %s\n", mb200_last_error());
+    else
+      for (size_t i = 0; i < one.size(); i++) count[i] += one[i];
+  } else if (mb200_render_pass(s, &p, image.data(), count.data(), nullptr) != MB200_OK) {
     printf("Mallie:err\tmsg:Render failed: %s\n", mb200_last_error());
+  }
   const auto t1 = std::chrono::steady_clock::now();
   const double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
   printf("\r[Mallie] Render time: %f sec(s) | %f fps", ms / 1000.0, 1000.0 / ms);
@@ -390,7 +423,17 @@ double RenderAccumulate(Scene &scene, const RenderConfig &config, std::vector<fl
   g_render.pass += (unsigned int)num_passes;
   mb200_render_stats local;
   const auto t0 = std::chrono::steady_clock::now();
-  if (mb200_render_accumulate(s, &p, num_passes, image.data(), count.data(), &local) != MB200_OK) {
+  std::vector<mb200_scene *> gpus;
+  if (config.num_gpus > 1 && scene.DeviceScenes(config.num_gpus, gpus)) {
+    std::vector<float> sum((size_t)width * height * 3);
+    std::vector<int> cnt((size_t)width * height);
+    if (mb200_render_frame_multi(gpus.data(), (int)gpus.size(), &p, num_passes, 8, sum.data(), cnt.data(), &local) != MB200_OK) {
+      printf("Mallie:err\tmsg:RenderAccumulate failed: %s\n", mb200_last_error());
+      return 0.0;
+    }
+    for (size_t i = 0; i < sum.size(); i++) image[i] += sum[i];
+    for (size_t i = 0; i < cnt.size(); i++) count[i] += cnt[i];
+  } else if (mb200_render_accumulate(s, &p, num_passes, image.data(), count.data(), &local) != MB200_OK) {
     printf("Mallie:err\tmsg:RenderAccumulate failed: %s\n", mb200_last_error());
     return 0.0;
   }

@@ -177,6 +177,8 @@ public:
   void SetDevice(int device) { device_ = device; }
   // Device replica; created lazily from (mesh, nodes_, indices_) on first use.
   mb200_scene *DeviceScene(const Mesh *mesh);
+  // `count` replicas on GPUs device, device + 1, ... (element 0 is DeviceScene()); false if one cannot be made.
+  bool DeviceScenes(const Mesh *mesh, int count, std::vector<mb200_scene *> &out);
   void ReleaseDevice();
 
 private:
@@ -187,6 +189,7 @@ private:
   int device_;
   mb200_scene *dev_;
   const Mesh *devMesh_;
+  std::vector<mb200_scene *> replicas_; // GPUs device_ + 1, ...
 };
 
 // ----------------------------------------------------------------------------
@@ -256,6 +259,7 @@ public:
   // --- additions -----------------------------------------------------------
   void SetDevice(int device) { accel_.SetDevice(device); }
   mb200_scene *DeviceScene() { return accel_.DeviceScene(&mesh_); }
+  bool DeviceScenes(int count, std::vector<mb200_scene *> &out) { return accel_.DeviceScenes(&mesh_, count, out); }
   const Mesh &GetMesh() const { return mesh_; }
   BVHAccel &GetAccel() { return accel_; }
 

@@ -1,6 +1,6 @@
 // host_api_check.cc -- exercises the host C++ mirror of the Mallie API (mallie_api.h) the way a
 // Mallie program would, and dumps what it got so tests/test_gpu_host_api.py can compare it with the
-// oracle:   host_api_check <obj> <out.bin> <width> <height> [plane]
+// oracle:   host_api_check <obj> <out.bin> <width> <height> [plane] [gpus]
 //   1. Scene::Init(obj) (loader + host BVH build), Scene::BoundingBox
 //   2. Camera::BuildCameraFrame + Camera::GenerateRay for every pixel, Scene::TraceBatch
 //   3. Scene::Trace for a handful of single rays (must equal the batch entries)
@@ -29,6 +29,7 @@ int main(int argc, char **argv) {
 
   mallie::RenderConfig config;
   config.width = W, config.height = H, config.plane = plane;
+  if (argc > 6) config.num_gpus = atoi(argv[6]);
   config.eye[0] = 0.4, config.eye[1] = 0.9, config.eye[2] = 6.0;
   config.lookat[0] = 0.5, config.lookat[1] = 0.8, config.lookat[2] = 0.0;
 
