@@ -79,8 +79,7 @@ __global__ void __launch_bounds__(kBlock, MINB)
                unsigned long long *__restrict__ gcounters) {
   extern __shared__ uint4 smem_stack[];
   TravStack<S, CAP> st;
-  st.sm = smem_stack + threadIdx.x;
-  st.stride = kBlock;
+  st.init(smem_stack + threadIdx.x, kBlock);
   if (n_dev) n = __ldg(n_dev);
   trace_state_machine<IO, F32, S, CAP, ANYHIT, COUNT, REFILL_MIN, POLICY, CHUNK, VAR>(sc, io, n, work, st, gcounters);
 }

@@ -116,8 +116,7 @@ __device__ __forceinline__ void trace_multi_ray(const SceneView &sc, const IO &i
                 sm.st2(s, 2, r.ix, r.iy);
                 sm.st2(s, 3, r.iz, dx);
                 sm.st2(s, 4, dy, dz);
-                const uint32_t signs = (r.sx ? 1u : 0u) | (r.sy ? 2u : 0u) | (r.sz ? 4u : 0u);
-                *sm.unit(s, 5) = make_uint4(sc.root_ref, sc.root_cnt, signs << 16, item);
+                *sm.unit(s, 5) = make_uint4(sc.root_ref, sc.root_cnt, r.sgn << 16, item);
                 if (sc.root_cnt == kBranch) {
                   m_inner |= 1u << s;
                 } else {
@@ -150,7 +149,7 @@ __device__ __forceinline__ void trace_multi_ray(const SceneView &sc, const IO &i
       wi = *sm.unit(si, 5);
       ri.ox = a.x, ri.oy = a.y, ri.oz = b.x, hit_i = b.y, ri.ix = c.x, ri.iy = c.y, ri.iz = d.x;
       ri.dx = ri.dy = ri.dz = 0.0;
-      ri.sx = (wi.z >> 16) & 1u, ri.sy = (wi.z >> 17) & 1u, ri.sz = (wi.z >> 18) & 1u;
+      ri.sgn = (wi.z >> 16) & 7u;
       nw = load_pair_node<true>(sc.nodes + wi.x);
     }
     RayD rl;
@@ -162,7 +161,7 @@ __device__ __forceinline__ void trace_multi_ray(const SceneView &sc, const IO &i
       wl = *sm.unit(sl, 5);
       rl.ox = a.x, rl.oy = a.y, rl.oz = b.x, hit_l = b.y, rl.dx = d.y, rl.dy = e.x, rl.dz = e.y;
       rl.ix = rl.iy = rl.iz = 0.0;
-      rl.sx = rl.sy = rl.sz = false;
+      rl.sgn = 0u;
       tv = load_tri_edges<F32>(sc.tris, wl.x);
     }
 

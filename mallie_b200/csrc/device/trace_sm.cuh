@@ -221,7 +221,7 @@ struct IOQueueShadow {
 // VAR: bit set of code-generation variants kept for A/B runs (development builds pick them with
 // MB200_TRACE_VAR; production value kVar in kernels.cu):
 //   1  PairNode fetched with four 256-bit loads (LDG.E.256) instead of seven 128-bit + one 32-bit
-//   2  near/far order from a 3-bit sign mask ((mask >> axis) & 1) instead of a select chain
+//   2  (retired: the direction signs are always one 3-bit mask now, traverse.cuh)
 //   4  leaf prefetch touches only the first 128-byte line of the leaf's records (no per-lane loop)
 //   8  no software prefetch at all
 //  16  branch-free triangle test (one predicate at the end instead of early returns)
@@ -293,7 +293,7 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
   TravCounters cnt = {0u, 0u, 0u};
   unsigned int nrays = 0;
   r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = r.ix = r.iy = r.iz = 0.0;
-  r.sx = r.sy = r.sz = false;
+  r.sgn = 0u;
 
   for (;;) {
     // ---- A. refill idle lanes from the warp's pool of ray indices ----------------------------------
@@ -378,13 +378,7 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
       const bool h0 = slab_test(nw.b[0][0], nw.b[0][1], nw.b[0][2], nw.b[0][3], nw.b[0][4], nw.b[0][5], r, hit_t, t0);
       const bool h1 = slab_test(nw.b[1][0], nw.b[1][1], nw.b[1][2], nw.b[1][3], nw.b[1][4], nw.b[1][5], r, hit_t, t1);
       if (COUNT) cnt.nodes += 2;
-      bool sgn;
-      if (VAR & kVarSignMask) {
-        const uint32_t smask = (r.sx ? 1u : 0u) | (r.sy ? 2u : 0u) | (r.sz ? 4u : 0u);
-        sgn = ((smask >> nw.axis) & 1u) != 0u;
-      } else {
-        sgn = (nw.axis == 0) ? r.sx : ((nw.axis == 1) ? r.sy : r.sz);
-      }
+      const bool sgn = ((r.sgn >> nw.axis) & 1u) != 0u; // dirSign[axis]
       if (h0 && h1) { // near = data[dirSign[axis]] first, far pushed with its tmin (bvh_accel.cc:818-823)
         st.put(sp++, sgn ? t0 : t1, sgn ? nw.ref0 : nw.ref1, sgn ? nw.cnt0 : nw.cnt1);
         if (COUNT) cnt.max_stack = max(cnt.max_stack, (unsigned int)sp + 1u);

@@ -36,13 +36,14 @@ struct RayD {
   double ox, oy, oz;
   double dx, dy, dz;
   double ix, iy, iz; // 1.0 / dir, may be +-inf (bvh_accel.cc:793-797)
-  bool sx, sy, sz;   // dir < 0.0 (so -0.0 counts as non-negative), bvh_accel.cc:787-790
+  uint32_t sgn;      // bit a = (dir[a] < 0.0), so -0.0 counts as non-negative (bvh_accel.cc:787-790); one
+                     // register instead of three flags (which ptxas spilled under the 64-register cap)
 };
 
 __device__ __forceinline__ void ray_setup(RayD &r, double ox, double oy, double oz, double dx, double dy, double dz) {
   r.ox = ox, r.oy = oy, r.oz = oz;
   r.dx = dx, r.dy = dy, r.dz = dz;
-  r.sx = dx < 0.0, r.sy = dy < 0.0, r.sz = dz < 0.0;
+  r.sgn = (dx < 0.0 ? 1u : 0u) | (dy < 0.0 ? 2u : 0u) | (dz < 0.0 ? 4u : 0u);
   r.ix = 1.0 / dx, r.iy = 1.0 / dy, r.iz = 1.0 / dz;
 }
 
@@ -51,12 +52,13 @@ __device__ __forceinline__ void ray_setup(RayD &r, double ox, double oy, double 
 __device__ __forceinline__ bool slab_test(const double b0, const double b1, const double b2, const double b3,
                                           const double b4, const double b5, const RayD &r, const double max_t,
                                           double &tmin_out) {
-  const double min_x = r.sx ? b3 : b0;
-  const double min_y = r.sy ? b4 : b1;
-  const double min_z = r.sz ? b5 : b2;
-  const double max_x = r.sx ? b0 : b3;
-  const double max_y = r.sy ? b1 : b4;
-  const double max_z = r.sz ? b2 : b5;
+  const bool sx = (r.sgn & 1u) != 0u, sy = (r.sgn & 2u) != 0u, sz = (r.sgn & 4u) != 0u;
+  const double min_x = sx ? b3 : b0;
+  const double min_y = sy ? b4 : b1;
+  const double min_z = sz ? b5 : b2;
+  const double max_x = sx ? b0 : b3;
+  const double max_y = sy ? b1 : b4;
+  const double max_z = sz ? b2 : b5;
 
   const double tmin_x = (min_x - r.ox) * r.ix;
   const double tmax_x = (max_x - r.ox) * r.ix;
@@ -160,17 +162,31 @@ __device__ __forceinline__ bool tri_test_edges(double &t_io, double &u_out, doub
 // thread t at [k * blockDim.x + t] -> conflict-free 128-bit accesses), the rest in a per-thread
 // local-memory array.  An entry is (tmin of the pushed child, its ref, its cnt).
 template <int S, int CAP> struct TravStack {
-  uint4 *sm; // this thread's column base
-  int stride;
+  uint32_t sm_addr; // this thread's column base as a shared-window address (kept in one register: without
+                    // it ptxas re-derived the pointer from %tid and the CTA id on every pop)
+  uint32_t stride_bytes;
   uint4 ovf[(CAP > S) ? (CAP - S) : 1];
+  __device__ __forceinline__ void init(uint4 *column, int stride) {
+    sm_addr = (uint32_t)__cvta_generic_to_shared(column);
+    stride_bytes = (uint32_t)stride * 16u;
+  }
   __device__ __forceinline__ void put(int k, double tmin, uint32_t ref, uint32_t cnt) {
     const unsigned long long tb = (unsigned long long)__double_as_longlong(tmin);
     const uint4 e = make_uint4((uint32_t)tb, (uint32_t)(tb >> 32), ref, cnt);
-    if (S > 0 && k < S) sm[k * stride] = e;
+    if (S > 0 && k < S)
+      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sm_addr + (uint32_t)k * stride_bytes), "r"(e.x), "r"(e.y),
+                   "r"(e.z), "r"(e.w)
+                   : "memory");
     else ovf[k - S] = e;
   }
   __device__ __forceinline__ void get(int k, double &tmin, uint32_t &ref, uint32_t &cnt) const {
-    const uint4 e = (S > 0 && k < S) ? sm[k * stride] : ovf[k - S];
+    uint4 e;
+    if (S > 0 && k < S)
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
+                   : "r"(sm_addr + (uint32_t)k * stride_bytes)
+                   : "memory");
+    else e = ovf[k - S];
     tmin = __longlong_as_double((long long)(((unsigned long long)e.y << 32) | e.x));
     ref = e.z;
     cnt = e.w;
