@@ -63,23 +63,35 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The sampler is
+    started before the warm-up (nvidia-smi needs ~0.2 s to deliver its first line) and only the samples whose
+    timestamp falls inside [mark_start(), mark_end()] are used; a timed region shorter than the sampling period
+    falls back to the samples taken under the same load during the warm-up and says so."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.t0 = self.t1 = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -87,25 +99,27 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons, power = [], [], set(), []
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-                power.append(float(c[3]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(c[1]), float(c[2]), float(c[3]),
+                             [nm for k, nm in enumerate(names) if c[5 + k].lower().startswith("active")]))
             except ValueError:
                 continue
-            for k, nm in enumerate(names):
-                if c[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
         os.unlink(self.f.name)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
-                       samples=len(sm), power_w_max=float(max(power)))
+        inside = [r for r in rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1]
+        window = "timed region"
+        if not inside:          # timed region shorter than one sampling period: samples since the warm-up began
+            inside, window = rows, "warm-up + timed region (timed region shorter than the sampling period)"
+        if inside:
+            out.update(sm_mhz=float(np.median([r[1] for r in inside])), sm_max_mhz=float(max(r[2] for r in inside)),
+                       reasons=sorted({nm for r in inside for nm in r[4]}), samples=len(inside),
+                       power_w_max=float(max(r[3] for r in inside)), window=window)
         return out
 
 
@@ -267,14 +281,15 @@ def main():
         torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ value: device-resident
+    sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
         step_device()
     barrier()
     sc.timing(True)                        # CUDA events around every kernel the scene launches
     launches0 = M.capi.launches_issued()
-    sampler = ClockSampler(local_rank)
     evs = []
     barrier()
+    sampler.mark_start()
     for _ in range(args.steps):
         e0, em, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         with torch.cuda.stream(stream):
@@ -285,6 +300,7 @@ def main():
             e1.record(stream)
         evs.append((e0, em, e1))
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     launches = M.capi.launches_issued() - launches0
     kt = sc.kernel_times()
