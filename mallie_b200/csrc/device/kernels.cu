@@ -413,29 +413,46 @@ int env_int(const char *name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
+// Function attributes (dynamic shared memory opt-in, carve-out) are per device: a process that drives several
+// GPUs (mb200_render_frame_multi) sets them once on each.  Returns the persistent grid for the current device.
+template <class Kernel>
+cudaError_t persistent_grid(Kernel k, size_t smem, int minb, int grids[64], int *grid_out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (grids[dev] == 0) {
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    // shared memory for `minb` resident CTAs and no more: what is left of the SM's 256 KB stays L1, which
+    // is what the node / triangle fetches hit in
+    int carve = (int)((smem + 1024) * minb * 100 / (228 * 1024)) + 1;
+    if (carve > 100) carve = 100;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0, sms = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kBlock, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > minb) per_sm = minb;
+    grids[dev] = (sms > 0 ? sms : 148) * per_sm;
+  }
+  *grid_out = grids[dev];
+  return cudaSuccess;
+}
+
 // One persistent wave: a whole number of CTAs per SM.
 template <class IO, bool F32, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int POLICY, int S, int MINB, unsigned CHUNK, int VAR>
 cudaError_t launch_sm(const SceneView &sc, const IO &io, size_t n, const unsigned int *n_dev,
                       unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
   auto k = k_trace_sm<IO, F32, CAP, ANYHIT, COUNT, REFILL_MIN, POLICY, S, MINB, CHUNK, VAR>;
   const size_t smem = (size_t)S * kBlock * sizeof(uint4);
-  static int grid = 0; // per instantiation
-  if (grid == 0) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    // shared memory for MINB resident CTAs and no more: what is left of the SM's 256 KB stays L1, which
-    // is what the node / triangle fetches hit in
-    int carve = (int)((smem + 1024) * MINB * 100 / (228 * 1024)) + 1;
-    if (carve > 100) carve = 100;
-    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kBlock, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > MINB) per_sm = MINB;
-    grid = num_sms() * per_sm;
-  }
+  static int grids[64]; // per instantiation, per device
+  int grid = 0;
+  const cudaError_t ge = persistent_grid(k, smem, MINB, grids, &grid);
+  if (ge != cudaSuccess) return ge;
   k<<<grid, kBlock, smem, s>>>(sc, io, (unsigned long long)n, n_dev, work, counters);
   g_launches++;
   return cudaGetLastError();
@@ -446,21 +463,10 @@ cudaError_t launch_mr(const SceneView &sc, const IO &io, size_t n, const unsigne
                       unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
   auto k = k_trace_mr<IO, F32, K, S, ANYHIT, COUNT, REFILL_MIN, MINB, CHUNK>;
   const size_t smem = (size_t)K * (kSlotUnits + S) * kBlock * sizeof(uint4);
-  static int grid = 0; // per instantiation
-  if (grid == 0) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int carve = (int)((smem + 1024) * MINB * 100 / (228 * 1024)) + 1;
-    if (carve > 100) carve = 100;
-    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kBlock, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > MINB) per_sm = MINB;
-    grid = num_sms() * per_sm;
-  }
+  static int grids[64]; // per instantiation, per device
+  int grid = 0;
+  const cudaError_t ge = persistent_grid(k, smem, MINB, grids, &grid);
+  if (ge != cudaSuccess) return ge;
   k<<<grid, kBlock, smem, s>>>(sc, io, (unsigned long long)n, n_dev, work, counters);
   g_launches++;
   return cudaGetLastError();

@@ -390,9 +390,9 @@ void Render(Scene &scene, const RenderConfig &config, std::vector<float> &image,
   memset(image.data(), 0, sizeof(float) * (size_t)width * height * 3); // render.cc:639
   std::vector<mb200_scene *> gpus;
   if (config.num_gpus > 1 && p.pixel_step == 1 && scene.DeviceScenes(config.num_gpus, gpus)) {
-    // rows interleaved over the GPUs in bands of 8 scanlines; the frame is assembled on the first GPU
+    // rows interleaved over the GPUs in bands of 4 scanlines (one tile row); the frame is assembled on the first GPU
     std::vector<int> one((size_t)width * height);
-    if (mb200_render_frame_multi(gpus.data(), (int)gpus.size(), &p, 1, 8, image.data(), one.data(), nullptr) != MB200_OK)
+    if (mb200_render_frame_multi(gpus.data(), (int)gpus.size(), &p, 1, 4, image.data(), one.data(), nullptr) != MB200_OK)
       printf("Mallie:err\tmsg:Render failed: %s\n", mb200_last_error());
     else
       for (size_t i = 0; i < one.size(); i++) count[i] += one[i];
@@ -427,7 +427,7 @@ double RenderAccumulate(Scene &scene, const RenderConfig &config, std::vector<fl
   if (config.num_gpus > 1 && scene.DeviceScenes(config.num_gpus, gpus)) {
     std::vector<float> sum((size_t)width * height * 3);
     std::vector<int> cnt((size_t)width * height);
-    if (mb200_render_frame_multi(gpus.data(), (int)gpus.size(), &p, num_passes, 8, sum.data(), cnt.data(), &local) != MB200_OK) {
+    if (mb200_render_frame_multi(gpus.data(), (int)gpus.size(), &p, num_passes, 4, sum.data(), cnt.data(), &local) != MB200_OK) {
       printf("Mallie:err\tmsg:RenderAccumulate failed: %s\n", mb200_last_error());
       return 0.0;
     }
