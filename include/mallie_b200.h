@@ -237,6 +237,11 @@ int mb200_camera_frame_build(mb200_camera_frame *out, const double eye[3], const
 /* rays[i] = GenerateRay(px[i], py[i]); px/py/rays host or device. */
 int mb200_generate_rays(mb200_scene *scene, const mb200_camera_frame *frame, const double *px, const double *py,
                         size_t n, mb200_ray *rays);
+/* rays[i] = GenerateEnvRay(px[i], py[i]) or, stereo != 0, GenerateStereoEnvRay(px[i], py[i]) for a width x height
+ * panorama seen from origin (camera.cc:242-329).  sin / cos / fmod / atan2 are CUDA's: directions agree with the
+ * reference's glibc results to a few ulp, not bit for bit. */
+int mb200_generate_rays_env(mb200_scene *scene, const double origin[3], int width, int height, const double *px,
+                            const double *py, size_t n, int stereo, mb200_ray *rays);
 /* Un-jittered primary rays GenerateRay((double)x,(double)y) for the tile [x0,x1)x[y0,y1), row-major. */
 int mb200_generate_rays_grid(mb200_scene *scene, const mb200_camera_frame *frame, int x0, int y0, int x1, int y1,
                              mb200_ray *rays);
@@ -247,8 +252,16 @@ int mb200_generate_rays_grid(mb200_scene *scene, const mb200_camera_frame *frame
 typedef enum {
   MB200_SHADER_PATHTRACE = 0,      /* PathTrace, render.cc:381-456 */
   MB200_SHADER_PRIMARY_SHADOW = 1, /* primary closest hit + one shadow ray to `light` */
-  MB200_SHADER_PRIMARY_ONLY = 2    /* primary closest hit; radiance = |normal| visualisation-free: hit ? 1 : 0 */
+  MB200_SHADER_PRIMARY_ONLY = 2,   /* primary closest hit; radiance = |normal| visualisation-free: hit ? 1 : 0 */
+  MB200_SHADER_PATHTRACE_ENV = 3   /* PathTraceEnv, render.cc:518-590: PathTrace without the plane and without the
+                                      material attenuation (miss term 0.5 / pathLength); used by RenderPanoramic */
 } mb200_shader;
+
+typedef enum {
+  MB200_CAMERA_PINHOLE = 0,   /* Camera::GenerateRay,          camera.cc:222-240 */
+  MB200_CAMERA_ENV = 1,       /* Camera::GenerateEnvRay,       camera.cc:242-257 (equirectangular panorama) */
+  MB200_CAMERA_ENV_STEREO = 2 /* Camera::GenerateStereoEnvRay, camera.cc:259-329 (top / bottom stereo pair) */
+} mb200_camera_mode;
 
 typedef struct {
   int width, height;          /* full image size (RenderConfig::width/height)                        */
@@ -271,6 +284,7 @@ typedef struct {
    * tile), and count += 3 for every pixel of the block -- the reference increments it inside the k < 3
    * colour loop (render.cc:689-693).  Not combinable with band_rows. */
   int pixel_step;
+  int camera_mode;            /* mb200_camera_mode; the panorama cameras use frame.origin and width / height only */
 } mb200_render_params;
 
 typedef struct {

@@ -24,7 +24,8 @@ NODE_DTYPE = np.dtype([("bmin", "<f8", 3), ("bmax", "<f8", 3), ("flag", "<i4"), 
 assert RAY_DTYPE.itemsize == 48 and HIT_DTYPE.itemsize == 32
 assert ISECT_DTYPE.itemsize == 184 and NODE_DTYPE.itemsize == 64
 
-SHADER_PATHTRACE, SHADER_PRIMARY_SHADOW, SHADER_PRIMARY_ONLY = 0, 1, 2
+SHADER_PATHTRACE, SHADER_PRIMARY_SHADOW, SHADER_PRIMARY_ONLY, SHADER_PATHTRACE_ENV = 0, 1, 2, 3
+CAMERA_PINHOLE, CAMERA_ENV, CAMERA_ENV_STEREO = 0, 1, 2
 
 # Every symbol include/mallie_b200.h declares (tests/test_abi.py checks the header against this list).
 EXPORTS = [
@@ -36,7 +37,7 @@ EXPORTS = [
     "mb200_scene_stream", "mb200_scene_device", "mb200_scene_uses_f32_vertices", "mb200_scene_synchronize",
     "mb200_scene_timing", "mb200_scene_kernel_times",
     "mb200_trace_closest", "mb200_trace_closest_full", "mb200_trace_occluded", "mb200_trace_closest_async",
-    "mb200_camera_frame_build", "mb200_generate_rays", "mb200_generate_rays_grid",
+    "mb200_camera_frame_build", "mb200_generate_rays", "mb200_generate_rays_env", "mb200_generate_rays_grid",
     "mb200_render_params_default", "mb200_plane_from_bounds", "mb200_render_pass", "mb200_render_accumulate",
     "mb200_render_frame", "mb200_render_frame_multi", "mb200_band_local_rows",
     "mb200_mesh_load_obj", "mb200_mesh_load_eson", "mb200_mesh_transform", "mb200_mesh_num_vertices",
@@ -73,7 +74,7 @@ class RenderParams(C.Structure):
                 ("max_path_length", C.c_int), ("pass_", C.c_uint32), ("jitter", C.c_int), ("shader", C.c_int),
                 ("light", C.c_double * 3),
                 ("band_rows", C.c_int), ("band_count", C.c_int), ("band_index", C.c_int), ("band_compact", C.c_int),
-                ("pixel_step", C.c_int)]
+                ("pixel_step", C.c_int), ("camera_mode", C.c_int)]
 
 
 class RenderStats(C.Structure):
@@ -159,6 +160,7 @@ def lib():
         L.mb200_camera_frame_build.argtypes = [C.POINTER(CameraFrame), vp, vp, vp, dbl, vp, i32, i32]
         L.mb200_generate_rays.argtypes = [vp, C.POINTER(CameraFrame), vp, vp, sz, vp]
         L.mb200_generate_rays_grid.argtypes = [vp, C.POINTER(CameraFrame), i32, i32, i32, i32, vp]
+        L.mb200_generate_rays_env.argtypes = [vp, vp, i32, i32, vp, vp, sz, i32, vp]
         L.mb200_render_params_default.argtypes = [C.POINTER(RenderParams), i32, i32]
         L.mb200_plane_from_bounds.argtypes = [vp, vp, vp]
         L.mb200_render_pass.argtypes = [vp, C.POINTER(RenderParams), vp, vp, C.POINTER(RenderStats)]
@@ -429,6 +431,14 @@ class Scene:
         check(lib().mb200_generate_rays(self.h, C.byref(frame), _p(px), _p(py), px.size, _p(rays)))
         return rays
 
+    def generate_rays_env(self, origin, width, height, px, py, stereo=False):
+        """Camera::GenerateEnvRay / GenerateStereoEnvRay for arrays of pixel coordinates."""
+        o = np.ascontiguousarray(origin, np.float64)
+        px, py = np.ascontiguousarray(px, np.float64).reshape(-1), np.ascontiguousarray(py, np.float64).reshape(-1)
+        rays = np.zeros((px.size, 6))
+        check(lib().mb200_generate_rays_env(self.h, _p(o), width, height, _p(px), _p(py), px.size, int(stereo), _p(rays)))
+        return rays
+
     def generate_rays_grid(self, frame, x0, y0, x1, y1, out=None):
         if out is None:
             out = np.zeros(((y1 - y0) * (x1 - x0), 6))
@@ -437,7 +447,8 @@ class Scene:
 
     # -- frame
     def render_params(self, frame, width, height, tile=None, plane=None, max_path_length=16, pass_index=0,
-                      jitter=True, shader=SHADER_PATHTRACE, light=(0.0, 20.0, 0.0), bands=None, compact=False, step=1):
+                      jitter=True, shader=SHADER_PATHTRACE, light=(0.0, 20.0, 0.0), bands=None, compact=False, step=1,
+                      camera_mode=0):
         """bands = (band_rows, band_count, band_index) enables the multi-GPU row-band interleave; step is
         Render()'s coarse-preview step (render.cc:657-698)."""
         p = RenderParams()
@@ -456,6 +467,7 @@ class Scene:
             p.band_rows, p.band_count, p.band_index = bands
             p.band_compact = int(compact)
         p.pixel_step = int(step)
+        p.camera_mode = int(camera_mode)
         return p
 
     @staticmethod

@@ -432,6 +432,27 @@ int mb200_generate_rays(mb200_scene *s, const mb200_camera_frame *frame, const d
   return MB200_OK;
 }
 
+int mb200_generate_rays_env(mb200_scene *s, const double origin[3], int width, int height, const double *px,
+                            const double *py, size_t n, int stereo, mb200_ray *rays) {
+  if (!s || !origin || width <= 0 || height <= 0 || (n && (!px || !py || !rays)))
+    return set_err(MB200_ERR_INVALID_ARG, "bad argument");
+  if (n == 0) return MB200_OK;
+  CU(cudaSetDevice(s->device));
+  const void *d_px, *d_py;
+  void *d_rays;
+  bool staged;
+  int rc;
+  if ((rc = stage_in(s, s->in0, px, n * sizeof(double), &d_px)) != MB200_OK) return rc;
+  if ((rc = stage_in(s, s->in1, py, n * sizeof(double), &d_py)) != MB200_OK) return rc;
+  if ((rc = stage_out_begin(s->out0, rays, n * sizeof(mb200_ray), &d_rays, &staged)) != MB200_OK) return rc;
+  CU(mb200::launch_generate_rays_env(origin, width, height, stereo, (const double *)d_px, (const double *)d_py, n,
+                                     (mb200_ray *)d_rays, s->stream));
+  if (staged && (rc = stage_out_enqueue(s, s->out0, n * sizeof(mb200_ray))) != MB200_OK) return rc;
+  CU(cudaStreamSynchronize(s->stream));
+  if (staged) memcpy(rays, s->out0.pinned, n * sizeof(mb200_ray));
+  return MB200_OK;
+}
+
 int mb200_generate_rays_grid(mb200_scene *s, const mb200_camera_frame *frame, int x0, int y0, int x1, int y1,
                              mb200_ray *rays) {
   if (!s || !frame || !rays || x1 < x0 || y1 < y0) return set_err(MB200_ERR_INVALID_ARG, "bad argument");
@@ -477,7 +498,9 @@ static int render_common(mb200_scene *s, const mb200_render_params *p, int num_p
   if (p->width <= 0 || p->height <= 0 || p->x0 < 0 || p->y0 < 0 || p->x1 > p->width || p->y1 > p->height ||
       p->x0 > p->x1 || p->y0 > p->y1 || p->max_path_length < 1 || num_passes < 1)
     return set_err(MB200_ERR_INVALID_ARG, "bad render parameters");
-  if (p->shader < 0 || p->shader > MB200_SHADER_PRIMARY_ONLY) return set_err(MB200_ERR_INVALID_ARG, "unknown shader");
+  if (p->shader < 0 || p->shader > MB200_SHADER_PATHTRACE_ENV) return set_err(MB200_ERR_INVALID_ARG, "unknown shader");
+  if (p->camera_mode < 0 || p->camera_mode > MB200_CAMERA_ENV_STEREO)
+    return set_err(MB200_ERR_INVALID_ARG, "unknown camera mode");
   if (p->band_rows < 0 || (p->band_rows > 0 && (p->band_rows % 4 != 0 || p->band_count < 1 || p->band_index < 0 ||
                                                  p->band_index >= p->band_count)))
     return set_err(MB200_ERR_INVALID_ARG, "bad band parameters (band_rows must be a multiple of 4)");
@@ -568,7 +591,8 @@ int mb200_render_frame_multi(mb200_scene *const *scenes, int n, const mb200_rend
   if (n == 1) return render_common(scenes[0], p, num_passes, 2, image, count, stats);
   if (p->width <= 0 || p->height <= 0 || p->x0 != 0 || p->y0 != 0 || p->x1 != p->width || p->y1 != p->height ||
       p->band_rows != 0 || p->pixel_step > 1 || p->max_path_length < 1 || num_passes < 1 || band_rows < 4 ||
-      band_rows % 4 != 0 || p->shader < 0 || p->shader > MB200_SHADER_PRIMARY_ONLY)
+      band_rows % 4 != 0 || p->shader < 0 || p->shader > MB200_SHADER_PATHTRACE_ENV || p->camera_mode < 0 ||
+      p->camera_mode > MB200_CAMERA_ENV_STEREO)
     return set_err(MB200_ERR_INVALID_ARG,
                    "multi-GPU frames need whole-image parameters without bands / step and band_rows = 4k");
   if (n > 64) return set_err(MB200_ERR_INVALID_ARG, "too many scenes");

@@ -11,8 +11,10 @@
 // (no FMA contraction: see traverse.cuh).
 #include "kernels.h"
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "shade.cuh"
 #include "trace_mr.cuh"
@@ -65,6 +67,20 @@ __global__ void __launch_bounds__(256) k_generate_grid(const __grid_constant__ m
     double dx, dy, dz;
     generate_ray(frame, (double)x, (double)y, dx, dy, dz);
     store_ray(rays + i, frame, dx, dy, dz);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_generate_rays_env(const __grid_constant__ mb200_camera_frame frame, int width,
+                                                           int height, int stereo, const double *__restrict__ px,
+                                                           const double *__restrict__ py, size_t n,
+                                                           mb200_ray *__restrict__ rays) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double ox, oy, oz, dx, dy, dz;
+    generate_env_ray(frame.origin, width, height, px[i], py[i], stereo != 0, ox, oy, oz, dx, dy, dz);
+    double2 *o = reinterpret_cast<double2 *>(rays + i);
+    o[0] = make_double2(ox, oy);
+    o[1] = make_double2(oz, dx);
+    o[2] = make_double2(dy, dz);
   }
 }
 
@@ -229,9 +245,9 @@ __global__ void __launch_bounds__(256)
   unsigned int zombies = 0;
   if (valid) {
     Xorshift128 rng;
-    double dx, dy, dz;
-    camera_sample(p, x, y, pass, rng, dx, dy, dz);
-    const double ox = p.frame.origin[0], oy = p.frame.origin[1], oz = p.frame.origin[2];
+    double ox, oy, oz, dx, dy, dz;
+    camera_sample(p, x, y, pass, rng, ox, oy, oz, dx, dy, dz);
+    const bool env = p.shader == MB200_SHADER_PATHTRACE_ENV;
     double t, u, v;
     uint32_t face, mat;
     load_hit(hits + i, t, u, v, face, mat);
@@ -244,7 +260,8 @@ __global__ void __launch_bounds__(256)
       nx = d.nx, ny = d.ny, nz = d.nz;
       cur_mat = mat;
     }
-    if (p.use_plane) hit |= plane_intersect(p.plane, ox, oy, oz, dx, dy, dz, t, nx, ny, nz, cur_mat);
+    if (p.use_plane && !env) hit |= plane_intersect(p.plane, ox, oy, oz, dx, dy, dz, t, nx, ny, nz, cur_mat);
+    if (env) cur_mat = 0xFFFFFFFFu; // PathTraceEnv never attenuates (render.cc:518-590)
     if (hit) {
       const double hx = ox + t * dx, hy = oy + t * dy, hz = oz + t * dz;
       if (p.shader == MB200_SHADER_PRIMARY_ONLY) {
@@ -319,7 +336,9 @@ __global__ void __launch_bounds__(256)
         nx = d.nx, ny = d.ny, nz = d.nz;
         cur_mat = mat;
       }
-      if (p.use_plane) hit |= plane_intersect(p.plane, ox, oy, oz, dx, dy, dz, t, nx, ny, nz, cur_mat);
+      const bool env = p.shader == MB200_SHADER_PATHTRACE_ENV;
+      if (p.use_plane && !env) hit |= plane_intersect(p.plane, ox, oy, oz, dx, dy, dz, t, nx, ny, nz, cur_mat);
+      if (env) cur_mat = 0xFFFFFFFFu;
       if (!hit) { // escaped: this segment and every later one adds throughput*0.5/pathLength
         radiance += thr * 0.5 / (double)len;
         zombies += zombie_tail(len, max_len, cur_mat, thr, radiance);
@@ -396,7 +415,7 @@ __global__ void k_add_stats(const unsigned long long *__restrict__ batch, const 
 // launch helpers
 // ---------------------------------------------------------------------------
 int g_num_sms = 0;
-int g_launches = 0;
+std::atomic<int> g_launches{0}; // hosts may drive one scene per thread
 
 int num_sms() {
   if (g_num_sms == 0) {
@@ -575,7 +594,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 } // namespace
 
-int launches_issued() { return g_launches; }
+int launches_issued() { return g_launches.load(); }
 
 // ---------------------------------------------------------------------------
 // KernelTimer
@@ -675,6 +694,17 @@ cudaError_t launch_generate_rays(const mb200_camera_frame &f, const double *px, 
   return cudaGetLastError();
 }
 
+cudaError_t launch_generate_rays_env(const double origin[3], int width, int height, int stereo, const double *px,
+                                     const double *py, size_t n, mb200_ray *rays, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  mb200_camera_frame f;
+  memset(&f, 0, sizeof(f));
+  for (int c = 0; c < 3; c++) f.origin[c] = origin[c];
+  k_generate_rays_env<<<flat_grid(n, 256), 256, 0, s>>>(f, width, height, stereo, px, py, n, rays);
+  g_launches++;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_generate_grid(const mb200_camera_frame &f, int x0, int y0, int w, int h, mb200_ray *rays,
                                  cudaStream_t s) {
   const size_t n = (size_t)w * h;
@@ -723,7 +753,7 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
   const size_t tiles = frame_map_tiles(m0);
   if (tiles == 0 || num_passes < 1) return cudaSuccess;
   if (tiles * 32 > 0xFFFFFFE0ull) return cudaErrorInvalidValue;
-  const bool path = p.shader == MB200_SHADER_PATHTRACE && p.max_path_length > 1;
+  const bool path = (p.shader == MB200_SHADER_PATHTRACE || p.shader == MB200_SHADER_PATHTRACE_ENV) && p.max_path_length > 1;
   const bool shadow = p.shader == MB200_SHADER_PRIMARY_SHADOW;
 
   size_t per_batch = batch_item_budget() / (tiles * 32);

@@ -43,6 +43,8 @@ cudaError_t launch_build_isects(const SceneView &sc, const mb200_ray *rays, cons
                                 mb200_isect *isects, unsigned char *mask, cudaStream_t s);
 cudaError_t launch_generate_rays(const mb200_camera_frame &f, const double *px, const double *py, size_t n,
                                  mb200_ray *rays, cudaStream_t s);
+cudaError_t launch_generate_rays_env(const double origin[3], int width, int height, int stereo, const double *px,
+                                     const double *py, size_t n, mb200_ray *rays, cudaStream_t s);
 cudaError_t launch_generate_grid(const mb200_camera_frame &f, int x0, int y0, int w, int h, mb200_ray *rays,
                                  cudaStream_t s);
 

@@ -62,10 +62,40 @@ __device__ __forceinline__ void rng_seed_pixel(Xorshift128 &g, uint32_t pixel, u
   if ((g.x | g.y | g.z | g.w) == 0u) g.w = 88675123u;
 }
 
-// The camera ray of sample `pass` of pixel (px, py): PathTrace's prologue (render.cc:386-393).
-// Leaves rng positioned after the two jitter draws.
+// Camera::GenerateEnvRay (camera.cc:242-257) / GenerateStereoEnvRay (camera.cc:259-329)
+__device__ __forceinline__ void generate_env_ray(const double origin[3], int width, int height, double u, double v,
+                                                 bool stereo, double &ox, double &oy, double &oz, double &dx,
+                                                 double &dy, double &dz) {
+  const double kPi = 3.14159265358979323846;
+  ox = origin[0], oy = origin[1], oz = origin[2];
+  const double phi = 2.0 * kPi * (u / (double)width);
+  if (!stereo) {
+    const double theta = kPi * (v / (double)height);
+    dx = sin(theta) * cos(phi);
+    dy = cos(theta);
+    dz = sin(theta) * sin(phi);
+    return;
+  }
+  const bool left = v < (double)(height >> 1);
+  const double focal_length = 4.0, r = 0.5;
+  const double theta = kPi * fmod(2.0 * v / (double)height, 1.0);
+  const double ex = sin(theta) * cos(phi), ey = cos(theta), ez = sin(theta) * sin(phi);
+  double px = left ? -ez : ez, py = 0.0, pz = left ? ex : -ex;
+  normalize3(px, py, pz);
+  ox += px * r, oy += py * r, oz += pz * r;
+  double psi = atan2(r, focal_length);
+  if (left) psi = -psi;
+  dx = ex * cos(psi) - ez * sin(psi);
+  dy = ey;
+  dz = ex * sin(psi) + ez * cos(psi);
+  normalize3(dx, dy, dz);
+}
+
+// The camera ray of sample `pass` of pixel (px, py): PathTrace's / PathTraceEnv's prologue
+// (render.cc:386-393, 524-533).  Leaves rng positioned after the two jitter draws.
 __device__ __forceinline__ void camera_sample(const mb200_render_params &p, int px, int py, uint32_t pass,
-                                              Xorshift128 &rng, double &dx, double &dy, double &dz) {
+                                              Xorshift128 &rng, double &ox, double &oy, double &oz, double &dx,
+                                              double &dy, double &dz) {
   rng_seed_pixel(rng, (uint32_t)((size_t)py * p.width + px), pass);
   double fu = (double)px, fv = (double)py;
   if (p.jitter) {
@@ -74,7 +104,13 @@ __device__ __forceinline__ void camera_sample(const mb200_render_params &p, int 
     fu = (double)((float)px + ju); // int + float is a float add (render.cc:391)
     fv = (double)((float)py + jv);
   }
-  generate_ray(p.frame, fu, fv, dx, dy, dz);
+  if (p.camera_mode == MB200_CAMERA_PINHOLE) {
+    ox = p.frame.origin[0], oy = p.frame.origin[1], oz = p.frame.origin[2];
+    generate_ray(p.frame, fu, fv, dx, dy, dz);
+  } else {
+    generate_env_ray(p.frame.origin, p.width, p.height, fu, fv, p.camera_mode == MB200_CAMERA_ENV_STEREO, ox, oy, oz,
+                     dx, dy, dz);
+  }
 }
 
 // Plane::intersect (prim-plane.cc:8-44): float vn / on_d / t.

@@ -136,8 +136,7 @@ struct IOCamera {
     const int x = c.x_tile + lx * m.step, y = c.y_tile + ly * m.step;
     if (!(x < m.x1 && ly < c.rows_valid)) return false;
     Xorshift128 rng;
-    camera_sample(p, x, y, c.pass, rng, dx, dy, dz);
-    ox = p.frame.origin[0], oy = p.frame.origin[1], oz = p.frame.origin[2];
+    camera_sample(p, x, y, c.pass, rng, ox, oy, oz, dx, dy, dz);
     t0 = DBL_MAX;
     return true;
   }
@@ -151,8 +150,7 @@ struct IOCamera {
     store_miss(hits + i);
     if (!item_pixel(m, i, x, y, rl, pass)) return false;
     Xorshift128 rng;
-    camera_sample(p, x, y, pass, rng, dx, dy, dz);
-    ox = p.frame.origin[0], oy = p.frame.origin[1], oz = p.frame.origin[2];
+    camera_sample(p, x, y, pass, rng, ox, oy, oz, dx, dy, dz);
     t0 = DBL_MAX;
     return true;
   }

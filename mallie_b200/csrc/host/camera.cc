@@ -210,4 +210,33 @@ Ray Camera::GenerateRay(double u, double v) const {
   return ray;
 }
 
+// Camera::GenerateEnvRay (camera.cc:242-257): host version for single rays (same libm as the reference).
+Ray Camera::GenerateEnvRay(double u, double v) const {
+  const double theta = M_PI * (v / height_);
+  const double phi = 2.0 * M_PI * (u / width_);
+  Ray ray;
+  ray.org = real3(origin_[0], origin_[1], origin_[2]);
+  ray.dir = real3(sin(theta) * cos(phi), cos(theta), sin(theta) * sin(phi));
+  return ray;
+}
+
+// Camera::GenerateStereoEnvRay (camera.cc:259-329): upper half of the image = left eye.
+Ray Camera::GenerateStereoEnvRay(double u, double v) const {
+  const bool left = v < (height_ >> 1);
+  const double focal_length = 4.0, r = 0.5;
+  const double theta = M_PI * fmod(2.0 * v / height_, 1.0);
+  const double phi = 2.0 * M_PI * (u / width_);
+  const real3 d0(sin(theta) * cos(phi), cos(theta), sin(theta) * sin(phi));
+  real3 parallax = left ? real3(-d0.z, 0.0, d0.x) : real3(d0.z, 0.0, -d0.x);
+  parallax.normalize();
+  parallax = parallax * r;
+  Ray ray;
+  ray.org = real3(origin_[0] + parallax.x, origin_[1] + parallax.y, origin_[2] + parallax.z);
+  double psi = atan2(r, focal_length);
+  if (left) psi = -psi;
+  ray.dir = real3(d0.x * cos(psi) - d0.z * sin(psi), d0.y, d0.x * sin(psi) + d0.z * cos(psi));
+  ray.dir.normalize();
+  return ray;
+}
+
 } // namespace mallie

@@ -405,6 +405,39 @@ void Render(Scene &scene, const RenderConfig &config, std::vector<float> &image,
   fflush(stdout);
 }
 
+void RenderPanoramic(Scene &scene, const RenderConfig &config, std::vector<float> &image, std::vector<int> &count,
+                     const double eye[3], const double lookat[3], const double up[3], const double quat[4],
+                     bool stereo) {
+  const int width = config.width, height = config.height;
+  assert(image.size() >= (size_t)3 * width * height);
+  assert(count.size() >= (size_t)width * height);
+  const auto t0 = std::chrono::steady_clock::now();
+  mb200_scene *s = scene.DeviceScene();
+  if (!s) {
+    printf("Mallie:err\tmsg:RenderPanoramic: no device scene (%s)\n", mb200_last_error());
+    return;
+  }
+  mb200_render_params p;
+  mb200_render_params_default(&p, width, height);
+  Camera camera(eye, lookat, up);
+  double origin[3], corner[3], du[3], dv[3];
+  camera.BuildCameraFrame(origin, corner, du, dv, config.fov, quat, width, height);
+  for (int c = 0; c < 3; c++)
+    p.frame.origin[c] = origin[c], p.frame.corner[c] = corner[c], p.frame.du[c] = du[c], p.frame.dv[c] = dv[c];
+  p.max_path_length = config.max_path_length;
+  p.shader = MB200_SHADER_PATHTRACE_ENV;
+  p.camera_mode = stereo ? MB200_CAMERA_ENV_STEREO : MB200_CAMERA_ENV;
+  p.pass = g_render.pass;
+  g_render.pass += 10u;
+  memset(image.data(), 0, sizeof(float) * (size_t)width * height * 3); // render.cc:740
+  if (mb200_render_accumulate(s, &p, 10, image.data(), count.data(), nullptr) != MB200_OK)
+    printf("Mallie:err\tmsg:RenderPanoramic failed: %s\n", mb200_last_error());
+  const auto t1 = std::chrono::steady_clock::now();
+  const double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  printf("\r[Mallie] Render time: %f sec(s) | %f fps", ms / 1000.0, 1000.0 / ms);
+  fflush(stdout);
+}
+
 double RenderAccumulate(Scene &scene, const RenderConfig &config, std::vector<float> &image, std::vector<int> &count,
                         const double eye[3], const double lookat[3], const double up[3], const double quat[4],
                         int num_passes, mb200_render_stats *stats) {

@@ -217,6 +217,8 @@ public:
   void BuildCameraFrame(double origin[3], double corner[3], double u[3], double v[3], double fov,
                         const double quat[4], int width, int height);
   Ray GenerateRay(double u, double v) const;
+  Ray GenerateEnvRay(double u, double v) const;       // camera.cc:242-257
+  Ray GenerateStereoEnvRay(double u, double v) const; // camera.cc:259-329
 
   double eye_[3];
   double up_[3];
@@ -312,6 +314,12 @@ struct RenderConfig {
 // (render.cc:593-708).  Blocking; prints the "[Mallie] Render time" line.
 void Render(Scene &scene, const RenderConfig &config, std::vector<float> &image, std::vector<int> &count,
             const double eye[3], const double lookat[3], const double up[3], const double quat[4], int step);
+
+// RenderPanoramic (render.h:56-61, render.cc:710-763): image zeroed, then TEN samples of PathTraceEnv per pixel
+// through the equirectangular (or top/bottom stereo) panorama camera are added, count += 10.
+void RenderPanoramic(Scene &scene, const RenderConfig &config, std::vector<float> &image, std::vector<int> &count,
+                     const double eye[3], const double lookat[3], const double up[3], const double quat[4],
+                     bool stereo);
 
 // num_passes passes accumulated on the GPU (the SDL render thread's loop, main_sdl.cc:572-606):
 // image += sum of passes, count += num_passes.  Returns Mrays/s of the call.

@@ -762,6 +762,42 @@ void ora_generate_ray(const double origin[3], const double corner[3], const doub
   ray6[3] = d.x; ray6[4] = d.y; ray6[5] = d.z;
 }
 
+/* Camera::GenerateEnvRay, camera.cc:242-257, and GenerateStereoEnvRay, camera.cc:259-329 */
+void ora_generate_env_ray(const double origin[3], int width, int height, double u, double v, int stereo,
+                          double ray6[6]) {
+  if (!stereo) {
+    double theta = M_PI * (v / height);
+    double phi = 2.0 * M_PI * (u / width);
+    ray6[0] = origin[0]; ray6[1] = origin[1]; ray6[2] = origin[2];
+    ray6[3] = sin(theta) * cos(phi);
+    ray6[4] = cos(theta);
+    ray6[5] = sin(theta) * sin(phi);
+    return;
+  }
+  const int is_left_side = v < (height >> 1);
+  const double focal_length = 4.0, r = 0.5;
+  double theta = M_PI * fmod(2.0 * v / height, 1.0);
+  double phi = 2.0 * M_PI * (u / width);
+  v3 d0;
+  d0.x = sin(theta) * cos(phi);
+  d0.y = cos(theta);
+  d0.z = sin(theta) * sin(phi);
+  v3 par;
+  if (is_left_side) { par.x = -d0.z; par.y = 0.0; par.z = d0.x; }
+  else { par.x = d0.z; par.y = 0.0; par.z = -d0.x; }
+  par = v3_normalize(par);
+  par = v3_scale(par, r);
+  ray6[0] = origin[0] + par.x; ray6[1] = origin[1] + par.y; ray6[2] = origin[2] + par.z;
+  double psi = atan2(r, focal_length);
+  if (is_left_side) psi = -psi;
+  v3 d;
+  d.x = d0.x * cos(psi) - d0.z * sin(psi);
+  d.y = d0.y;
+  d.z = d0.x * sin(psi) + d0.z * cos(psi);
+  d = v3_normalize(d);
+  ray6[3] = d.x; ray6[4] = d.y; ray6[5] = d.z;
+}
+
 void ora_generate_grid(const double origin[3], const double corner[3], const double du[3], const double dv[3],
                        int width, int height, double *rays) {
 #pragma omp parallel for
@@ -888,7 +924,11 @@ static v3 path_trace(const ora_bvh *b, const ora_mesh *mesh, const ora_render_pa
   float ju = (float)(ora_randomreal(rng) - 0.5);
   float jv = (float)(ora_randomreal(rng) - 0.5);
   double ray[6];
-  ora_generate_ray(p->origin, p->corner, p->du, p->dv, (double)(px + ju), (double)(py + jv), ray);
+  /* PathTraceEnv (render.cc:518-590) is PathTrace with a panorama camera, without the plane and without
+   * the material attenuation (its `throughput` is never used; the miss term is kd / pathLength, kd = 0.5) */
+  const int env = p->shader == 2;
+  if (p->camera_mode == 0) ora_generate_ray(p->origin, p->corner, p->du, p->dv, (double)(px + ju), (double)(py + jv), ray);
+  else ora_generate_env_ray(p->origin, p->width, p->height, (double)(px + ju), (double)(py + jv), p->camera_mode == 2, ray);
 
   ora_isect is;
   memset(&is, 0, sizeof(is));
@@ -908,7 +948,7 @@ static v3 path_trace(const ora_bvh *b, const ora_mesh *mesh, const ora_render_pa
         cnt[3] += tc[0];
         cnt[4] += tc[1];
       }
-      if (p->use_plane) hit |= ora_plane_intersect(p->plane, ray, ray + 3, &is);
+      if (p->use_plane && !env) hit |= ora_plane_intersect(p->plane, ray, ray + 3, &is);
     }
     if (!hit) {
       if (len < 2) break; /* kMinPathLength */
@@ -922,7 +962,7 @@ static v3 path_trace(const ora_bvh *b, const ora_mesh *mesh, const ora_render_pa
       /* the three RNG draws are unobservable with per-pixel seeding; the sequential reference
        * stream (rng_mode 0) must still consume them to stay aligned for the following pixels */
       if (p->rng_mode == 0) { (void)ora_randomreal(rng); (void)ora_randomreal(rng); (void)ora_randomreal(rng); }
-      if (is.material_id != (uint32_t)-1) { thr.x *= 0.5; thr.y *= 0.5; thr.z *= 0.5; }
+      if (!env && is.material_id != (uint32_t)-1) { thr.x *= 0.5; thr.y *= 0.5; thr.z *= 0.5; }
       continue;
     }
     v3 org = v3_ptr(ray), dir = v3_ptr(ray + 3);
@@ -932,7 +972,7 @@ static v3 path_trace(const ora_bvh *b, const ora_mesh *mesh, const ora_render_pa
     double ndoti = v3_dot(n, v3_neg(dir));
     if (ndoti < 0.0) n = v3_neg(n);
     v3 nd = sample_diffuse(rng, n);
-    if (is.material_id != (uint32_t)-1) { /* Scene::GetMaterial -> default diffuse 0.5, scene.h:58-65 */
+    if (!env && is.material_id != (uint32_t)-1) { /* Scene::GetMaterial -> default diffuse 0.5, scene.h:58-65 */
       thr.x *= 0.5; thr.y *= 0.5; thr.z *= 0.5;
     }
     v3 no = v3_add(hit_p, v3_scale(nd, kRenderEPS));
@@ -995,7 +1035,7 @@ static v3 primary_shadow(const ora_bvh *b, const ora_mesh *mesh, const ora_rende
 /* One pixel sample with either shader. */
 static v3 shade_pixel(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, ora_rng *rng, int x, int y,
                       uint64_t c[7], double *primary_out, double *shadow_out) {
-  if (p->shader == 0) return path_trace(b, mesh, p, rng, x, y, c);
+  if (p->shader == 0 || p->shader == 2) return path_trace(b, mesh, p, rng, x, y, c);
   return primary_shadow(b, mesh, p, rng, x, y, c, primary_out, shadow_out);
 }
 
@@ -1056,6 +1096,49 @@ void ora_render_pass_ex(const ora_bvh *b, const ora_mesh *mesh, const ora_render
 void ora_render_pass(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, int x0, int y0, int x1,
                      int y1, float *image, int *count, uint64_t ray_counts[7], int nthreads) {
   ora_render_pass_ex(b, mesh, p, x0, y0, x1, y1, image, count, ray_counts, nthreads, NULL, NULL);
+}
+
+/* RenderPanoramic, render.cc:710-763 */
+void ora_render_panoramic(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p0, float *image,
+                          int *count, int nthreads) {
+  ora_render_params p = *p0;
+  p.shader = 2;
+  p.use_plane = 0;
+  const int W = p.width, H = p.height;
+  memset(image, 0, sizeof(float) * (size_t)W * H * 3);
+  if (p.rng_mode == 0) {
+    ora_rng rng;
+    ora_rng_seed_reference(&rng, 0);
+    for (int y = 0; y < H; y++)
+      for (int x = 0; x < W; x++)
+        for (int i = 0; i < 10; i++) {
+          uint64_t c[7] = {0, 0, 0, 0, 0, 0, 0};
+          size_t pix = (size_t)y * W + x;
+          v3 r = path_trace(b, mesh, &p, &rng, x, y, c);
+          image[3 * pix + 0] += r.x;
+          image[3 * pix + 1] += r.y;
+          image[3 * pix + 2] += r.z;
+          count[pix]++;
+        }
+    return;
+  }
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++)
+      for (int i = 0; i < 10; i++) {
+        ora_rng rng;
+        size_t pix = (size_t)y * W + x;
+        ora_rng_seed_pixel(&rng, (uint32_t)pix, p0->pass + (uint32_t)i);
+        uint64_t c[7] = {0, 0, 0, 0, 0, 0, 0};
+        v3 r = path_trace(b, mesh, &p, &rng, x, y, c);
+        image[3 * pix + 0] += r.x;
+        image[3 * pix + 1] += r.y;
+        image[3 * pix + 2] += r.z;
+        count[pix]++;
+      }
 }
 
 /* ======================================================================

@@ -91,6 +91,10 @@ void ora_camera_frame(const double eye[3], const double lookat[3], const double 
                       double du[3], double dv[3]);
 void ora_generate_ray(const double origin[3], const double corner[3], const double du[3], const double dv[3],
                       double u, double v, double ray6[6]);
+/* Camera::GenerateEnvRay (camera.cc:242-257) / GenerateStereoEnvRay (camera.cc:259-329): equirectangular
+ * panorama rays from pixel coordinates (u, v) of a width x height image; stereo != 0 = top/bottom stereo pair. */
+void ora_generate_env_ray(const double origin[3], int width, int height, double u, double v, int stereo,
+                          double ray6[6]);
 void ora_generate_grid(const double origin[3], const double corner[3], const double du[3], const double dv[3],
                        int width, int height, double *rays);
 
@@ -116,8 +120,10 @@ typedef struct {
                           1 = per-pixel counter seeding ora_rng_seed_pixel(pixel, pass) */
   uint32_t pass;
   int skip_zombies;    /* 1 = do not trace post-escape segments (closed form); same image */
-  int shader;          /* 0 = PathTrace (render.cc:381), 1 = primary + shadow (direct light) */
+  int shader;          /* 0 = PathTrace (render.cc:381), 1 = primary + shadow (direct light),
+                          2 = PathTraceEnv (render.cc:518-590): no plane, no material attenuation */
   double light[3];     /* shader 1 */
+  int camera_mode;     /* 0 = Camera::GenerateRay, 1 = GenerateEnvRay, 2 = GenerateStereoEnvRay */
 } ora_render_params;
 /* image: float[3*W*H] overwritten; count[W*H] incremented; x0..x1,y0..y1 tile (whole image: 0,0,W,H).
  * ray_counts (nullable, accumulated): [0] Trace calls for camera/bounce rays, [1] zombie segments,
@@ -131,6 +137,13 @@ void ora_render_pass(const ora_bvh *b, const ora_mesh *mesh, const ora_render_pa
 void ora_render_pass_ex(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, int x0, int y0, int x1,
                         int y1, float *image, int *count, uint64_t ray_counts[7], int nthreads,
                         double *primary_rays_out, double *shadow_rays_out);
+
+/* RenderPanoramic, render.cc:710-763: image zeroed, then per pixel TEN samples of PathTraceEnv added
+ * (float += double), count += 10.  p->camera_mode selects env (1) / stereo (2); p->shader is taken as 2.
+ * rng_mode 0 = the reference's sequential stream (OMP_NUM_THREADS=1); rng_mode 1 = per-pixel seeding with
+ * pass index p->pass + sample. */
+void ora_render_panoramic(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, float *image,
+                          int *count, int nthreads);
 
 /* --- misc ---------------------------------------------------------------- */
 uint64_t ora_fnv1a64(const void *data, size_t nbytes, uint64_t seed /* 0 = standard offset basis */);

@@ -38,7 +38,7 @@ class _RenderParams(C.Structure):
                 ("du", C.c_double * 3), ("dv", C.c_double * 3),
                 ("use_plane", C.c_int), ("plane", C.c_float * 4),
                 ("max_path_length", C.c_int), ("rng_mode", C.c_int), ("pass_", C.c_uint32),
-                ("skip_zombies", C.c_int), ("shader", C.c_int), ("light", C.c_double * 3)]
+                ("skip_zombies", C.c_int), ("shader", C.c_int), ("light", C.c_double * 3), ("camera_mode", C.c_int)]
 
 
 _lib = None
@@ -79,6 +79,7 @@ def lib():
         L.ora_camera_frame.argtypes = [vp, vp, vp, dbl, vp, i32, i32, vp, vp, vp, vp]
         L.ora_generate_grid.argtypes = [vp, vp, vp, vp, i32, i32, vp]
         L.ora_generate_ray.argtypes = [vp, vp, vp, vp, dbl, dbl, vp]
+        L.ora_generate_env_ray.argtypes = [vp, i32, i32, dbl, dbl, i32, vp]
         L.ora_plane_intersect.restype = i32
         L.ora_plane_intersect.argtypes = [vp, vp, vp, vp]
         L.ora_plane_from_bbox.argtypes = [vp, vp, vp]
@@ -86,6 +87,7 @@ def lib():
                                       vp, vp, vp, i32]
         L.ora_render_pass_ex.argtypes = [vp, C.POINTER(_Mesh), C.POINTER(_RenderParams), i32, i32, i32, i32,
                                          vp, vp, vp, i32, vp, vp]
+        L.ora_render_panoramic.argtypes = [vp, C.POINTER(_Mesh), C.POINTER(_RenderParams), vp, vp, i32]
         L.ora_fnv1a64.restype = C.c_uint64
         L.ora_fnv1a64.argtypes = [vp, sz, C.c_uint64]
         L.ora_rng_seed_pixel.argtypes = [vp, C.c_uint32, C.c_uint32]
@@ -188,7 +190,7 @@ class BVH:
 
     def render_pass(self, frame, width, height, plane=None, max_path_length=16, rng_mode=1, pass_index=0,
                     skip_zombies=1, shader=0, light=(0.0, 0.0, 0.0), tile=None, image=None, count=None,
-                    nthreads=0, emit_rays=False):
+                    nthreads=0, emit_rays=False, camera_mode=0):
         p = _RenderParams()
         p.width, p.height = width, height
         o, c, du, dv = frame
@@ -200,7 +202,7 @@ class BVH:
             for k in range(4):
                 p.plane[k] = plane[k]
         p.max_path_length, p.rng_mode, p.pass_ = max_path_length, rng_mode, pass_index
-        p.skip_zombies, p.shader = skip_zombies, shader
+        p.skip_zombies, p.shader, p.camera_mode = skip_zombies, shader, camera_mode
         if image is None:
             image = np.zeros((height, width, 3), np.float32)
         if count is None:
@@ -221,12 +223,39 @@ class BVH:
         return image, count, info
 
 
+def render_panoramic(bvh, origin, width, height, stereo=False, max_path_length=16, rng_mode=1, pass_index=0,
+                     nthreads=0):
+    """RenderPanoramic (render.cc:710-763): 10 samples of PathTraceEnv per pixel, count += 10."""
+    p = _RenderParams()
+    p.width, p.height = width, height
+    for k in range(3):
+        p.origin[k] = origin[k]
+    p.max_path_length, p.rng_mode, p.pass_, p.skip_zombies = max_path_length, rng_mode, pass_index, 1
+    p.shader, p.camera_mode = 2, (2 if stereo else 1)
+    image = np.zeros((height, width, 3), np.float32)
+    count = np.zeros((height, width), np.int32)
+    lib().ora_render_panoramic(bvh.h, C.byref(bvh.mesh.c), C.byref(p), _p(image), _p(count), nthreads)
+    return image, count
+
+
 def camera_frame(eye, lookat, up=(0, 1, 0), fov=45.0, quat=(0, 0, 0, 0), width=512, height=512):
     e, l, u = (np.ascontiguousarray(x, np.float64) for x in (eye, lookat, up))
     q = np.ascontiguousarray(quat, np.float64)
     o, c, du, dv = (np.zeros(3) for _ in range(4))
     lib().ora_camera_frame(_p(e), _p(l), _p(u), float(fov), _p(q), width, height, _p(o), _p(c), _p(du), _p(dv))
     return o, c, du, dv
+
+
+def generate_env(origin, width, height, px, py, stereo=False):
+    """Camera::GenerateEnvRay / GenerateStereoEnvRay for arrays of pixel coordinates."""
+    o = np.ascontiguousarray(origin, np.float64)
+    px, py = np.asarray(px, np.float64).reshape(-1), np.asarray(py, np.float64).reshape(-1)
+    rays = np.zeros((px.size, 6))
+    tmp = np.zeros(6)
+    for i in range(px.size):
+        lib().ora_generate_env_ray(_p(o), width, height, float(px[i]), float(py[i]), int(stereo), _p(tmp))
+        rays[i] = tmp
+    return rays
 
 
 def generate_grid(frame, width, height):

@@ -284,6 +284,19 @@ void ref_camera_generate(const double eye[3], const double lookat[3],
   }
 }
 
+// rays[i] = GenerateEnvRay / GenerateStereoEnvRay (px[i], py[i]) (camera.cc:242-329).
+void ref_camera_generate_env(const double eye[3], const double lookat[3], const double up[3], double fov,
+                             const double quat[4], int width, int height, const double *px, const double *py,
+                             size_t n, int stereo, double *rays) {
+  mallie::Camera cam(eye, lookat, up);
+  double origin[3], corner[3], du[3], dv[3];
+  cam.BuildCameraFrame(origin, corner, du, dv, fov, quat, width, height);
+  for (size_t i = 0; i < n; i++) {
+    Ray r = stereo ? cam.GenerateStereoEnvRay(px[i], py[i]) : cam.GenerateEnvRay(px[i], py[i]);
+    for (int k = 0; k < 3; k++) rays[6 * i + k] = r.org[k], rays[6 * i + 3 + k] = r.dir[k];
+  }
+}
+
 // Un-jittered primary rays for every integer pixel, row-major.
 void ref_camera_generate_grid(const double eye[3], const double lookat[3],
                               const double up[3], double fov,
@@ -362,6 +375,33 @@ double ref_scene_render(void *h, int width, int height, double fov,
   memcpy(&cnt[0], count, sizeof(int) * cnt.size());
   double t0 = now_sec();
   mallie::Render(*s->scene, cfg, img, cnt, eye, lookat, up, quat, step);
+  double t1 = now_sec();
+  printf("\n");
+  memcpy(image, &img[0], sizeof(float) * img.size());
+  memcpy(count, &cnt[0], sizeof(int) * cnt.size());
+  return t1 - t0;
+}
+
+// One call of mallie::RenderPanoramic (render.cc:710-763): 10 samples per pixel accumulated into image,
+// count += 10.  Same static-state caveats as ref_scene_render.
+double ref_scene_render_panoramic(void *h, int width, int height, double fov, const double eye[3],
+                                  const double lookat[3], const double up[3], const double quat[4], int stereo,
+                                  int nthreads, float *image, int *count) {
+  RefScene *s = (RefScene *)h;
+  mallie::RenderConfig cfg;
+  cfg.width = width;
+  cfg.height = height;
+  cfg.fov = fov;
+  for (int k = 0; k < 3; k++) cfg.eye[k] = eye[k], cfg.lookat[k] = lookat[k], cfg.up[k] = up[k];
+  for (int k = 0; k < 4; k++) cfg.quat[k] = quat[k];
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+  std::vector<float> img((size_t)3 * width * height);
+  std::vector<int> cnt((size_t)width * height);
+  memcpy(&cnt[0], count, sizeof(int) * cnt.size());
+  double t0 = now_sec();
+  mallie::RenderPanoramic(*s->scene, cfg, img, cnt, eye, lookat, up, quat, stereo != 0);
   double t1 = now_sec();
   printf("\n");
   memcpy(image, &img[0], sizeof(float) * img.size());

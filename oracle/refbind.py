@@ -67,6 +67,9 @@ def lib():
         L.ref_camera_frame.argtypes = [vp, vp, vp, dbl, vp, i32, i32, vp, vp, vp, vp]
         L.ref_camera_generate.argtypes = [vp, vp, vp, dbl, vp, i32, i32, vp, vp, sz, vp]
         L.ref_camera_generate_grid.argtypes = [vp, vp, vp, dbl, vp, i32, i32, vp]
+        L.ref_camera_generate_env.argtypes = [vp, vp, vp, dbl, vp, i32, i32, vp, vp, sz, i32, vp]
+        L.ref_scene_render_panoramic.restype = dbl
+        L.ref_scene_render_panoramic.argtypes = [vp, i32, i32, dbl, vp, vp, vp, vp, i32, i32, vp, vp]
         L.ref_plane_intersect.argtypes = [C.c_float] * 4 + [vp, vp, sz, vp, vp, vp, vp]
         L.ref_scene_render.restype = dbl
         L.ref_scene_render.argtypes = [vp, i32, i32, dbl, vp, vp, vp, vp, i32, i32, i32, vp, vp]
@@ -169,6 +172,23 @@ class RefScene:
                                      _p(_d3(up)), _p(_d3(quat, 4)), int(plane), step, nthreads,
                                      _p(img), _p(cnt))
         return img, cnt, sec
+
+    def render_panoramic(self, width, height, eye, lookat, up=(0, 1, 0), quat=(0, 0, 0, 0), fov=45.0, stereo=False,
+                         nthreads=0, count=None):
+        img = np.zeros((height, width, 3), np.float32)
+        cnt = np.zeros((height, width), np.int32) if count is None else np.ascontiguousarray(count, np.int32)
+        sec = lib().ref_scene_render_panoramic(self.h, width, height, float(fov), _p(_d3(eye)), _p(_d3(lookat)),
+                                               _p(_d3(up)), _p(_d3(quat, 4)), int(stereo), nthreads, _p(img), _p(cnt))
+        return img, cnt, sec
+
+
+def camera_generate_env(eye, lookat, up, fov, quat, width, height, px, py, stereo=False):
+    px = np.ascontiguousarray(px, np.float64)
+    py = np.ascontiguousarray(py, np.float64)
+    rays = np.zeros((px.size, 6))
+    lib().ref_camera_generate_env(_p(_d3(eye)), _p(_d3(lookat)), _p(_d3(up)), float(fov), _p(_d3(quat, 4)),
+                                  width, height, _p(px), _p(py), px.size, int(stereo), _p(rays))
+    return rays
 
 
 def camera_frame(eye, lookat, up, fov, quat, width, height):

@@ -1,10 +1,11 @@
 // host_api_check.cc -- exercises the host C++ mirror of the Mallie API (mallie_api.h) the way a
 // Mallie program would, and dumps what it got so tests/test_gpu_host_api.py can compare it with the
-// oracle:   host_api_check <obj> <out.bin> <width> <height> [plane] [gpus]
+// oracle:   host_api_check <obj> <out.bin> <width> <height> [plane] [gpus] [panoramic]
 //   1. Scene::Init(obj) (loader + host BVH build), Scene::BoundingBox
 //   2. Camera::BuildCameraFrame + Camera::GenerateRay for every pixel, Scene::TraceBatch
 //   3. Scene::Trace for a handful of single rays (must equal the batch entries)
 //   4. mallie::Render (one pass, step 1), then Render with step 4 (coarse preview)
+//   5. (panoramic != 0) Camera::GenerateEnvRay / GenerateStereoEnvRay on a few pixels, RenderPanoramic mono + stereo
 // Written against the reference-style headers through the forwarding includes.
 #include <string>
 
@@ -73,6 +74,21 @@ int main(int argc, char **argv) {
   put(fp, count.data(), count.size() * sizeof(int));
   put(fp, coarse.data(), coarse.size() * sizeof(float));
   put(fp, coarse_count.data(), coarse_count.size() * sizeof(int));
+  if (argc > 7 && atoi(argv[7]) != 0) {
+    for (int k = 0; k < 5; k++) { // single host rays through the panorama cameras
+      const Ray a = camera.GenerateEnvRay(0.37 * W * k / 4.0, 0.61 * H * k / 4.0);
+      const Ray b = camera.GenerateStereoEnvRay(0.93 * W * k / 4.0, 0.99 * H * k / 4.0);
+      put(fp, &a.org, 48), put(fp, &b.org, 48);
+    }
+    for (int stereo = 0; stereo < 2; stereo++) {
+      std::vector<float> pano((size_t)W * H * 3, -1.f);
+      std::vector<int> pcount((size_t)W * H, 0);
+      mallie::RenderPanoramic(scene, config, pano, pcount, config.eye, config.lookat, config.up, config.quat, stereo != 0);
+      put(fp, pano.data(), pano.size() * sizeof(float));
+      put(fp, pcount.data(), pcount.size() * sizeof(int));
+    }
+    printf("\n");
+  }
   fclose(fp);
   printf("host_api_check: %ld hits of %zu rays, %d single-ray mismatches\n", nhit, rays.size(), single_bad);
   return single_bad ? 4 : 0;

@@ -213,3 +213,40 @@ def test_kernel_timing_hooks():
     sc.render_pass(p)
     assert all(v == 0 for v in sc.kernel_times().values())
     sc.close()
+
+
+@pytest.mark.parametrize("stereo", [False, True])
+def test_panorama_cameras_and_env_shader(stereo):
+    """K1 for Camera::GenerateEnvRay / GenerateStereoEnvRay (camera.cc:242-329) and the PathTraceEnv shader
+    (render.cc:518-590).  CUDA's sin / cos / fmod / atan2 are not glibc's: rays agree to a few ulp (the contract's
+    1e-5 relative leaves nine orders of magnitude), hit records on identical rays are bit-exact as everywhere."""
+    W, H = 192, 96
+    m = T.load_mesh("cornellbox")
+    sc = M.Scene(m["vertices"], m["faces"], m["material_ids"], m["normals"], m["uvs"])
+    om, ob = T.oracle_scene("cornellbox")
+    origin = (0.5, 1.0, 2.0)                     # inside the box
+    rng = np.random.default_rng(9)
+    px, py = rng.uniform(-0.5, W - 0.5, 4000), rng.uniform(-0.5, H - 0.5, 4000)
+    got = sc.generate_rays_env(origin, W, H, px, py, stereo=stereo)
+    want = O.generate_env(origin, W, H, px, py, stereo=stereo)
+    assert np.abs(got - want).max() < 1e-13
+    T.assert_hits_equal(sc.trace_closest(want), ob.trace(want)["hits"], "env rays")
+    # one pass of the env shader through the frame pipeline vs the oracle
+    fg = M.camera_frame(origin, (0, 1, 0), width=W, height=H)
+    fo = O.camera_frame(origin, (0, 1, 0), width=W, height=H)
+    mode = M.CAMERA_ENV_STEREO if stereo else M.CAMERA_ENV
+    p = sc.render_params(fg, W, H, shader=M.SHADER_PATHTRACE_ENV, camera_mode=mode, pass_index=4)
+    img, cnt, st = sc.render_pass(p)
+    oimg, _, oc = ob.render_pass(fo, W, H, rng_mode=1, pass_index=4, shader=2, camera_mode=int(mode))
+    same = (img.view(np.uint32) == oimg.view(np.uint32)).all(axis=2)
+    assert same.mean() >= 0.99, same.mean()
+    assert abs(float(img.sum(dtype=np.float64)) - float(oimg.sum(dtype=np.float64))) <= 2e-3 * float(oimg.sum(dtype=np.float64))
+    assert st["primary_rays"] == W * H and (cnt == 1).all() and img.max() > 0
+    # the plane and the materials are ignored by PathTraceEnv
+    pl = M.plane_from_bounds(*sc.bounds())
+    p2 = sc.render_params(fg, W, H, plane=pl, shader=M.SHADER_PATHTRACE_ENV, camera_mode=mode, pass_index=4)
+    assert sc.render_pass(p2)[0].tobytes() == img.tobytes()
+    bad = sc.render_params(fg, W, H, camera_mode=7)
+    with pytest.raises(M.MallieB200Error):
+        sc.render_pass(bad)
+    sc.close()

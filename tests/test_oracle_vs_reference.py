@@ -159,3 +159,40 @@ print("RESULT %016x %d" % (O.fnv1a64(img), int(cnt.sum())))
     fr = O.camera_frame((0.3, 0.2, 3), (0, 0, 0), width=160, height=120)
     img, cnt, _ = ob.render_pass(fr, 160, 120, plane=pl, rng_mode=0, skip_zombies=1, shader=0, nthreads=1)
     assert T.fnv(img) == line[1] and int(cnt.sum()) == int(line[2]) == 160 * 120
+
+
+def test_env_camera_rays_bit_identical():
+    """Camera::GenerateEnvRay / GenerateStereoEnvRay (camera.cc:242-329): same libm, same bits."""
+    rng = np.random.default_rng(3)
+    W, H = 200, 100
+    px = np.concatenate([rng.uniform(-0.5, W, 500), [0.0, W - 1.0, 17.0]])
+    py = np.concatenate([rng.uniform(-0.5, H, 500), [0.0, H - 1.0, H / 2.0]])
+    eye = (0.3, -0.2, 2.5)
+    fr = O.camera_frame(eye, (0, 0, 0), width=W, height=H)
+    for stereo in (False, True):
+        want = R.camera_generate_env(eye, (0, 0, 0), (0, 1, 0), 45.0, (0, 0, 0, 0), W, H, px, py, stereo=stereo)
+        got = O.generate_env(fr[0], W, H, px, py, stereo=stereo)
+        assert got.tobytes() == want.tobytes(), stereo
+
+
+@pytest.mark.parametrize("stereo", [False, True])
+def test_render_panoramic_one_thread_bit_identical(stereo):
+    """RenderPanoramic (render.cc:710-763) in a fresh process (function-static RNG initialisation)."""
+    code = f"""
+import sys; sys.path.insert(0, {ROOT!r})
+import numpy as np
+from oracle import refbind as R, orabind as O
+from tests import common as T
+m = T.load_mesh("sphere40")
+rs = R.RefScene.from_arrays(m["vertices"], m["faces"]); rs.build()
+img, cnt, sec = rs.render_panoramic(96, 48, (0.1, 0.2, 0.3), (0, 0, 1), stereo={stereo}, nthreads=1)
+print("RESULT %016x %d %r" % (O.fnv1a64(img), int(cnt.sum()), float(img.sum(dtype=np.float64))))
+"""
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True).stdout
+    line = [l for l in out.splitlines() if l.startswith("RESULT")][0].split()
+    om, ob = T.oracle_scene("sphere40")
+    fr = O.camera_frame((0.1, 0.2, 0.3), (0, 0, 1), width=96, height=48)
+    img, cnt = O.render_panoramic(ob, fr[0], 96, 48, stereo=stereo, rng_mode=0, nthreads=1)
+    assert int(cnt.sum()) == int(line[2]) == 96 * 48 * 10
+    assert T.fnv(img) == line[1], (float(img.sum(dtype=np.float64)), line[3])
+    assert img.max() > 0
