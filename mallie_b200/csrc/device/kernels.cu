@@ -510,9 +510,10 @@ cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const
 #undef MB200_MR
   }
   if (!COUNT && CAP <= 64) {
-    static const int policy = env_int("MB200_TRACE_POLICY", kPolicy), occ = env_int("MB200_TRACE_OCC", kMinBlocks),
-                     chunk = env_int("MB200_TRACE_CHUNK", (int)kChunk), refill = env_int("MB200_TRACE_REFILL", kRefillMin),
-                     var = env_int("MB200_TRACE_VAR", kVar);
+    // -1 = not set: only an explicitly requested variant replaces the production instantiation
+    static const int policy = env_int("MB200_TRACE_POLICY", -1), occ = env_int("MB200_TRACE_OCC", -1),
+                     chunk = env_int("MB200_TRACE_CHUNK", -1), refill = env_int("MB200_TRACE_REFILL", -1),
+                     var = env_int("MB200_TRACE_VAR", -1);
     if (policy == 0) return MB200_SM(8, 0, 12, 8, 32, 11);
     if (policy == 3) return MB200_SM(8, 3, 12, 8, 32, 11);
     if (policy == 4) return MB200_SM(8, 4, 12, 8, 32, 11);
@@ -540,6 +541,9 @@ cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const
     if (var == 119) return MB200_SM(8, 2, 12, 8, 32, 3 + 4 + 16 + 32 + 64);
     if (var == 123) return MB200_SM(8, 2, 12, 8, 32, 3 + 8 + 16 + 32 + 64);
     // stack split between shared memory and (L1-cached) local memory, no prefetch
+    if (var == 2009) return MB200_SM(8, 2, 0, 9, 32, 11);
+    if (var == 2129) return MB200_SM(8, 2, 12, 9, 32, 11);
+    if (var == 2010) return MB200_SM(8, 2, 0, 10, 32, 11);
     if (var == 1100) return MB200_SM(8, 2, 0, 8, 32, 11);
     if (var == 1104) return MB200_SM(8, 2, 4, 8, 32, 11);
     if (var == 1108) return MB200_SM(8, 2, 8, 8, 32, 11);
