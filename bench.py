@@ -308,11 +308,13 @@ def main():
     step_ms = [a.elapsed_time(c) for a, _, c in evs]
     kern_ms = [a.elapsed_time(b) for a, b, _ in evs]
     total_ms = torch.tensor([sum(step_ms), float(np.mean(kern_ms)), kt["camera_trace_ms"], kt["shadow_trace_ms"],
-                             kt["shade_ms"], kt["resolve_ms"]], dtype=torch.float64, device="cuda")
+                             kt["shade_ms"], kt["resolve_ms"], kt["trace_union_ms"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms_max, kern_ms_max = float(total_ms[0]), float(total_ms[1])
-    cam_ms, shd_ms, shade_ms, resolve_ms = (float(x) for x in total_ms[2:6])       # totals over the timed steps
+    # totals over the timed steps; per class the UNION of the launches' spans (a frame's batches alternate between
+    # two streams so that one launch's drain phase overlaps the next launch), trace_all = union over both classes
+    cam_ms, shd_ms, shade_ms, resolve_ms, trace_all_ms = (float(x) for x in total_ms[2:7])
     cam_n, shd_n = int(kt["camera_trace_launches"]), int(kt["shadow_trace_launches"])
     value = rays_frame * args.steps / (total_ms_max * 1e-3) / 1e6
 
@@ -376,7 +378,7 @@ def main():
             kernels.append({"kernel": inst, "launches_per_step": n / args.steps, "ms_per_launch": ms / n,
                             "algorithmic_bytes_per_launch": b, "achieved": a, "frac": a / peak,
                             "traffic": traffic.get(name + "_trace_dram_bytes_per_launch")})
-        trace_ms, trace_n = cam_ms + shd_ms, cam_n + shd_n
+        trace_ms, trace_n = trace_all_ms, cam_n + shd_n
         bytes_launch = (per_frame["camera"] + per_frame["shadow"]) * args.steps / trace_n
         achieved = bytes_launch / (trace_ms / trace_n * 1e-3) / 1e9
         tr = [k["traffic"] for k in kernels]
@@ -384,12 +386,16 @@ def main():
                     "traffic": (sum(t * k["launches_per_step"] for t, k in zip(tr, kernels)) /
                                 sum(k["launches_per_step"] for k in kernels)) if all(tr) and tr else None,
                     "peak_source": peak_src,
-                    "kernel": "k_trace_sm (persistent-warp BVH traversal state machine): all launches of a step",
+                    "kernel": "k_trace_sm (persistent-warp BVH traversal state machine): all launches of a step; "
+                              "duration = time with at least one of them in flight / launches (launches of consecutive "
+                              "batches overlap on two streams)",
                     "launches_per_step": trace_n / args.steps, "ms_per_launch": trace_ms / trace_n,
                     "algorithmic_bytes_per_launch": bytes_launch, "kernels": kernels,
-                    "step_share": {"trace": trace_ms / args.steps / (total_ms_max / args.steps),
-                                   "shade": shade_ms / args.steps / (total_ms_max / args.steps),
-                                   "resolve": resolve_ms / args.steps / (total_ms_max / args.steps)},
+                    # share of the step with a traversal launch in flight; the shade / resolve launches run inside the
+                    # drain phases of the other stream's traversal launch (their event spans include that wait:
+                    # ncu's serialised launch list, profiles/r1_launches_sm.csv, has trace 92 %, shade 7.5 %)
+                    "step_share": {"trace": trace_ms / args.steps / (total_ms_max / args.steps)},
+                    "span_ms_per_step_incl_queueing": {"shade": shade_ms / args.steps, "resolve": resolve_ms / args.steps},
                     "bytes_per_ray": alg["bytes"] / alg["rays"],
                     "nodes_per_ray": alg["n_node"] / alg["rays"], "tris_per_ray": alg["n_tri"] / alg["rays"],
                     "camera_nodes_per_ray": (alg["n_node"] - alg["shadow_n_node"]) / (alg["rays"] - alg["shadow"]),

@@ -201,9 +201,12 @@ int mb200_scene_uses_f32_vertices(const mb200_scene *scene);
  * CUDA events on the scene's stream.  mb200_scene_kernel_times synchronises the stream, returns the
  * milliseconds and launch counts accumulated since the last call (per kernel class) and resets them. */
 typedef struct {
+  /* per class: length of the union of the launches' time spans (consecutive batches of a frame run on two
+   * streams, so launches of a class can overlap each other and launches of other classes) */
   double camera_trace_ms, shadow_trace_ms, bounce_trace_ms, shade_ms, resolve_ms, query_trace_ms;
   uint64_t camera_trace_launches, shadow_trace_launches, bounce_trace_launches, shade_launches, resolve_launches,
       query_trace_launches;
+  double trace_union_ms; /* time during which at least one camera / shadow / bounce traversal launch was in flight */
 } mb200_kernel_times;
 int mb200_scene_timing(mb200_scene *scene, int enable);
 int mb200_scene_kernel_times(mb200_scene *scene, mb200_kernel_times *out);

@@ -100,7 +100,7 @@ class KernelTimes(C.Structure):
     _fields_ = [(k + "_ms", C.c_double) for k in ("camera_trace", "shadow_trace", "bounce_trace", "shade", "resolve",
                                                   "query_trace")] + \
                [(k + "_launches", C.c_uint64) for k in ("camera_trace", "shadow_trace", "bounce_trace", "shade",
-                                                        "resolve", "query_trace")]
+                                                        "resolve", "query_trace")] + [("trace_union_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

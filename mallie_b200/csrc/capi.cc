@@ -305,7 +305,8 @@ int mb200_scene_kernel_times(mb200_scene *scene, mb200_kernel_times *out) {
   CU(cudaStreamSynchronize(scene->stream));
   double ms[mb200::kKClasses] = {0};
   unsigned long long n[mb200::kKClasses] = {0};
-  scene->timer.collect(ms, n);
+  if (scene->pipe.aux) CU(cudaStreamSynchronize(scene->pipe.aux));
+  scene->timer.collect(ms, n, &out->trace_union_ms);
   out->camera_trace_ms = ms[mb200::kKCameraTrace], out->camera_trace_launches = n[mb200::kKCameraTrace];
   out->shadow_trace_ms = ms[mb200::kKShadowTrace], out->shadow_trace_launches = n[mb200::kKShadowTrace];
   out->bounce_trace_ms = ms[mb200::kKBounceTrace], out->bounce_trace_launches = n[mb200::kKBounceTrace];
@@ -542,7 +543,7 @@ static int render_common(mb200_scene *s, const mb200_render_params *p, int num_p
   }
   if (stats) CU(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream));
   CU(mb200::launch_frame(s->view, s->stack_cap, *p, num_passes, mode, d_img, d_cnt, s->frame_scratch,
-                         stats ? s->d_counters : nullptr, s->stream, &s->timer));
+                         stats ? s->d_counters : nullptr, s->stream, &s->timer, &s->pipe));
   if (img_kind != kDevice)
     CU(cudaMemcpyAsync(img_kind == kPinned ? (void *)image : s->out0.pinned, d_img, img_bytes, cudaMemcpyDeviceToHost,
                        s->stream));
@@ -643,7 +644,7 @@ int mb200_render_frame_multi(mb200_scene *const *scenes, int n, const mb200_rend
     if (e == cudaSuccess && stats) e = cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream);
     if (e == cudaSuccess)
       e = mb200::launch_frame(s->view, s->stack_cap, pg, num_passes, 2, t_img, t_cnt, s->frame_scratch,
-                              stats ? s->d_counters : nullptr, s->stream, &s->timer);
+                              stats ? s->d_counters : nullptr, s->stream, &s->timer, &s->pipe);
     if (e == cudaSuccess && !direct) {
       size_t local = 0;
       const size_t nbands = (H + band_rows - 1) / band_rows;

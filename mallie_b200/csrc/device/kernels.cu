@@ -11,6 +11,7 @@
 // (no FMA contraction: see traverse.cuh).
 #include "kernels.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -407,8 +408,9 @@ __global__ void __launch_bounds__(256)
 // stats of a batch -> the caller's accumulated stats (shadow rays traced = fill of the shadow queue)
 __global__ void k_add_stats(const unsigned long long *__restrict__ batch, const unsigned int *__restrict__ shadow_count,
                             unsigned long long *__restrict__ total) {
-  if (threadIdx.x < 4) total[threadIdx.x] += batch[threadIdx.x];
-  if (threadIdx.x == 2 && shadow_count) total[2] += *shadow_count;
+  // batches of a frame run on two streams: accumulate atomically
+  if (threadIdx.x < 4 && batch[threadIdx.x]) atomicAdd(&total[threadIdx.x], batch[threadIdx.x]);
+  if (threadIdx.x == 2 && shadow_count && *shadow_count) atomicAdd(&total[2], (unsigned long long)*shadow_count);
 }
 
 // ---------------------------------------------------------------------------
@@ -625,17 +627,72 @@ void KernelTimer::end(cudaStream_t s) {
   cudaEventRecord(spans.back().b, s);
 }
 
-void KernelTimer::collect(double ms[kKClasses], unsigned long long launches[kKClasses]) {
-  for (const Span &sp : spans) {
-    float t = 0.f;
-    if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess && sp.cls >= 0 && sp.cls < kKClasses) {
-      ms[sp.cls] += (double)t;
+void KernelTimer::collect(double ms[kKClasses], unsigned long long launches[kKClasses], double *trace_union_ms) {
+  if (trace_union_ms) *trace_union_ms = 0.0;
+  if (!spans.empty()) {
+    // absolute intervals relative to the first recorded event, then the union length per class
+    struct Iv {
+      float a, b;
+      int cls;
+    };
+    std::vector<Iv> iv;
+    const cudaEvent_t ref = spans[0].a;
+    for (const Span &sp : spans) {
+      Iv v;
+      v.cls = sp.cls;
+      if (cudaEventElapsedTime(&v.a, ref, sp.a) != cudaSuccess || cudaEventElapsedTime(&v.b, ref, sp.b) != cudaSuccess ||
+          sp.cls < 0 || sp.cls >= kKClasses) {
+        cudaGetLastError();
+        continue;
+      }
+      iv.push_back(v);
       launches[sp.cls]++;
     }
+    std::sort(iv.begin(), iv.end(), [](const Iv &x, const Iv &y) { return x.a < y.a; });
+    auto union_len = [&](auto pred) {
+      double total = 0.0;
+      float lo = 0.f, hi = -1.f;
+      bool open = false;
+      for (const Iv &v : iv) {
+        if (!pred(v.cls)) continue;
+        if (!open || v.a > hi) {
+          if (open) total += (double)(hi - lo);
+          lo = v.a, hi = v.b, open = true;
+        } else if (v.b > hi) {
+          hi = v.b;
+        }
+      }
+      if (open) total += (double)(hi - lo);
+      return total;
+    };
+    for (int c = 0; c < kKClasses; c++) ms[c] += union_len([c](int k) { return k == c; });
+    if (trace_union_ms)
+      *trace_union_ms = union_len([](int k) { return k == kKCameraTrace || k == kKShadowTrace || k == kKBounceTrace; });
+  }
+  for (const Span &sp : spans) {
     pool.push_back(sp.a);
     pool.push_back(sp.b);
   }
   spans.clear();
+}
+
+cudaError_t FramePipe::init() {
+  if (aux) return cudaSuccess;
+  cudaError_t e = cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking);
+  if (e != cudaSuccess) return e;
+  for (cudaEvent_t *ev : {&fork, &join, &resolved[0], &resolved[1]}) {
+    e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+void FramePipe::release() {
+  for (cudaEvent_t ev : {fork, join, resolved[0], resolved[1]})
+    if (ev) cudaEventDestroy(ev);
+  if (aux) cudaStreamDestroy(aux);
+  aux = nullptr;
+  fork = join = resolved[0] = resolved[1] = nullptr;
 }
 
 void KernelTimer::release() {
@@ -752,7 +809,7 @@ static size_t batch_item_budget() {
 
 cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_params &p, int num_passes, int mode,
                          float *image, int *count, FrameScratch &scratch, unsigned long long *stats, cudaStream_t s,
-                         KernelTimer *timer) {
+                         KernelTimer *timer, FramePipe *pipe) {
   const FrameMap m0 = make_frame_map(p, p.pass, 1);
   const size_t tiles = frame_map_tiles(m0);
   if (tiles == 0 || num_passes < 1) return cudaSuccess;
@@ -764,83 +821,109 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
   if (per_batch < 1) per_batch = 1;
   if (per_batch > (size_t)num_passes) per_batch = (size_t)num_passes;
   while (per_batch > 1 && tiles * 32 * per_batch > 0xFFFFFFE0ull) per_batch--;
+  // Two streams need at least two batches to overlap one batch's drain with the other's kernels.
+  static const bool pipeline_off = env_int("MB200_FRAME_PIPELINE", 1) == 0;
+  const bool piped = pipe && !pipeline_off && num_passes >= 2;
+  if (piped && per_batch > (size_t)(num_passes + 1) / 2) per_batch = (size_t)(num_passes + 1) / 2;
   const size_t max_items = tiles * 32 * per_batch;
 
-  // scratch carve-up
+  // scratch carve-up (one slot per stream)
   const size_t n_traces = path ? (size_t)p.max_path_length : 2;
   const size_t ctl_bytes = align_up(sizeof(unsigned long long) * (4 + n_traces) + sizeof(unsigned int) * (n_traces + 1), 256);
   const size_t hits_bytes = align_up(max_items * sizeof(mb200_hit), 256);
   const size_t contrib_bytes = align_up(max_items * sizeof(float), 256);
   const size_t queue_bytes = (path || shadow) ? align_up(max_items * sizeof(QRay), 256) : 0;
   const size_t state_bytes = path ? align_up(max_items * sizeof(PathState), 256) : 0;
-  const size_t total = ctl_bytes + hits_bytes + contrib_bytes + queue_bytes * (path ? 2 : 1) + state_bytes;
-  cudaError_t e = frame_scratch_reserve(scratch, total, s);
-  if (e != cudaSuccess) return e;
-  char *base = reinterpret_cast<char *>(scratch.base);
-  unsigned long long *bstats = reinterpret_cast<unsigned long long *>(base);           // [4]
-  unsigned long long *work = bstats + 4;                                               // [n_traces]
-  unsigned int *qcount = reinterpret_cast<unsigned int *>(work + n_traces);            // [n_traces + 1]
-  mb200_hit *hits = reinterpret_cast<mb200_hit *>(base + ctl_bytes);
-  float *contrib = reinterpret_cast<float *>(base + ctl_bytes + hits_bytes);
-  QRay *queue[2] = {reinterpret_cast<QRay *>(base + ctl_bytes + hits_bytes + contrib_bytes), nullptr};
-  queue[1] = path ? reinterpret_cast<QRay *>(reinterpret_cast<char *>(queue[0]) + queue_bytes) : queue[0];
-  PathState *states = path ? reinterpret_cast<PathState *>(reinterpret_cast<char *>(queue[0]) + 2 * queue_bytes) : nullptr;
+  const size_t slot_bytes = ctl_bytes + hits_bytes + contrib_bytes + queue_bytes * (path ? 2 : 1) + state_bytes;
+  cudaError_t e = cudaSuccess;
+  if (piped) {
+    if ((e = pipe->init()) != cudaSuccess) return e;
+    // the previous frame may still be running on aux when the block has to grow
+    if (scratch.bytes < slot_bytes * 2 && (e = cudaStreamSynchronize(pipe->aux)) != cudaSuccess) return e;
+  }
+  if ((e = frame_scratch_reserve(scratch, slot_bytes * (piped ? 2 : 1), s)) != cudaSuccess) return e;
+  if (piped) { // aux starts after whatever the caller queued on s (uploads, the previous frame)
+    if ((e = cudaEventRecord(pipe->fork, s)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(pipe->aux, pipe->fork, 0)) != cudaSuccess) return e;
+  }
 
-  int done = 0;
+  int done = 0, batch = 0;
+  bool aux_used = false;
   while (done < num_passes) {
     const int nb = (int)((size_t)(num_passes - done) < per_batch ? (size_t)(num_passes - done) : per_batch);
+    const int slot = piped ? (batch & 1) : 0;
+    const cudaStream_t st = slot ? pipe->aux : s;
+    aux_used |= slot != 0;
+    char *base = reinterpret_cast<char *>(scratch.base) + (size_t)slot * slot_bytes;
+    unsigned long long *bstats = reinterpret_cast<unsigned long long *>(base);           // [4]
+    unsigned long long *work = bstats + 4;                                               // [n_traces]
+    unsigned int *qcount = reinterpret_cast<unsigned int *>(work + n_traces);            // [n_traces + 1]
+    mb200_hit *hits = reinterpret_cast<mb200_hit *>(base + ctl_bytes);
+    float *contrib = reinterpret_cast<float *>(base + ctl_bytes + hits_bytes);
+    QRay *queue[2] = {reinterpret_cast<QRay *>(base + ctl_bytes + hits_bytes + contrib_bytes), nullptr};
+    queue[1] = path ? reinterpret_cast<QRay *>(reinterpret_cast<char *>(queue[0]) + queue_bytes) : queue[0];
+    PathState *states = path ? reinterpret_cast<PathState *>(reinterpret_cast<char *>(queue[0]) + 2 * queue_bytes) : nullptr;
+
     const FrameMap m = make_frame_map(p, p.pass + (uint32_t)done, (uint32_t)nb);
     const uint32_t items = (uint32_t)(tiles * 32 * (size_t)nb);
-    if ((e = cudaMemsetAsync(base, 0, ctl_bytes, s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(base, 0, ctl_bytes, st)) != cudaSuccess) return e;
 
     // camera rays: K1 fused into K2
     const IOCamera cam{p, m, hits};
     {
-      TimedScope ts(timer, kKCameraTrace, s);
-      e = launch_trace_nocount<IOCamera, false>(sc, stack_cap, cam, items, nullptr, work + 0, s);
+      TimedScope ts(timer, kKCameraTrace, st);
+      e = launch_trace_nocount<IOCamera, false>(sc, stack_cap, cam, items, nullptr, work + 0, st);
     }
     if (e != cudaSuccess) return e;
     {
-      TimedScope ts(timer, kKShade, s);
-      k_shade_primary<<<(items + 255) / 256, 256, 0, s>>>(sc, p, m, items, hits, contrib, queue[0], qcount + 0, states, bstats);
+      TimedScope ts(timer, kKShade, st);
+      k_shade_primary<<<(items + 255) / 256, 256, 0, st>>>(sc, p, m, items, hits, contrib, queue[0], qcount + 0, states, bstats);
     }
     g_launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
     if (shadow) {
       const IOQueueShadow io{queue[0], contrib};
-      TimedScope ts(timer, kKShadowTrace, s);
-      if ((e = launch_trace_nocount<IOQueueShadow, true>(sc, stack_cap, io, 0, qcount + 0, work + 1, s)) != cudaSuccess) return e;
+      TimedScope ts(timer, kKShadowTrace, st);
+      if ((e = launch_trace_nocount<IOQueueShadow, true>(sc, stack_cap, io, 0, qcount + 0, work + 1, st)) != cudaSuccess) return e;
     } else if (path) {
       for (int len = 2; len <= p.max_path_length; len++) {
         const int qi = len & 1; // segment `len` reads queue[qi], writes queue[qi ^ 1]
         const IOQueueClosest io{queue[qi], hits};
         {
-          TimedScope ts(timer, kKBounceTrace, s);
-          e = launch_trace_nocount<IOQueueClosest, false>(sc, stack_cap, io, 0, qcount + (len - 2), work + (len - 1), s);
+          TimedScope ts(timer, kKBounceTrace, st);
+          e = launch_trace_nocount<IOQueueClosest, false>(sc, stack_cap, io, 0, qcount + (len - 2), work + (len - 1), st);
         }
         if (e != cudaSuccess) return e;
-        TimedScope ts(timer, kKShade, s);
-        k_shade_bounce<<<num_sms() * 8, 256, 0, s>>>(sc, p, (unsigned int)len, queue[qi], qcount + (len - 2), hits, queue[qi ^ 1],
-                                                     qcount + (len - 1), states, contrib, bstats);
+        TimedScope ts(timer, kKShade, st);
+        k_shade_bounce<<<num_sms() * 8, 256, 0, st>>>(sc, p, (unsigned int)len, queue[qi], qcount + (len - 2), hits, queue[qi ^ 1],
+                                                      qcount + (len - 1), states, contrib, bstats);
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
       }
     }
 
+    // the image is accumulated in pass order (float += float): batch k resolves after batch k - 1
+    if (piped && batch > 0 && (e = cudaStreamWaitEvent(st, pipe->resolved[(batch - 1) & 1], 0)) != cudaSuccess) return e;
     int bmode = mode;
     if (mode == 2 && done > 0) bmode = 1;
     {
-      TimedScope ts(timer, kKResolve, s);
-      k_resolve<<<(unsigned)((tiles * 32 + 255) / 256), 256, 0, s>>>(m, (uint32_t)tiles, bmode, contrib, image, count);
+      TimedScope ts(timer, kKResolve, st);
+      k_resolve<<<(unsigned)((tiles * 32 + 255) / 256), 256, 0, st>>>(m, (uint32_t)tiles, bmode, contrib, image, count);
     }
     g_launches++;
+    if (piped && (e = cudaEventRecord(pipe->resolved[batch & 1], st)) != cudaSuccess) return e;
     if (stats) {
-      k_add_stats<<<1, 32, 0, s>>>(bstats, shadow ? qcount : nullptr, stats);
+      k_add_stats<<<1, 32, 0, st>>>(bstats, shadow ? qcount : nullptr, stats);
       g_launches++;
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     done += nb;
+    batch++;
+  }
+  if (piped && aux_used) { // everything the frame queued on aux is ordered before what follows on s
+    if ((e = cudaEventRecord(pipe->join, pipe->aux)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(s, pipe->join, 0)) != cudaSuccess) return e;
   }
   return cudaSuccess;
 }

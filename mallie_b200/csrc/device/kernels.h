@@ -25,8 +25,21 @@ struct KernelTimer {
   std::vector<cudaEvent_t> pool;  // recycled events
   void begin(int cls, cudaStream_t s);
   void end(cudaStream_t s);
-  // After the stream has been synchronised: adds every span's elapsed ms / launch to the arrays, recycles events.
-  void collect(double ms[kKClasses], unsigned long long launches[kKClasses]);
+  // After the streams have been synchronised: adds, per class, the length of the UNION of its spans (kernels of
+  // consecutive batches run on two streams and may overlap, see FramePipe) and the launch counts; *trace_union_ms
+  // (nullable) receives the union over the three traversal classes.  Recycles the events.
+  void collect(double ms[kKClasses], unsigned long long launches[kKClasses], double *trace_union_ms = nullptr);
+  void release();
+};
+
+// Second stream + events of the frame pipeline: consecutive batches of a frame alternate between the scene's
+// stream and `aux`, so that the drain phase of one persistent traversal kernel (the last, longest rays of a
+// launch run at single-warp latency while the rest of the GPU idles: ~0.35 ms per launch on the 1 M-triangle
+// scene) is filled by the next batch's kernel instead of being waited for.
+struct FramePipe {
+  cudaStream_t aux = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, resolved[2] = {nullptr, nullptr};
+  cudaError_t init();
   void release();
 };
 
@@ -65,7 +78,7 @@ void frame_scratch_release(FrameScratch &fs);
 // stats: device unsigned long long[4] primary, bounce, shadow, zombie (accumulated).
 cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_params &p, int num_passes, int mode,
                          float *image, int *count, FrameScratch &scratch, unsigned long long *stats, cudaStream_t s,
-                         KernelTimer *timer = nullptr);
+                         KernelTimer *timer = nullptr, FramePipe *pipe = nullptr);
 
 // Rows owned by one band index (see mb200_render_params::band_rows).
 int band_rows_owned(int rows, int band_rows, int count, int index);

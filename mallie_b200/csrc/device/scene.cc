@@ -264,6 +264,7 @@ void scene_destroy(mb200_scene *s) {
     if (st->dev) cudaFree(st->dev);
   }
   s->timer.release();
+  s->pipe.release();
   frame_scratch_release(s->frame_scratch);
   frame_scratch_release(s->hit_scratch);
   if (s->stream) cudaStreamDestroy(s->stream);

@@ -38,6 +38,8 @@ struct mb200_scene {
 
   // per-kernel timing (mb200_scene_timing / mb200_scene_kernel_times)
   mb200::KernelTimer timer;
+  // second stream of the frame pipeline (kernels.h)
+  mb200::FramePipe pipe;
 };
 
 namespace mb200 {

@@ -197,13 +197,15 @@ def test_kernel_timing_hooks():
     sc.render_pass(p)
     assert all(v == 0 for v in sc.kernel_times().values())          # disabled: nothing recorded
     sc.timing(True)
-    sc.render_frame(p, 3)
+    sc.render_frame(p, 3)                          # 3 passes = 2 batches (2 + 1) alternating between two streams
     rays = sc.generate_rays_grid(fg, 0, 0, W, H)
     sc.trace_closest(rays)
     kt = sc.kernel_times()
-    assert kt["camera_trace_launches"] == 1 and kt["shadow_trace_launches"] == 1 and kt["shade_launches"] == 1
-    assert kt["resolve_launches"] == 1 and kt["query_trace_launches"] == 1 and kt["bounce_trace_launches"] == 0
+    assert kt["camera_trace_launches"] == 2 and kt["shadow_trace_launches"] == 2 and kt["shade_launches"] == 2
+    assert kt["resolve_launches"] == 2 and kt["query_trace_launches"] == 1 and kt["bounce_trace_launches"] == 0
     assert 0 < kt["camera_trace_ms"] < 1000 and 0 < kt["shadow_trace_ms"] < 1000 and kt["query_trace_ms"] > 0
+    assert max(kt["camera_trace_ms"], kt["shadow_trace_ms"]) <= kt["trace_union_ms"] <= \
+        kt["camera_trace_ms"] + kt["shadow_trace_ms"] + 1e-6
     assert all(v == 0 for v in sc.kernel_times().values())          # reading resets
     pp = sc.render_params(fg, W, H, shader=M.SHADER_PATHTRACE, max_path_length=4)
     sc.render_pass(pp)
