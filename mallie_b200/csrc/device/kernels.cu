@@ -546,6 +546,12 @@ cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const
     if (var == 2009) return MB200_SM(8, 2, 0, 9, 32, 11);
     if (var == 2129) return MB200_SM(8, 2, 12, 9, 32, 11);
     if (var == 2010) return MB200_SM(8, 2, 0, 10, 32, 11);
+    if (var == 3016) return MB200_SM(8, 2, 12, 8, 16, 11);
+    if (var == 3008) return MB200_SM(8, 2, 12, 8, 8, 11);
+    if (var == 3116) return MB200_SM(16, 2, 12, 8, 16, 11);
+    if (var == 3404) return MB200_SM(4, 2, 12, 8, 4, 11);
+    if (var == 267) return MB200_SM(8, 2, 12, 8, 32, 11 + 256);
+    if (var == 523) return MB200_SM(8, 2, 12, 8, 32, 11 + 512);
     if (var == 1100) return MB200_SM(8, 2, 0, 8, 32, 11);
     if (var == 1104) return MB200_SM(8, 2, 4, 8, 32, 11);
     if (var == 1108) return MB200_SM(8, 2, 8, 8, 32, 11);

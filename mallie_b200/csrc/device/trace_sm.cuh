@@ -225,8 +225,9 @@ struct IOQueueShadow {
 //  16  branch-free triangle test (one predicate at the end instead of early returns)
 //  32  at most one stack pop per warp iteration (no inner pop loop)
 //  64  camera rays: the (tile, pass) decode of a 32-item chunk is done once per chunk, not per ray
+// 256 / 512  a LEAF step tests up to 2 / 4 triangles of the leaf (in order) instead of one
 constexpr int kVarWideNode = 1, kVarSignMask = 2, kVarLeafPrefetch1 = 4, kVarNoPrefetch = 8, kVarTriBranchFree = 16,
-              kVarSinglePop = 32, kVarChunkDecode = 64;
+              kVarSinglePop = 32, kVarChunkDecode = 64, kVarLeaf2 = 256, kVarLeaf4 = 512;
 
 template <bool F32, int VAR> __device__ __forceinline__ void prefetch_next(const SceneView &sc, uint32_t ref, uint32_t rc) {
   if (VAR & kVarNoPrefetch) return;
@@ -394,18 +395,22 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
       }
     } else if (run_leaf && at_leaf) {
       // ---- LEAF: one triangle of TestLeafNode (bvh_accel.cc:640-697), in indices_ order -----------------
-      const TriEdges tv = load_tri_edges<F32>(sc.tris, ref);
-      double u, v;
-      if (tri_test_edges<(VAR & kVarTriBranchFree) != 0>(hit_t, u, v, tv, r)) {
-        io.accept(item, hit_t, u, v, tv.face, tv.mat);
-        if (ANYHIT && hit_t < tmax_any) { // occluded: closest-hit Traverse would return t < tmax
-          io.finish(item, true);
-          rc = kIdle;
+      constexpr int kPerStep = (VAR & kVarLeaf4) ? 4 : ((VAR & kVarLeaf2) ? 2 : 1);
+#pragma unroll
+      for (int k = 0; k < kPerStep; k++) {
+        const TriEdges tv = load_tri_edges<F32>(sc.tris, ref);
+        double u, v;
+        if (tri_test_edges<(VAR & kVarTriBranchFree) != 0>(hit_t, u, v, tv, r)) {
+          io.accept(item, hit_t, u, v, tv.face, tv.mat);
+          if (ANYHIT && hit_t < tmax_any) { // occluded: closest-hit Traverse would return t < tmax
+            io.finish(item, true);
+            rc = kIdle;
+          }
         }
-      }
-      if (rc != kIdle) {
+        if (rc == kIdle) break;
         ref++;
         rc--;
+        if (rc == 0u) break;
       }
     }
 
