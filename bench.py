@@ -79,6 +79,11 @@ class ClockSampler:
                                        "-lms", "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+        # nvidia-smi needs a moment (longer when several ranks start at once) before its first line: wait for it,
+        # so that short timed regions are covered
+        t_end = time.time() + 5.0
+        while self.p is not None and time.time() < t_end and os.path.getsize(self.f.name) == 0:
+            time.sleep(0.02)
 
     def mark_start(self):
         self.t0 = time.time()
@@ -281,7 +286,7 @@ def main():
         torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ value: device-resident
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # rank 0 reports; one nvidia-smi per job
     for _ in range(args.warmup):
         step_device()
     barrier()
@@ -289,7 +294,8 @@ def main():
     launches0 = M.capi.launches_issued()
     evs = []
     barrier()
-    sampler.mark_start()
+    if sampler:
+        sampler.mark_start()
     for _ in range(args.steps):
         e0, em, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         with torch.cuda.stream(stream):
@@ -300,8 +306,10 @@ def main():
             e1.record(stream)
         evs.append((e0, em, e1))
     barrier()
-    sampler.mark_end()
-    clocks = sampler.stop()
+    clocks = None
+    if sampler:
+        sampler.mark_end()
+        clocks = sampler.stop()
     launches = M.capi.launches_issued() - launches0
     kt = sc.kernel_times()
     sc.timing(False)

@@ -550,6 +550,7 @@ cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const
     if (var == 3008) return MB200_SM(8, 2, 12, 8, 8, 11);
     if (var == 3116) return MB200_SM(16, 2, 12, 8, 16, 11);
     if (var == 3404) return MB200_SM(4, 2, 12, 8, 4, 11);
+    if (var == 1035) return MB200_SM(8, 2, 12, 8, 32, 11 + 1024);
     if (var == 267) return MB200_SM(8, 2, 12, 8, 32, 11 + 256);
     if (var == 523) return MB200_SM(8, 2, 12, 8, 32, 11 + 512);
     if (var == 1100) return MB200_SM(8, 2, 0, 8, 32, 11);

@@ -226,10 +226,19 @@ struct IOQueueShadow {
 //  32  at most one stack pop per warp iteration (no inner pop loop)
 //  64  camera rays: the (tile, pass) decode of a 32-item chunk is done once per chunk, not per ray
 // 256 / 512  a LEAF step tests up to 2 / 4 triangles of the leaf (in order) instead of one
+// 1024  drain-phase prefetch: once the ray pool is exhausted (the warps that are left run at memory latency, not
+//       at issue rate) the records of a leaf are prefetched when the leaf is entered and a pushed far child when
+//       it is pushed, whatever bit 8 says
 constexpr int kVarWideNode = 1, kVarSignMask = 2, kVarLeafPrefetch1 = 4, kVarNoPrefetch = 8, kVarTriBranchFree = 16,
-              kVarSinglePop = 32, kVarChunkDecode = 64, kVarLeaf2 = 256, kVarLeaf4 = 512;
+              kVarSinglePop = 32, kVarChunkDecode = 64, kVarLeaf2 = 256, kVarLeaf4 = 512, kVarDrainPrefetch = 1024;
 
-template <bool F32, int VAR> __device__ __forceinline__ void prefetch_next(const SceneView &sc, uint32_t ref, uint32_t rc) {
+template <bool F32, int VAR>
+__device__ __forceinline__ void prefetch_next(const SceneView &sc, uint32_t ref, uint32_t rc, bool draining = false) {
+  if ((VAR & kVarDrainPrefetch) && draining) {
+    if (rc == kBranch) prefetch_l1(sc.nodes + ref);
+    else prefetch_leaf<F32>(sc.tris, ref, rc);
+    return;
+  }
   if (VAR & kVarNoPrefetch) return;
   if (rc == kBranch) {
     prefetch_l1(sc.nodes + ref);
@@ -380,6 +389,8 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
       const bool sgn = ((r.sgn >> nw.axis) & 1u) != 0u; // dirSign[axis]
       if (h0 && h1) { // near = data[dirSign[axis]] first, far pushed with its tmin (bvh_accel.cc:818-823)
         st.put(sp++, sgn ? t0 : t1, sgn ? nw.ref0 : nw.ref1, sgn ? nw.cnt0 : nw.cnt1);
+        if ((VAR & kVarDrainPrefetch) && exhausted && (sgn ? nw.cnt0 : nw.cnt1) != 0u)
+          prefetch_next<F32, VAR>(sc, sgn ? nw.ref0 : nw.ref1, sgn ? nw.cnt0 : nw.cnt1, true);
         if (COUNT) cnt.max_stack = max(cnt.max_stack, (unsigned int)sp + 1u);
         ref = sgn ? nw.ref1 : nw.ref0, rc = sgn ? nw.cnt1 : nw.cnt0;
       } else if (h0) {
@@ -391,7 +402,7 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
       }
       if (rc != 0u) {
         if (COUNT && rc != kBranch) cnt.tris += rc;
-        prefetch_next<F32, VAR>(sc, ref, rc);
+        prefetch_next<F32, VAR>(sc, ref, rc, exhausted);
       }
     } else if (run_leaf && at_leaf) {
       // ---- LEAF: one triangle of TestLeafNode (bvh_accel.cc:640-697), in indices_ order -----------------

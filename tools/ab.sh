@@ -1,7 +1,8 @@
 mkdir -p gpurun_out
 run() { env "$@" python tools/ab_frame.py 2>&1 | tail -1; }
 run A=1
-for v in 3016 3008 3116 3404; do
-run MB200_TRACE_VAR=$v
-MB200_TRACE_VAR=$v python tools/ab_small.py | tail -2
-done
+python tools/ab_small.py | tail -2
+python tools/ab_size.py | head -4
+run MB200_TRACE_VAR=1035
+MB200_TRACE_VAR=1035 python tools/ab_small.py | tail -2
+MB200_TRACE_VAR=1035 python tools/ab_size.py | head -4
