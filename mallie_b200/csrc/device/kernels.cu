@@ -405,6 +405,54 @@ __global__ void __launch_bounds__(256)
   else count[pix] += (int)m.passes;
 }
 
+// order = stable partition of 0 .. tiles-1: the tiles flagged in `hot` first, then the others; clears `hot`.
+// One CTA of 1024 threads (a 1080p frame has 64 800 tiles: 64 rounds).
+__global__ void __launch_bounds__(1024) k_build_order(unsigned char *__restrict__ hot, uint32_t tiles,
+                                                      uint32_t *__restrict__ order) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t base_hot, base_cold;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  // pass 1: how many hot tiles
+  uint32_t mine = 0;
+  for (uint32_t i = tid; i < tiles; i += 1024u) mine += hot[i] ? 1u : 0u;
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(kFullMask, mine, o);
+  if (lane == 0) warp_sums[warp] = mine;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < 32; w++) t += warp_sums[w];
+    base_hot = 0, base_cold = t;
+  }
+  __syncthreads();
+  // pass 2: rounds of 1024 tiles, each a block-wide exclusive scan of the hot flags
+  for (uint32_t start = 0; start < tiles; start += 1024u) {
+    const uint32_t i = start + tid;
+    const bool in = i < tiles;
+    const bool h = in && hot[i] != 0;
+    const unsigned bal = __ballot_sync(kFullMask, h);
+    const uint32_t before = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_sums[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t warp_off = 0, round_hot = 0;
+    for (uint32_t w = 0; w < 32u; w++) {
+      const uint32_t c = warp_sums[w];
+      if (w < warp) warp_off += c;
+      round_hot += c;
+    }
+    const uint32_t hot_rank = warp_off + before;   // hot tiles of this round before me
+    const uint32_t cold_rank = tid - hot_rank;     // cold tiles of this round before me
+    if (in) order[h ? base_hot + hot_rank : base_cold + cold_rank] = i;
+    if (in) hot[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t n = (tiles - start < 1024u) ? tiles - start : 1024u;
+      base_hot += round_hot;
+      base_cold += n - round_hot;
+    }
+    __syncthreads();
+  }
+}
+
 // stats of a batch -> the caller's accumulated stats (shadow rays traced = fill of the shadow queue)
 __global__ void k_add_stats(const unsigned long long *__restrict__ batch, const unsigned int *__restrict__ shadow_count,
                             unsigned long long *__restrict__ total) {
@@ -694,12 +742,29 @@ cudaError_t FramePipe::init() {
   return cudaSuccess;
 }
 
+cudaError_t FramePipe::reserve_tiles(size_t tiles, cudaStream_t s) {
+  if (tiles <= tiles_cap) return cudaSuccess;
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return e;
+  if (hot) cudaFree(hot);
+  if (order) cudaFree(order);
+  hot = nullptr, order = nullptr, tiles_cap = 0, have_hot = false;
+  const size_t cap = tiles + tiles / 4 + 1024;
+  if ((e = cudaMalloc(&hot, cap)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&order, cap * sizeof(uint32_t))) != cudaSuccess) return e;
+  tiles_cap = cap;
+  return cudaSuccess;
+}
+
 void FramePipe::release() {
   for (cudaEvent_t ev : {fork, join, resolved[0], resolved[1]})
     if (ev) cudaEventDestroy(ev);
   if (aux) cudaStreamDestroy(aux);
+  if (hot) cudaFree(hot);
+  if (order) cudaFree(order);
   aux = nullptr;
   fork = join = resolved[0] = resolved[1] = nullptr;
+  hot = nullptr, order = nullptr, tiles_cap = 0, have_hot = false;
 }
 
 void KernelTimer::release() {
@@ -849,6 +914,27 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
     if (scratch.bytes < slot_bytes * 2 && (e = cudaStreamSynchronize(pipe->aux)) != cudaSuccess) return e;
   }
   if ((e = frame_scratch_reserve(scratch, slot_bytes * (piped ? 2 : 1), s)) != cudaSuccess) return e;
+  // longest-rays-first schedule from the previous frame's flags (same tile layout only)
+  const uint32_t *order = nullptr;
+  unsigned char *hot = nullptr;
+  static const bool lpt_off = env_int("MB200_FRAME_LPT", 1) == 0;
+  if (pipe && !lpt_off && tiles >= 1024) {
+    const long long layout[12] = {p.width, p.height, p.x0, p.y0, p.x1, p.y1, p.band_rows, p.band_count,
+                                  p.band_index, p.band_compact, p.pixel_step, (long long)tiles};
+    if ((e = pipe->reserve_tiles(tiles, s)) != cudaSuccess) return e;
+    const bool same = pipe->have_hot && memcmp(layout, pipe->layout, sizeof(layout)) == 0;
+    if (same) {
+      k_build_order<<<1, 1024, 0, s>>>(pipe->hot, (uint32_t)tiles, pipe->order);
+      g_launches++;
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      order = pipe->order;
+    } else {
+      if ((e = cudaMemsetAsync(pipe->hot, 0, tiles, s)) != cudaSuccess) return e;
+      memcpy(pipe->layout, layout, sizeof(layout));
+    }
+    hot = pipe->hot;
+    pipe->have_hot = true;
+  }
   if (piped) { // aux starts after whatever the caller queued on s (uploads, the previous frame)
     if ((e = cudaEventRecord(pipe->fork, s)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(pipe->aux, pipe->fork, 0)) != cudaSuccess) return e;
@@ -871,7 +957,8 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
     queue[1] = path ? reinterpret_cast<QRay *>(reinterpret_cast<char *>(queue[0]) + queue_bytes) : queue[0];
     PathState *states = path ? reinterpret_cast<PathState *>(reinterpret_cast<char *>(queue[0]) + 2 * queue_bytes) : nullptr;
 
-    const FrameMap m = make_frame_map(p, p.pass + (uint32_t)done, (uint32_t)nb);
+    FrameMap m = make_frame_map(p, p.pass + (uint32_t)done, (uint32_t)nb);
+    m.order = order, m.hot = hot;
     const uint32_t items = (uint32_t)(tiles * 32 * (size_t)nb);
     if ((e = cudaMemsetAsync(base, 0, ctl_bytes, st)) != cudaSuccess) return e;
 
@@ -890,13 +977,13 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
     if (shadow) {
-      const IOQueueShadow io{queue[0], contrib};
+      const IOQueueShadow io{queue[0], contrib, m};
       TimedScope ts(timer, kKShadowTrace, st);
       if ((e = launch_trace_nocount<IOQueueShadow, true>(sc, stack_cap, io, 0, qcount + 0, work + 1, st)) != cudaSuccess) return e;
     } else if (path) {
       for (int len = 2; len <= p.max_path_length; len++) {
         const int qi = len & 1; // segment `len` reads queue[qi], writes queue[qi ^ 1]
-        const IOQueueClosest io{queue[qi], hits};
+        const IOQueueClosest io{queue[qi], hits, m};
         {
           TimedScope ts(timer, kKBounceTrace, st);
           e = launch_trace_nocount<IOQueueClosest, false>(sc, stack_cap, io, 0, qcount + (len - 2), work + (len - 1), st);

@@ -36,10 +36,22 @@ struct KernelTimer {
 // stream and `aux`, so that the drain phase of one persistent traversal kernel (the last, longest rays of a
 // launch run at single-warp latency while the rest of the GPU idles: ~0.35 ms per launch on the 1 M-triangle
 // scene) is filled by the next batch's kernel instead of being waited for.
+//
+// It also owns the longest-rays-first schedule.  What is left of the tail belongs to the last launch of a
+// frame, whose long rays (silhouette tiles) happen to be handed out late.  The traversal kernels flag the tiles
+// that held a ray of more than kHotSteps steps (`hot`); the next frame over the same tile layout hands those
+// tiles out first (`order`, a stable partition of the tile indices built by k_build_order), so its long rays
+// start while the GPU is full.  Pure scheduling: which warp traces a ray never changes a result.
 struct FramePipe {
   cudaStream_t aux = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr, resolved[2] = {nullptr, nullptr};
+  unsigned char *hot = nullptr; // [tiles_cap]
+  uint32_t *order = nullptr;    // [tiles_cap]
+  size_t tiles_cap = 0;
+  long long layout[12] = {0};   // the tile layout `hot` was collected for
+  bool have_hot = false;
   cudaError_t init();
+  cudaError_t reserve_tiles(size_t tiles, cudaStream_t s);
   void release();
 };
 

@@ -227,7 +227,14 @@ struct FrameMap {
   int y1;               // end row of the rectangle (block fill clipping)
   // exact division by the launch constants passes / tiles_x as one 64-bit high multiply (0 means d == 1)
   unsigned long long magic_passes, magic_tiles_x;
+  // Longest-rays-first scheduling (kernels.h: FramePipe).  order (nullable = identity): the tile that work-item
+  // slot k stands for, tiles that held long rays in the previous frame first; hot (nullable): per tile, set
+  // by the traversal kernels when one of the tile's rays needed more than kHotSteps steps.
+  const uint32_t *order;
+  unsigned char *hot;
 };
+
+constexpr uint32_t kHotSteps = 160; // mean ray ~35 steps, p99 ~130, silhouette rays up to ~430 (1 M-triangle sphere)
 
 // M = ceil(2^64 / d) = (2^64 + e) / d with 0 <= e < d.  For n < 2^32: n * M / 2^64 = n / d + n * e / (d * 2^64),
 // and n * e < 2^64, so the extra term is below 1 / d and floor(n * M / 2^64) == floor(n / d): exact.
@@ -257,6 +264,7 @@ __host__ inline FrameMap make_frame_map(const mb200_render_params &p, uint32_t p
   m.band_rows = p.band_rows, m.band_count = p.band_count, m.band_index = p.band_index, m.compact = p.band_compact;
   m.passes = passes, m.pass0 = pass0;
   m.magic_passes = div_magic(passes), m.magic_tiles_x = div_magic((uint32_t)m.tiles_x);
+  m.order = nullptr, m.hot = nullptr;
   return m;
 }
 
@@ -267,8 +275,9 @@ __host__ inline size_t frame_map_tiles(const FrameMap &m) {
 // item -> pixel; returns false for padding lanes.  rl = row among the rows this call owns.
 __device__ __forceinline__ bool item_pixel(const FrameMap &m, uint32_t item, int &x, int &y, int &rl, uint32_t &pass) {
   const uint32_t lane = item & 31u, g = item >> 5;
-  const uint32_t tile = m.magic_passes ? (uint32_t)__umul64hi((unsigned long long)g, m.magic_passes) : g;
-  pass = m.pass0 + (g - tile * m.passes);
+  const uint32_t slot = m.magic_passes ? (uint32_t)__umul64hi((unsigned long long)g, m.magic_passes) : g;
+  pass = m.pass0 + (g - slot * m.passes);
+  const uint32_t tile = m.order ? __ldg(m.order + slot) : slot;
   const uint32_t tyu = m.magic_tiles_x ? (uint32_t)__umul64hi((unsigned long long)tile, m.magic_tiles_x) : tile;
   const int ty = (int)tyu, tx = (int)(tile - tyu * (uint32_t)m.tiles_x);
   x = m.x0 + (tx * 8 + (int)(lane & 7u)) * m.step;
@@ -276,6 +285,14 @@ __device__ __forceinline__ bool item_pixel(const FrameMap &m, uint32_t item, int
   y = m.y0 + rl * m.step;
   if (m.band_rows > 0) y = m.y0 + ((rl / m.band_rows) * m.band_count + m.band_index) * m.band_rows + rl % m.band_rows;
   return x < m.x1 && rl < m.rows_local;
+}
+
+// a ray of work item `item` turned out to be long: remember its tile for the next frame's schedule
+__device__ __forceinline__ void mark_hot_tile(const FrameMap &m, uint32_t item) {
+  if (!m.hot) return;
+  const uint32_t g = item >> 5;
+  const uint32_t slot = m.magic_passes ? (uint32_t)__umul64hi((unsigned long long)g, m.magic_passes) : g;
+  m.hot[m.order ? __ldg(m.order + slot) : slot] = 1;
 }
 
 // where a pixel of this call lives in the caller's image / count buffers

@@ -64,6 +64,8 @@ struct NoChunk {};
 
 // K2 over a caller's ray buffer (mb200_trace_closest).
 struct IOClosest {
+  static constexpr bool kTracksCost = false;
+  __device__ __forceinline__ void mark_hot(uint32_t) const {}
   typedef NoChunk Chunk;
   __device__ __forceinline__ void prepare(Chunk &, uint32_t) const {}
   __device__ __forceinline__ bool load(const Chunk &, uint32_t i, double &ox, double &oy, double &oz, double &dx,
@@ -89,6 +91,8 @@ struct IOClosest {
 
 // K4 over a caller's ray buffer (mb200_trace_occluded).
 struct IOOccluded {
+  static constexpr bool kTracksCost = false;
+  __device__ __forceinline__ void mark_hot(uint32_t) const {}
   typedef NoChunk Chunk;
   __device__ __forceinline__ void prepare(Chunk &, uint32_t) const {}
   __device__ __forceinline__ bool load(const Chunk &, uint32_t i, double &ox, double &oy, double &oz, double &dx,
@@ -115,6 +119,8 @@ struct IOOccluded {
 // the refill step -- Camera::GenerateRay (camera.cc:222-240) after PathTrace's jitter (render.cc:386-393)
 // -- and never stored; hits[i] receives the 32-byte record.
 struct IOCamera {
+  static constexpr bool kTracksCost = true;
+  __device__ __forceinline__ void mark_hot(uint32_t i) const { mark_hot_tile(m, i); }
   // (tile, pass) of the chunk the warp is drawing from: one decode (three integer divisions) per 32 rays
   struct Chunk {
     uint32_t group; // item >> 5 the fields below belong to (0xFFFFFFFF: none)
@@ -162,6 +168,8 @@ struct IOCamera {
 
 // K2 over a queue of path-continuation rays: hits[i] for queue slot i.
 struct IOQueueClosest {
+  static constexpr bool kTracksCost = true;
+  __device__ __forceinline__ void mark_hot(uint32_t i) const { mark_hot_tile(m, __ldg(&q[i].item)); }
   typedef NoChunk Chunk;
   __device__ __forceinline__ void prepare(Chunk &, uint32_t) const {}
   __device__ __forceinline__ bool load(const Chunk &, uint32_t i, double &ox, double &oy, double &oz, double &dx,
@@ -170,6 +178,7 @@ struct IOQueueClosest {
   }
   const QRay *q;
   mb200_hit *hits;
+  FrameMap m;
   __device__ __forceinline__ bool load(uint32_t i, double &ox, double &oy, double &oz, double &dx, double &dy,
                                        double &dz, double &t0) const {
     const double2 *p = reinterpret_cast<const double2 *>(q + i);
@@ -187,6 +196,8 @@ struct IOQueueClosest {
 
 // K4 over the queue of shadow rays: an unoccluded ray deposits its `value` into its sample's slot.
 struct IOQueueShadow {
+  static constexpr bool kTracksCost = true;
+  __device__ __forceinline__ void mark_hot(uint32_t i) const { mark_hot_tile(m, __ldg(&q[i].item)); }
   typedef NoChunk Chunk;
   __device__ __forceinline__ void prepare(Chunk &, uint32_t) const {}
   __device__ __forceinline__ bool load(const Chunk &, uint32_t i, double &ox, double &oy, double &oz, double &dx,
@@ -195,6 +206,7 @@ struct IOQueueShadow {
   }
   const QRay *q;
   float *contrib; // [items]
+  FrameMap m;
   __device__ __forceinline__ bool load(uint32_t i, double &ox, double &oy, double &oz, double &dx, double &dy,
                                        double &dz, double &t0) const {
     const double2 *p = reinterpret_cast<const double2 *>(q + i);
@@ -297,13 +309,14 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
   int sp = 0;
   uint32_t pool_next = 0, pool_end = 0;
   bool exhausted = false;
+  uint32_t iter = 0, born = 0; // warp iterations so far / at the time this lane's ray was loaded
   typename IO::Chunk chunk;
   TravCounters cnt = {0u, 0u, 0u};
   unsigned int nrays = 0;
   r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = r.ix = r.iy = r.iz = 0.0;
   r.sgn = 0u;
 
-  for (;;) {
+  for (;; iter++) {
     // ---- A. refill idle lanes from the warp's pool of ray indices ----------------------------------
     const unsigned idle = __ballot_sync(kFullMask, rc == kIdle);
     if (idle) {
@@ -332,6 +345,7 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
               hit_t = t0;
               if (ANYHIT) tmax_any = t0;
               sp = 0;
+              if (IO::kTracksCost) born = iter;
               if (COUNT) nrays++;
               bool enter = false;
               if (!sc.empty) {
@@ -415,6 +429,7 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
           io.accept(item, hit_t, u, v, tv.face, tv.mat);
           if (ANYHIT && hit_t < tmax_any) { // occluded: closest-hit Traverse would return t < tmax
             io.finish(item, true);
+            if (IO::kTracksCost && iter - born > kHotSteps) io.mark_hot(item);
             rc = kIdle;
           }
         }
@@ -445,6 +460,7 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
         for (;;) {
           if (sp == 0) {
             io.finish(item, false);
+            if (IO::kTracksCost && iter - born > kHotSteps) io.mark_hot(item);
             rc = kIdle;
             break;
           }
