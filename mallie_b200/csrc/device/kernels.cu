@@ -796,7 +796,7 @@ cudaError_t launch_trace_closest(const SceneView &sc, int stack_cap, const mb200
                                  cudaStream_t s, KernelTimer *timer) {
   cudaError_t e = cudaMemsetAsync(work, 0, sizeof(unsigned long long), s);
   if (e != cudaSuccess) return e;
-  const IOClosest io{rays, hits};
+  const IOClosest io{{0u}, rays, hits};
   TimedScope ts(timer, kKQueryTrace, s);
   return launch_trace<IOClosest, false>(sc, stack_cap, io, n, nullptr, work, counters, s);
 }
@@ -806,7 +806,7 @@ cudaError_t launch_trace_occluded(const SceneView &sc, int stack_cap, const mb20
                                   unsigned long long *counters, cudaStream_t s, KernelTimer *timer) {
   cudaError_t e = cudaMemsetAsync(work, 0, sizeof(unsigned long long), s);
   if (e != cudaSuccess) return e;
-  const IOOccluded io{rays, tmax, occ};
+  const IOOccluded io{{0u}, rays, tmax, occ};
   TimedScope ts(timer, kKQueryTrace, s);
   return launch_trace<IOOccluded, true>(sc, stack_cap, io, n, nullptr, work, counters, s);
 }
@@ -959,6 +959,10 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
 
     FrameMap m = make_frame_map(p, p.pass + (uint32_t)done, (uint32_t)nb);
     m.order = order, m.hot = hot;
+    {
+      static const int hs = env_int("MB200_HOT_STEPS", (int)kHotSteps);
+      m.hot_steps = (uint32_t)hs;
+    }
     const uint32_t items = (uint32_t)(tiles * 32 * (size_t)nb);
     if ((e = cudaMemsetAsync(base, 0, ctl_bytes, st)) != cudaSuccess) return e;
 

@@ -232,6 +232,7 @@ struct FrameMap {
   // by the traversal kernels when one of the tile's rays needed more than kHotSteps steps.
   const uint32_t *order;
   unsigned char *hot;
+  uint32_t hot_steps;
 };
 
 constexpr uint32_t kHotSteps = 160; // mean ray ~35 steps, p99 ~130, silhouette rays up to ~430 (1 M-triangle sphere)
@@ -264,7 +265,7 @@ __host__ inline FrameMap make_frame_map(const mb200_render_params &p, uint32_t p
   m.band_rows = p.band_rows, m.band_count = p.band_count, m.band_index = p.band_index, m.compact = p.band_compact;
   m.passes = passes, m.pass0 = pass0;
   m.magic_passes = div_magic(passes), m.magic_tiles_x = div_magic((uint32_t)m.tiles_x);
-  m.order = nullptr, m.hot = nullptr;
+  m.order = nullptr, m.hot = nullptr, m.hot_steps = kHotSteps;
   return m;
 }
 

@@ -63,8 +63,13 @@ __device__ __forceinline__ void store_miss(mb200_hit *dst) { store_hit(dst, DBL_
 struct NoChunk {};
 
 // K2 over a caller's ray buffer (mb200_trace_closest).
+struct NoCostMap {
+  uint32_t hot_steps;
+};
+
 struct IOClosest {
   static constexpr bool kTracksCost = false;
+  NoCostMap m;
   __device__ __forceinline__ void mark_hot(uint32_t) const {}
   typedef NoChunk Chunk;
   __device__ __forceinline__ void prepare(Chunk &, uint32_t) const {}
@@ -92,6 +97,7 @@ struct IOClosest {
 // K4 over a caller's ray buffer (mb200_trace_occluded).
 struct IOOccluded {
   static constexpr bool kTracksCost = false;
+  NoCostMap m;
   __device__ __forceinline__ void mark_hot(uint32_t) const {}
   typedef NoChunk Chunk;
   __device__ __forceinline__ void prepare(Chunk &, uint32_t) const {}
@@ -429,7 +435,7 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
           io.accept(item, hit_t, u, v, tv.face, tv.mat);
           if (ANYHIT && hit_t < tmax_any) { // occluded: closest-hit Traverse would return t < tmax
             io.finish(item, true);
-            if (IO::kTracksCost && iter - born > kHotSteps) io.mark_hot(item);
+            if (IO::kTracksCost && iter - born > io.m.hot_steps) io.mark_hot(item);
             rc = kIdle;
           }
         }
@@ -460,7 +466,7 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
         for (;;) {
           if (sp == 0) {
             io.finish(item, false);
-            if (IO::kTracksCost && iter - born > kHotSteps) io.mark_hot(item);
+            if (IO::kTracksCost && iter - born > io.m.hot_steps) io.mark_hot(item);
             rc = kIdle;
             break;
           }

@@ -1,8 +1,1 @@
-mkdir -p gpurun_out
-run() { env "$@" python tools/ab_frame.py 2>&1 | tail -1; }
-run A=1
-python tools/ab_small.py | tail -2
-python tools/ab_size.py | head -4
-run MB200_TRACE_VAR=1035
-MB200_TRACE_VAR=1035 python tools/ab_small.py | tail -2
-MB200_TRACE_VAR=1035 python tools/ab_size.py | head -4
+for hs in 48 96 128 160 224 320; do echo "HOT_STEPS=$hs"; MB200_HOT_STEPS=$hs python tools/ab_band.py | grep "N=1\|N=8"; done
