@@ -257,6 +257,7 @@ void scene_destroy(mb200_scene *s) {
   if (!s) return;
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->pipe.aux) cudaStreamSynchronize(s->pipe.aux);
   for (void *p : s->allocs) cudaFree(p);
   mb200_scene::Staging *sts[4] = {&s->in0, &s->in1, &s->out0, &s->out1};
   for (auto *st : sts) {
