@@ -148,12 +148,13 @@ class CpuSide:
         if R.available():
             self.ref = R.RefScene.from_arrays(v, f)
             self.ref.build()
-        self.cores = os.cpu_count() or 1
+        # all host threads, explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers
+        self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
     def pass_rays(self, k):
         """Exact ray set of pass k (jittered camera rays + shadow rays) and its oracle node/triangle counts."""
         _, _, info = self.bvh.render_pass(self.frame, W, H, rng_mode=1, pass_index=k, shader=1, light=LIGHT,
-                                          emit_rays=True)
+                                          emit_rays=True, nthreads=self.cores)
         rays = np.concatenate([info["primary_rays"], info["shadow_rays_buf"]], axis=0)
         return rays, info
 
@@ -161,7 +162,8 @@ class CpuSide:
         """sum over all rays of 64*N_node + 88*N_tri + 48 + 32 (SURVEY.md §8d / BASELINE.md §3)."""
         tot = dict(rays=0, n_node=0, n_tri=0, shadow=0, shadow_n_node=0, shadow_n_tri=0)
         for k in passes:
-            _, _, info = self.bvh.render_pass(self.frame, W, H, rng_mode=1, pass_index=k, shader=1, light=LIGHT)
+            _, _, info = self.bvh.render_pass(self.frame, W, H, rng_mode=1, pass_index=k, shader=1, light=LIGHT,
+                                              nthreads=self.cores)
             tot["rays"] += info["trace_calls"] + info["shadow_rays"]
             tot["shadow"] += info["shadow_rays"]
             for key in ("n_node", "n_tri", "shadow_n_node", "shadow_n_tri"):
@@ -174,10 +176,10 @@ class CpuSide:
     def trace_seconds(self, rays, repeat=1):
         """Reference Scene::Trace over the ray buffer, OpenMP schedule(dynamic,1) over 1920-ray rows."""
         if self.ref is not None:
-            return self.ref.trace(rays, row=W, nthreads=0, repeat=repeat)["seconds"], "reference"
+            return self.ref.trace(rays, row=W, nthreads=self.cores, repeat=repeat)["seconds"], "reference"
         best = 1e30
         for _ in range(repeat):
-            best = min(best, self.bvh.trace(rays, row=W)["seconds"])
+            best = min(best, self.bvh.trace(rays, row=W, nthreads=self.cores)["seconds"])
         return best, "port"
 
 
@@ -237,6 +239,8 @@ def main():
     if world != args.gpus and world > 1:
         args.gpus = world
     torch.cuda.set_device(local_rank)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: one JSON line only
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
