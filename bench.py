@@ -43,6 +43,24 @@ METRIC = "Mrays/s primary+shadow at 1920x1080"
 L2_FLUSH_BYTES = 512 << 20
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything libraries print to stdout (NCCL's version banner, ...) goes to stderr; the one JSON line of the
+    contract is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def config_dict(n_gpus):
     return {
         "workload": "bumpy-sphere N=500 (1,000,000 triangles, 501,501 vertices), 1920x1080, 16 spp, "
@@ -210,7 +228,7 @@ def run_reference_arm(args):
                                    "over 1920-ray rows on all host threads"},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -223,6 +241,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the oracle legs (roofline bytes + cpu_baseline)")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
     if args.warmup < 3:
@@ -433,7 +452,7 @@ def main():
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "rays_per_step": rays_frame, "shadow_rays_per_step": shadow_frame, "scene_build_upload_s": build_s,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     # tensors that were used on the scene's stream must be released before the stream is destroyed
     # (torch's caching allocator records an event on that stream when it frees them)
     del d_img, d_cnt, flush, gather, h_img, h_cnt, evs
