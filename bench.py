@@ -17,9 +17,12 @@ A "step" is one 16-spp frame: 33.2 M primary rays + ~11.4 M shadow rays.
           rays; per-instantiation breakdown under roofline.kernels).  achieved = algorithmic bytes per launch
           (64 B/node popped + 88 B/triangle tested + 48 B ray + 32 B hit record, counted by the CPU oracle in
           reference traversal order for the exact ray set; a shadow ray counts as the closest-hit Traverse that
-          defines its oracle) / average launch duration, timed with CUDA events around every launch on the
-          scene's stream inside the timed region (mb200_scene_timing), against the measured HBM copy bandwidth
-          in MEASURED_PEAKS.json.  traffic = ncu dram read+write bytes per launch (profiles/r1_traffic.json).
+          defines its oracle) / average launch duration, timed with CUDA events around every launch on its
+          stream inside the timed region (mb200_scene_timing), against the measured HBM copy bandwidth in
+          MEASURED_PEAKS.json.  Consecutive batches of a frame run on two streams so that one launch's drain
+          phase is filled by the next launch: durations are the UNION of the launches' time spans (per
+          instantiation, and over both for the headline figure) divided by the number of launches.
+          traffic = ncu dram read+write bytes per launch (profiles/r1_traffic.json).
 * cpu_baseline : the unmodified reference (oracle/_ref) tracing a sample of the same ray set on the host cores.
 * --impl reference : times the reference's own OpenMP CPU path on the same workload (rank 0 only).
 """
