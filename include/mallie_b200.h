@@ -131,6 +131,22 @@ const uint32_t *mb200_bvh_indices(const mb200_bvh *bvh);     /* BVHAccel::GetInd
 int mb200_bvh_stats(const mb200_bvh *bvh, mb200_build_stats *out); /* BVHAccel::GetStatistics */
 void mb200_bvh_destroy(mb200_bvh *bvh);
 
+/* The device layout mb200_scene_create would upload for this mesh + reference-layout BVH (host only, no GPU
+ * needed): the tree is validated exactly as by mb200_scene_create (MB200_ERR_INVALID_ARG + message for a
+ * malformed one), re-laid out as 128-byte pair nodes (both children's boxes in the parent) and per-leaf-order
+ * triangle records (mallie_b200/csrc/device/layout.h).  pair_nodes_out / tri_records_out may be NULL (sizes
+ * only); otherwise they receive num_pair_nodes * 128 and num_tri_records * tri_record_bytes bytes. */
+typedef struct {
+  uint64_t num_pair_nodes, num_tri_records;
+  uint32_t tri_record_bytes; /* 48: float-exact vertices, 80: double p0 + edges */
+  uint32_t root_ref, root_cnt; /* as a pair node's ref / cnt; cnt == 0xFFFFFFFF: the root is a branch */
+  int32_t depth, empty;
+} mb200_layout_info;
+int mb200_bvh_device_layout(const double *vertices, size_t nverts, const uint32_t *faces, size_t nfaces,
+                            const uint32_t *material_ids, const mb200_bvh_node *nodes, size_t nnodes,
+                            const uint32_t *indices, size_t nindices, mb200_layout_info *info,
+                            void *pair_nodes_out, void *tri_records_out);
+
 /* -------------------------------------------------------------------------
  * Mesh ingestion and configuration: what Scene::Init does before the BVH build
  * (scene.cc:66-170) and LoadJSONConfig (main.cc:98-205).  Host only.

@@ -33,6 +33,7 @@ EXPORTS = [
     "mb200_build_options_default", "mb200_bvh_build", "mb200_bvh_load", "mb200_bvh_dump",
     "mb200_bvh_num_nodes", "mb200_bvh_num_indices", "mb200_bvh_nodes", "mb200_bvh_indices",
     "mb200_bvh_stats", "mb200_bvh_destroy",
+    "mb200_bvh_device_layout",
     "mb200_scene_create", "mb200_scene_destroy", "mb200_scene_bounds", "mb200_scene_device_bytes",
     "mb200_scene_stream", "mb200_scene_device", "mb200_scene_uses_f32_vertices", "mb200_scene_synchronize",
     "mb200_scene_timing", "mb200_scene_kernel_times",
@@ -106,6 +107,18 @@ class KernelTimes(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class LayoutInfo(C.Structure):
+    _fields_ = [("num_pair_nodes", C.c_uint64), ("num_tri_records", C.c_uint64), ("tri_record_bytes", C.c_uint32),
+                ("root_ref", C.c_uint32), ("root_cnt", C.c_uint32), ("depth", C.c_int32), ("empty", C.c_int32)]
+
+
+PAIR_DTYPE = np.dtype([("box", "<f8", (2, 6)), ("ref", "<u4", (2,)), ("cnt", "<u4", (2,)), ("axis", "<u4"),
+                       ("pad", "<u4", (3,))])
+TRI32_DTYPE = np.dtype([("p0", "<f4", (3,)), ("face", "<u4"), ("p1", "<f4", (3,)), ("mat", "<u4"), ("p2", "<f4", (3,)),
+                        ("pad", "<u4")])
+TRI64_DTYPE = np.dtype([("p0", "<f8", (3,)), ("e1", "<f8", (3,)), ("e2", "<f8", (3,)), ("face", "<u4"), ("mat", "<u4")])
+
+
 class MallieB200Error(RuntimeError):
     pass
 
@@ -141,6 +154,7 @@ def lib():
         L.mb200_bvh_indices.argtypes = [vp]
         L.mb200_bvh_stats.argtypes = [vp, C.POINTER(BuildStats)]
         L.mb200_bvh_destroy.argtypes = [vp]
+        L.mb200_bvh_device_layout.argtypes = [vp, sz, vp, sz, vp, vp, sz, vp, sz, C.POINTER(LayoutInfo), vp, vp]
         L.mb200_scene_create.argtypes = [C.POINTER(vp), i32, vp, sz, vp, sz, vp, vp, vp, vp, sz, vp, sz]
         L.mb200_scene_destroy.argtypes = [vp]
         L.mb200_scene_bounds.argtypes = [vp, vp, vp]
@@ -218,6 +232,22 @@ def render_frame_multi(scenes, params, num_passes, band_rows=8, image=None, coun
     check(lib().mb200_render_frame_multi(arr, len(scenes), C.byref(params), num_passes, band_rows, _p(image), _p(count),
                                          C.byref(st) if stats else None))
     return image, count, (st.as_dict() if stats else None)
+
+
+def device_layout(vertices, faces, nodes, indices, material_ids=None):
+    """mb200_bvh_device_layout: (info dict, pair nodes, triangle records) -- what scene creation would upload."""
+    v = np.ascontiguousarray(vertices, np.float64).reshape(-1, 3)
+    f = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
+    n = np.ascontiguousarray(nodes)
+    i = np.ascontiguousarray(indices, np.uint32)
+    m = None if material_ids is None else np.ascontiguousarray(material_ids, np.uint32)
+    info = LayoutInfo()
+    args = (_p(v), v.shape[0], _p(f), f.shape[0], _p(m), _p(n), n.shape[0], _p(i), i.shape[0])
+    check(lib().mb200_bvh_device_layout(*args, C.byref(info), None, None))
+    pairs = np.zeros(info.num_pair_nodes, PAIR_DTYPE)
+    tris = np.zeros(info.num_tri_records, TRI32_DTYPE if info.tri_record_bytes == 48 else TRI64_DTYPE)
+    check(lib().mb200_bvh_device_layout(*args, C.byref(info), _p(pairs), _p(tris)))
+    return {k: int(getattr(info, k)) for k, _ in info._fields_}, pairs, tris
 
 
 def load_config(path=None, text=None):

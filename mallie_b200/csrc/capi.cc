@@ -182,6 +182,28 @@ int mb200_bvh_stats(const mb200_bvh *bvh, mb200_build_stats *out) {
 }
 void mb200_bvh_destroy(mb200_bvh *bvh) { delete bvh; }
 
+int mb200_bvh_device_layout(const double *vertices, size_t nverts, const uint32_t *faces, size_t nfaces,
+                            const uint32_t *material_ids, const mb200_bvh_node *nodes, size_t nnodes,
+                            const uint32_t *indices, size_t nindices, mb200_layout_info *info, void *pair_nodes_out,
+                            void *tri_records_out) {
+  if (!info) return set_err(MB200_ERR_INVALID_ARG, "info is null");
+  memset(info, 0, sizeof(*info));
+  mb200::Relayout r;
+  std::string err;
+  const int rc = mb200::relayout_bvh(r, vertices, nverts, faces, nfaces, material_ids, nodes, nnodes, indices, nindices, &err);
+  if (rc != MB200_OK) return set_err(rc, err);
+  info->num_pair_nodes = r.pairs.size();
+  info->num_tri_records = r.f32 ? r.tris32.size() : r.tris64.size();
+  info->tri_record_bytes = r.f32 ? (uint32_t)sizeof(mb200::TriRecordF32) : (uint32_t)sizeof(mb200::TriRecordF64);
+  info->root_ref = r.root_ref, info->root_cnt = r.root_cnt;
+  info->depth = r.depth, info->empty = r.empty ? 1 : 0;
+  if (pair_nodes_out && !r.pairs.empty()) memcpy(pair_nodes_out, r.pairs.data(), r.pairs.size() * sizeof(mb200::PairNode));
+  if (tri_records_out && info->num_tri_records)
+    memcpy(tri_records_out, r.f32 ? (const void *)r.tris32.data() : (const void *)r.tris64.data(),
+           (size_t)info->num_tri_records * info->tri_record_bytes);
+  return MB200_OK;
+}
+
 // ---------------------------------------------------------------------------- mesh + config
 static int load_mesh(mb200_mesh **out, const char *path, bool eson) {
   if (!out || !path) return set_err(MB200_ERR_INVALID_ARG, "null argument");

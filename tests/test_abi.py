@@ -215,3 +215,73 @@ def test_no_gpu_means_loud_failure_not_fallback():
         M.Scene(m["vertices"], m["faces"])
     assert "error -3" in str(e.value)            # MB200_ERR_NO_DEVICE
     assert capi.launches_issued() == 0
+
+
+@pytest.mark.parametrize("mesh", ["cornellbox", "teapot", "sphere40"])
+def test_device_layout_is_the_reference_tree(mesh):
+    """The host-side re-layout (device/layout.h: pair nodes with both children's boxes, leaf-order triangle records)
+    walked in lock-step with the reference-layout tree it was made from."""
+    m = T.load_mesh(mesh)
+    hb = M.HostBVH.build(m["vertices"], m["faces"])
+    nodes, idx = hb.arrays()
+    info, pairs, tris = capi.device_layout(m["vertices"], m["faces"], nodes, idx, m["material_ids"])
+    assert info["empty"] == 0 and info["tri_record_bytes"] == 48 and info["num_tri_records"] == len(idx)
+    assert info["num_pair_nodes"] == int((nodes["flag"] == 0).sum()) and info["depth"] == hb.stats()["maxTreeDepth"]
+    assert pairs.dtype.itemsize == 128 and (info["root_cnt"] == 0xFFFFFFFF) == (nodes[0]["flag"] == 0)
+    v, f = m["vertices"], m["faces"]
+    mats = m["material_ids"] if m["material_ids"] is not None else np.full(len(f), 0xFFFFFFFF, np.uint32)
+    # triangle records: leaf (indices_) order, float-exact vertices, faceID + materialID
+    assert np.array_equal(tris["face"], idx)
+    for k, name in enumerate(("p0", "p1", "p2")):
+        assert np.array_equal(tris[name].astype(np.float64), v[f[idx, k]])
+    assert np.array_equal(tris["mat"], mats[idx])
+    # lock-step walk
+    stack, seen = [(0, info["root_ref"], info["root_cnt"])], 0
+    while stack:
+        ref_node, ref, cnt = stack.pop()
+        nd = nodes[ref_node]
+        if nd["flag"] == 1:
+            assert cnt == nd["data"][0] and ref == nd["data"][1]
+            continue
+        assert cnt == 0xFFFFFFFF
+        pn = pairs[ref]
+        seen += 1
+        assert pn["axis"] == nd["axis"]
+        for c in range(2):
+            child = nodes[nd["data"][c]]
+            assert np.array_equal(pn["box"][c][:3], child["bmin"]) and np.array_equal(pn["box"][c][3:], child["bmax"])
+            stack.append((int(nd["data"][c]), int(pn["ref"][c]), int(pn["cnt"][c])))
+    assert seen == info["num_pair_nodes"]
+    hb.close()
+
+
+def test_device_layout_f64_records_empty_and_malformed_trees():
+    rng = np.random.default_rng(2)
+    v = rng.uniform(-1, 1, (300, 3))                       # not float-representable: 80-byte records with edges
+    f = np.arange(300, dtype=np.uint32).reshape(100, 3)
+    hb = M.HostBVH.build(v, f)
+    nodes, idx = hb.arrays()
+    info, pairs, tris = capi.device_layout(v, f, nodes, idx)
+    assert info["tri_record_bytes"] == 80 and np.array_equal(tris["face"], idx) and (tris["mat"] == 0xFFFFFFFF).all()
+    assert np.array_equal(tris["p0"], v[f[idx, 0]])
+    assert np.array_equal(tris["e1"], v[f[idx, 1]] - v[f[idx, 0]]) and np.array_equal(tris["e2"], v[f[idx, 2]] - v[f[idx, 0]])
+    info0, p0, t0 = capi.device_layout(np.zeros((0, 3)), np.zeros((0, 3), np.uint32), np.zeros(0, capi.NODE_DTYPE),
+                                       np.zeros(0, np.uint32))
+    assert info0["empty"] == 1 and len(p0) == 0 and len(t0) == 0
+    for breakage in ("cycle", "child_oob", "leaf_oob", "axis", "index_oob"):
+        bad, bidx = nodes.copy(), idx.copy()
+        b = int(np.nonzero(bad["flag"] == 0)[0][0])
+        leaf = int(np.nonzero(bad["flag"] == 1)[0][0])
+        if breakage == "cycle":
+            bad["data"][b][1] = b
+        elif breakage == "child_oob":
+            bad["data"][b][0] = len(bad) + 5
+        elif breakage == "leaf_oob":
+            bad["data"][leaf][1] = len(idx)
+        elif breakage == "axis":
+            bad["axis"][b] = 3
+        else:
+            bidx[0] = len(f)
+        with pytest.raises(M.MallieB200Error):
+            capi.device_layout(v, f, bad, bidx)
+    hb.close()
