@@ -252,3 +252,40 @@ def test_panorama_cameras_and_env_shader(stereo):
     with pytest.raises(M.MallieB200Error):
         sc.render_pass(bad)
     sc.close()
+
+
+def test_longest_rays_first_schedule_is_invisible():
+    """The tile order built from the previous frame's long-ray flags (k_build_order) only changes which warp traces
+    which ray: frames 2 and 3 over the same layout must equal frame 1 (identity order) bit for bit.  The threshold
+    is lowered (MB200_HOT_STEPS, read once per process, hence the subprocess) so that a large share of the tiles is
+    flagged and reordered; the two-stream pipeline is exercised with 5 passes (batches of 3 + 2)."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+import mallie_b200 as M
+from tests import common as T
+m = T.load_mesh("teapot")
+sc = M.Scene(m["vertices"], m["faces"], m["material_ids"], m["normals"], m["uvs"])
+W, H = 640, 360                                     # 80 x 90 = 7200 tiles
+fg = M.camera_frame((5, 40, 150), (5, 40, 0), width=W, height=H)
+for shader, kw in ((M.SHADER_PRIMARY_SHADOW, dict(light=(100.0, 200.0, 150.0))), (M.SHADER_PATHTRACE, dict(max_path_length=4))):
+    p = sc.render_params(fg, W, H, shader=shader, pass_index=1, **kw)
+    frames = [sc.render_frame(p, 5) for _ in range(3)]
+    for img, cnt, st in frames[1:]:
+        assert img.tobytes() == frames[0][0].tobytes() and np.array_equal(cnt, frames[0][1]) and st == frames[0][2]
+    assert frames[0][0].max() > 0
+    # a different layout in between resets the schedule, and coming back is still exact
+    q = sc.render_params(fg, W, H, tile=(0, 0, W, H // 2), shader=shader, pass_index=1, **kw)
+    sc.render_frame(q, 2)
+    img, cnt, st = sc.render_frame(p, 5)
+    assert img.tobytes() == frames[0][0].tobytes()
+sc.close()
+print("LPT-OK")
+""" % T.HERE.rsplit("/", 1)[0]
+    for hot in ("6", "40"):
+        env = dict(os.environ, MB200_HOT_STEPS=hot)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+        assert r.returncode == 0 and "LPT-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
