@@ -122,6 +122,11 @@ int mb200_launches_issued(void);
 void mb200_build_options_default(mb200_build_options *opt);
 int mb200_bvh_build(mb200_bvh **out, const double *vertices, size_t nverts, const uint32_t *faces, size_t nfaces,
                     const mb200_build_options *opt /* NULL = defaults */);
+/* BVHAccel::Build on GPU `device`: the same tree as mb200_bvh_build, bit for bit (nodes, bounds, index order),
+ * grown level by level with one pass per level over all open nodes (mallie_b200/csrc/device/bvh_build_gpu.cu).
+ * Needs min_leaf_primitives >= 2.  MB200_ERR_CUDA when no usable device. */
+int mb200_bvh_build_device(mb200_bvh **out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
+                           size_t nfaces, const mb200_build_options *opt /* NULL = defaults */);
 int mb200_bvh_load(mb200_bvh **out, const char *path);       /* BVHAccel::Load  */
 int mb200_bvh_dump(const mb200_bvh *bvh, const char *path);  /* BVHAccel::Dump  */
 size_t mb200_bvh_num_nodes(const mb200_bvh *bvh);

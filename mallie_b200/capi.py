@@ -30,7 +30,7 @@ CAMERA_PINHOLE, CAMERA_ENV, CAMERA_ENV_STEREO = 0, 1, 2
 # Every symbol include/mallie_b200.h declares (tests/test_abi.py checks the header against this list).
 EXPORTS = [
     "mb200_last_error", "mb200_version", "mb200_device_count", "mb200_launches_issued",
-    "mb200_build_options_default", "mb200_bvh_build", "mb200_bvh_load", "mb200_bvh_dump",
+    "mb200_build_options_default", "mb200_bvh_build", "mb200_bvh_build_device", "mb200_bvh_load", "mb200_bvh_dump",
     "mb200_bvh_num_nodes", "mb200_bvh_num_indices", "mb200_bvh_nodes", "mb200_bvh_indices",
     "mb200_bvh_stats", "mb200_bvh_destroy",
     "mb200_bvh_device_layout",
@@ -142,6 +142,7 @@ def lib():
         L.mb200_launches_issued.restype = i32
         L.mb200_build_options_default.argtypes = [C.POINTER(BuildOptions)]
         L.mb200_bvh_build.argtypes = [C.POINTER(vp), vp, sz, vp, sz, C.POINTER(BuildOptions)]
+        L.mb200_bvh_build_device.argtypes = [C.POINTER(vp), C.c_int, vp, sz, vp, sz, C.POINTER(BuildOptions)]
         L.mb200_bvh_load.argtypes = [C.POINTER(vp), C.c_char_p]
         L.mb200_bvh_dump.argtypes = [vp, C.c_char_p]
         L.mb200_bvh_num_nodes.restype = sz
@@ -298,6 +299,16 @@ class HostBVH:
         opt = BuildOptions(cost_taabb, min_leaf, max_depth, bin_size)
         h = C.c_void_p()
         check(lib().mb200_bvh_build(C.byref(h), _p(v), v.shape[0], _p(f), f.shape[0], C.byref(opt)))
+        return cls(h)
+
+    @classmethod
+    def build_device(cls, vertices, faces, device=0, cost_taabb=0.2, min_leaf=16, max_depth=256, bin_size=64):
+        """The same tree, grown level by level on GPU `device` (mb200_bvh_build_device)."""
+        v = np.ascontiguousarray(vertices, np.float64).reshape(-1, 3)
+        f = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
+        opt = BuildOptions(cost_taabb, min_leaf, max_depth, bin_size)
+        h = C.c_void_p()
+        check(lib().mb200_bvh_build_device(C.byref(h), device, _p(v), v.shape[0], _p(f), f.shape[0], C.byref(opt)))
         return cls(h)
 
     @classmethod

@@ -151,6 +151,25 @@ int mb200_bvh_build(mb200_bvh **out, const double *vertices, size_t nverts, cons
   return MB200_OK;
 }
 
+int mb200_bvh_build_device(mb200_bvh **out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
+                           size_t nfaces, const mb200_build_options *opt) {
+  if (!out) return set_err(MB200_ERR_INVALID_ARG, "out is null");
+  *out = nullptr;
+  if ((nfaces && (!vertices || !faces))) return set_err(MB200_ERR_INVALID_ARG, "null mesh array");
+  mb200_build_options o;
+  mb200_build_options_default(&o);
+  if (opt) o = *opt;
+  mb200_bvh *b = new mb200_bvh;
+  std::string err;
+  bool cuda_failure = false;
+  if (!mb200::build_bvh_device(b->bvh, device, vertices, nverts, faces, nfaces, o, &err, &cuda_failure)) {
+    delete b;
+    return set_err(cuda_failure ? MB200_ERR_CUDA : MB200_ERR_INVALID_ARG, err);
+  }
+  *out = b;
+  return MB200_OK;
+}
+
 int mb200_bvh_load(mb200_bvh **out, const char *path) {
   if (!out || !path) return set_err(MB200_ERR_INVALID_ARG, "null argument");
   *out = nullptr;

@@ -1,0 +1,651 @@
+// bvh_build_gpu.cu -- BVHAccel::Build (bvh_accel.cc:36-482) on the device, bit-identical tree.
+//
+// The reference builder is a depth-first recursion; its result, however, is a pure function of the
+// triangle set of every node, so the same tree can be grown LEVEL BY LEVEL with all nodes of a level
+// processed side by side (host/bvh_build.cc is the sequential statement of the same algorithm and the
+// oracle for this file; tests compare the two bit for bit):
+//
+//   per level, over all active segments [l, r) of the index array:
+//     bounds      min / max of the cached triangle bounds, +- kEPS            (bvh_accel.cc:285-315)
+//     leaf test   n < minLeafPrimitives || depth >= maxTreeDepth               (bvh_accel.cc:341)
+//     histogram   64 bins x 3 axes of triangle-bound minima / maxima           (bvh_accel.cc:82-142)
+//     sweep       63 SAH planes per axis, evaluation order of the reference    (bvh_accel.cc:156-255)
+//     partition   std::partition on (p0+p1+p2)[axis] < 3*pos                   (bvh_accel.cc:257-277,402)
+//     children    [l, mid), [mid, r); object-median fallback                   (bvh_accel.cc:405-430)
+//   afterwards: subtree sizes bottom-up, pre-order numbers top-down (left child = parent + 1), emit.
+//
+// The partition is the only order-sensitive step.  libstdc++'s bidirectional std::partition swaps the
+// k-th misplaced element from the left with the k-th misplaced element from the RIGHT and touches nothing
+// else, so the final arrangement follows from two prefix sums over the "misplaced" flags; no sequential
+// pass is needed.  All floating-point expressions are those of host/bvh_build.cc (-fmad=false).
+//
+// Segmented reductions take a block-wide fast path when a whole CTA lies inside one segment (always true
+// near the root, where contention on per-segment atomics would otherwise serialise) and fall back to
+// per-element atomics elsewhere (deep levels: many small segments, no contention).
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../host/bvh_build.h"
+#include "mallie_b200.h"
+
+namespace mb200 {
+
+namespace {
+
+constexpr double kPad = DBL_EPSILON * 1024.0;
+constexpr uint32_t kNoSeg = 0xFFFFFFFFu;
+constexpr int kThreads = 256;
+
+#define CUB(call)                                   \
+  do {                                              \
+    cudaError_t e_ = (call);                        \
+    if (e_ != cudaSuccess) return e_;               \
+  } while (0)
+
+// order-preserving map double <-> uint64 (for atomicMin / atomicMax on doubles)
+__device__ __forceinline__ unsigned long long dkey(double x) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dunkey(unsigned long long k) {
+  const unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+struct Segs { // one level's active segments, sorted by l
+  uint32_t *l, *r, *node;
+};
+
+struct SegWork { // per segment, per level
+  unsigned long long *kmin; // [S*3] keys of min(lo)
+  unsigned long long *kmax; // [S*3] keys of max(hi)
+  double *bmin, *bmax;      // [S*3] padded bounds
+  double *scale, *step;     // [S*3]
+  uint8_t *leaf;            // [S]
+  uint32_t *hslot;          // [S] histogram slot of a branch segment
+  int32_t *axis;            // [S]
+  double *thresh;           // [S] 3 * cut position
+  uint32_t *ntrue;          // [S]
+  uint32_t *mid;            // [S]
+  uint32_t *isbranch;       // [S] 0 / 1 (scanned into child ordinals)
+};
+
+// ---- triangle cache ----------------------------------------------------------------------------------
+__global__ void k_tri_cache(const double *__restrict__ v, const uint32_t *__restrict__ f, uint32_t nt,
+                            double *__restrict__ lo, double *__restrict__ hi, double *__restrict__ cs,
+                            uint32_t *__restrict__ idx) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nt) return;
+  const double *p0 = v + 3 * (size_t)f[3 * t + 0], *p1 = v + 3 * (size_t)f[3 * t + 1], *p2 = v + 3 * (size_t)f[3 * t + 2];
+  for (int a = 0; a < 3; a++) {
+    double mn = p0[a], mx = p0[a];
+    if (p1[a] < mn) mn = p1[a];
+    if (mx < p1[a]) mx = p1[a];
+    if (p2[a] < mn) mn = p2[a];
+    if (mx < p2[a]) mx = p2[a];
+    lo[(size_t)a * nt + t] = mn;
+    hi[(size_t)a * nt + t] = mx;
+    cs[(size_t)a * nt + t] = p0[a] + p1[a] + p2[a];
+  }
+  idx[t] = t;
+}
+
+// ---- which segment does position i belong to (binary search over the sorted segment starts) ----------
+__global__ void k_assign_sid(uint32_t n, const uint32_t *__restrict__ sl, const uint32_t *__restrict__ sr, uint32_t S,
+                             uint32_t *__restrict__ sid) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t lo = 0, hi = S; // last segment with l <= i
+  while (hi - lo > 1) {
+    const uint32_t m = (lo + hi) >> 1;
+    if (sl[m] <= i) lo = m;
+    else hi = m;
+  }
+  sid[i] = (S > 0 && sl[lo] <= i && i < sr[lo]) ? lo : kNoSeg;
+}
+
+__global__ void k_init_keys(uint32_t S3, unsigned long long *kmin, unsigned long long *kmax) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < S3) kmin[i] = 0xFFFFFFFFFFFFFFFFull, kmax[i] = 0ull;
+}
+
+// ---- bounds -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_bounds(uint32_t n, uint32_t nt, const uint32_t *__restrict__ sid,
+                                                    const uint32_t *__restrict__ idx, const double *__restrict__ lo,
+                                                    const double *__restrict__ hi, unsigned long long *kmin,
+                                                    unsigned long long *kmax) {
+  __shared__ unsigned long long s_min[3][kThreads / 32], s_max[3][kThreads / 32];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t first = blockIdx.x * blockDim.x, last = min(first + blockDim.x, n) - 1;
+  const uint32_t s = i < n ? sid[i] : kNoSeg;
+  const bool uniform = sid[first] != kNoSeg && sid[first] == sid[last]; // segments are contiguous
+  unsigned long long mn[3] = {~0ull, ~0ull, ~0ull}, mx[3] = {0ull, 0ull, 0ull};
+  if (s != kNoSeg) {
+    const uint32_t t = idx[i];
+    for (int a = 0; a < 3; a++) mn[a] = dkey(lo[(size_t)a * nt + t]), mx[a] = dkey(hi[(size_t)a * nt + t]);
+  }
+  if (!uniform) {
+    if (s != kNoSeg)
+      for (int a = 0; a < 3; a++) atomicMin(&kmin[3 * (size_t)s + a], mn[a]), atomicMax(&kmax[3 * (size_t)s + a], mx[a]);
+    return;
+  }
+  for (int a = 0; a < 3; a++) {
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = min(mn[a], __shfl_down_sync(0xFFFFFFFFu, mn[a], o));
+      mx[a] = max(mx[a], __shfl_down_sync(0xFFFFFFFFu, mx[a], o));
+    }
+    if ((threadIdx.x & 31) == 0) s_min[a][threadIdx.x >> 5] = mn[a], s_max[a][threadIdx.x >> 5] = mx[a];
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int a = threadIdx.x;
+    unsigned long long m0 = ~0ull, m1 = 0ull;
+    for (int w = 0; w < kThreads / 32; w++) m0 = min(m0, s_min[a][w]), m1 = max(m1, s_max[a][w]);
+    const uint32_t sg = sid[first];
+    atomicMin(&kmin[3 * (size_t)sg + a], m0);
+    atomicMax(&kmax[3 * (size_t)sg + a], m1);
+  }
+}
+
+// ---- per segment: padded bounds, leaf decision, bin scale / step, histogram slot ----------------------
+__global__ void k_seg_setup(uint32_t S, const uint32_t *__restrict__ sl, const uint32_t *__restrict__ sr, int level,
+                            mb200_build_options opt, SegWork w, uint32_t *branch_counter) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const uint32_t n = sr[s] - sl[s];
+  const double nbins = (double)opt.bin_size;
+  for (int a = 0; a < 3; a++) {
+    const double bl = dunkey(w.kmin[3 * (size_t)s + a]) - kPad, bh = dunkey(w.kmax[3 * (size_t)s + a]) + kPad;
+    w.bmin[3 * (size_t)s + a] = bl;
+    w.bmax[3 * (size_t)s + a] = bh;
+    const double extent = bh - bl;
+    w.scale[3 * (size_t)s + a] = (extent > kPad) ? nbins / extent : 0.0;
+    w.step[3 * (size_t)s + a] = extent * (1.0 / opt.bin_size);
+  }
+  const bool leaf = n < (uint32_t)opt.min_leaf_primitives || level >= opt.max_tree_depth;
+  w.leaf[s] = leaf ? 1 : 0;
+  w.isbranch[s] = leaf ? 0u : 1u;
+  w.hslot[s] = leaf ? kNoSeg : atomicAdd(branch_counter, 1u);
+  w.ntrue[s] = 0u;
+}
+
+// ---- histograms: hist[slot][axis][0 = minima, 1 = maxima][bin] ----------------------------------------
+__global__ void __launch_bounds__(kThreads) k_histogram(uint32_t n, uint32_t nt, int nb, const uint32_t *__restrict__ sid,
+                                                       const uint32_t *__restrict__ idx, const double *__restrict__ lo,
+                                                       const double *__restrict__ hi, SegWork w, uint32_t *hist) {
+  extern __shared__ uint32_t s_hist[]; // [6 * nb] when the block lies inside one segment
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t first = blockIdx.x * blockDim.x, last = min(first + blockDim.x, n) - 1;
+  const uint32_t s0 = sid[first];
+  const bool uniform = s0 != kNoSeg && s0 == sid[last] && nb <= 512;
+  if (uniform && w.leaf[s0]) return;
+  if (uniform) {
+    for (int k = threadIdx.x; k < 6 * nb; k += blockDim.x) s_hist[k] = 0u;
+    __syncthreads();
+  }
+  const uint32_t s = i < n ? sid[i] : kNoSeg;
+  if (s != kNoSeg && !w.leaf[s]) {
+    const uint32_t t = idx[i];
+    const double nbins = (double)nb;
+    uint32_t *h = uniform ? s_hist : hist + (size_t)w.hslot[s] * 6 * nb;
+    for (int a = 0; a < 3; a++) {
+      const double bl = w.bmin[3 * (size_t)s + a], sc = w.scale[3 * (size_t)s + a];
+      size_t qlo = (unsigned int)floor((lo[(size_t)a * nt + t] - bl) * sc);
+      size_t qhi = (unsigned int)floor((hi[(size_t)a * nt + t] - bl) * sc);
+      if ((double)qlo >= nbins) qlo = (size_t)nb - 1;
+      if ((double)qhi >= nbins) qhi = (size_t)nb - 1;
+      atomicAdd(&h[(a * 2 + 0) * nb + qlo], 1u);
+      atomicAdd(&h[(a * 2 + 1) * nb + qhi], 1u);
+    }
+  }
+  if (uniform) {
+    __syncthreads();
+    uint32_t *g = hist + (size_t)w.hslot[s0] * 6 * nb;
+    for (int k = threadIdx.x; k < 6 * nb; k += blockDim.x)
+      if (s_hist[k]) atomicAdd(&g[k], s_hist[k]);
+  }
+}
+
+__device__ __forceinline__ double half_area2(const double lo[3], const double hi[3]) {
+  const double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+  return 2.0 * (dx * dy + dy * dz + dz * dx);
+}
+
+// ---- SAH sweep, one thread per branch segment (FindCutFromBinBuffer, bvh_accel.cc:156-255) -------------
+__global__ void k_sweep(uint32_t S, const uint32_t *__restrict__ sl, const uint32_t *__restrict__ sr,
+                        mb200_build_options opt, SegWork w, const uint32_t *__restrict__ hist) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S || w.leaf[s]) return;
+  const int nb = opt.bin_size;
+  const uint32_t *h = hist + (size_t)w.hslot[s] * 6 * nb;
+  double lo[3], hi[3];
+  for (int a = 0; a < 3; a++) lo[a] = w.bmin[3 * (size_t)s + a], hi[a] = w.bmax[3 * (size_t)s + a];
+  const size_t n = (size_t)sr[s] - sl[s];
+  const double t_box = opt.cost_taabb, t_tri = 1.0 - opt.cost_taabb;
+  const double whole = half_area2(lo, hi);
+  const double inv_whole = (whole > kPad) ? 1.0 / whole : 0.0;
+  double best_cost[3], best_pos[3];
+  for (int a = 0; a < 3; a++) {
+    const double step = w.step[3 * (size_t)s + a];
+    best_pos[a] = lo[a] + 0.5 * step;
+    best_cost[a] = DBL_MAX;
+    size_t nl = 0, nr = n;
+    double llo[3] = {lo[0], lo[1], lo[2]}, lhi[3] = {hi[0], hi[1], hi[2]};
+    double rlo[3] = {lo[0], lo[1], lo[2]}, rhi[3] = {hi[0], hi[1], hi[2]};
+    for (int i = 0; i < nb - 1; ++i) {
+      nl += h[(a * 2 + 0) * nb + i];
+      nr -= h[(a * 2 + 1) * nb + i];
+      const double pos = lo[a] + (i + 0.5) * step;
+      lhi[a] = pos;
+      rlo[a] = pos;
+      const double al = half_area2(llo, lhi), ar = half_area2(rlo, rhi);
+      const double cost = 2.0f * t_box + (al * inv_whole) * (double)(nl)*t_tri + (ar * inv_whole) * (double)(nr)*t_tri;
+      if (cost < best_cost[a]) {
+        best_cost[a] = cost;
+        best_pos[a] = pos;
+      }
+    }
+  }
+  int axis = 0;
+  double c = best_cost[0];
+  if (c > best_cost[1]) axis = 1, c = best_cost[1];
+  if (c > best_cost[2]) axis = 2, c = best_cost[2];
+  w.axis[s] = axis;
+  w.thresh[s] = best_pos[axis] * 3.0;
+}
+
+// ---- partition predicate + number of "left" triangles per segment --------------------------------------
+__global__ void __launch_bounds__(kThreads) k_pred(uint32_t n, uint32_t nt, const uint32_t *__restrict__ sid,
+                                                  const uint32_t *__restrict__ idx, const double *__restrict__ cs,
+                                                  SegWork w, uint8_t *__restrict__ pred) {
+  __shared__ uint32_t s_cnt[kThreads / 32];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t first = blockIdx.x * blockDim.x, last = min(first + blockDim.x, n) - 1;
+  const uint32_t s0 = sid[first];
+  const bool uniform = s0 != kNoSeg && s0 == sid[last];
+  const uint32_t s = i < n ? sid[i] : kNoSeg;
+  bool p = false;
+  if (s != kNoSeg && !w.leaf[s]) p = cs[(size_t)w.axis[s] * nt + idx[i]] < w.thresh[s];
+  if (i < n) pred[i] = p ? 1 : 0;
+  if (!uniform) {
+    if (p) atomicAdd(&w.ntrue[s], 1u);
+    return;
+  }
+  const unsigned b = __ballot_sync(0xFFFFFFFFu, p);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = __popc(b);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t c = 0;
+    for (int k = 0; k < kThreads / 32; k++) c += s_cnt[k];
+    if (c) atomicAdd(&w.ntrue[s0], c);
+  }
+}
+
+// misplaced flags: left part holds a "right" triangle / right part holds a "left" triangle
+__global__ void k_misplaced(uint32_t n, const uint32_t *__restrict__ sid, const uint32_t *__restrict__ sl,
+                            const uint8_t *__restrict__ pred, SegWork w, uint32_t *__restrict__ ml,
+                            uint32_t *__restrict__ mr) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t s = sid[i];
+  uint32_t a = 0, b = 0;
+  if (s != kNoSeg && !w.leaf[s]) {
+    const uint32_t mid = sl[s] + w.ntrue[s];
+    if (i < mid) a = pred[i] ? 0u : 1u;
+    else b = pred[i] ? 1u : 0u;
+  }
+  ml[i] = a, mr[i] = b;
+}
+
+// ---- exclusive scan of uint32 (three phases; out has n + 1 entries, out[n] = total) --------------------
+constexpr int kScanItems = 8; // per thread
+__global__ void __launch_bounds__(kThreads) k_scan_blocks(uint32_t n, const uint32_t *__restrict__ in,
+                                                         uint32_t *__restrict__ out, uint32_t *__restrict__ sums) {
+  __shared__ uint32_t s_w[kThreads / 32];
+  const uint32_t base = blockIdx.x * (kThreads * kScanItems) + threadIdx.x * kScanItems;
+  uint32_t v[kScanItems], t = 0;
+  for (int k = 0; k < kScanItems; k++) {
+    v[k] = (base + k < n) ? in[base + k] : 0u;
+    t += v[k];
+  }
+  uint32_t x = t; // inclusive scan of the per-thread totals
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+    if ((int)lane >= o) x += y;
+  }
+  if (lane == 31) s_w[warp] = x;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (unsigned k = 0; k < warp; k++) woff += s_w[k];
+  uint32_t run = woff + x - t;
+  for (int k = 0; k < kScanItems; k++) {
+    if (base + k < n) out[base + k] = run;
+    run += v[k];
+  }
+  if (threadIdx.x == kThreads - 1) sums[blockIdx.x] = woff + x;
+}
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t nblocks, uint32_t *sums, uint32_t *total) { // <<<1, 1024>>>
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_run;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_run = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < nblocks; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < nblocks ? sums[i] : 0u;
+    uint32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+      if ((int)lane >= o) x += y;
+    }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (unsigned k = 0; k < warp; k++) woff += s_w[k];
+    const uint32_t run = s_run;
+    if (i < nblocks) sums[i] = run + woff + x - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_run = run + woff + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = s_run;
+}
+__global__ void k_scan_add(uint32_t n, uint32_t *__restrict__ out, const uint32_t *__restrict__ sums,
+                           const uint32_t *__restrict__ total) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] += sums[i / (kThreads * kScanItems)];
+  if (i == 0) out[n] = *total;
+}
+
+// right-misplaced positions, compacted in position order
+__global__ void k_right_list(uint32_t n, const uint32_t *__restrict__ mr, const uint32_t *__restrict__ scan_r,
+                             uint32_t *__restrict__ rlist) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && mr[i]) rlist[scan_r[i]] = i;
+}
+
+// k-th misplaced from the left <-> k-th misplaced from the right (libstdc++ bidirectional __partition)
+__global__ void k_swap(uint32_t n, const uint32_t *__restrict__ sid, const uint32_t *__restrict__ sl,
+                       const uint32_t *__restrict__ sr, const uint32_t *__restrict__ ml,
+                       const uint32_t *__restrict__ scan_l, const uint32_t *__restrict__ scan_r,
+                       const uint32_t *__restrict__ rlist, uint32_t *idx) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !ml[i]) return;
+  const uint32_t s = sid[i];
+  const uint32_t k = scan_l[i] - scan_l[sl[s]];
+  const uint32_t m = scan_l[sr[s]] - scan_l[sl[s]]; // misplaced on either side of this segment
+  const uint32_t j = rlist[scan_r[sl[s]] + (m - 1u - k)];
+  const uint32_t a = idx[i], b = idx[j];
+  idx[i] = b, idx[j] = a;
+}
+
+// ---- nodes of this level + segments of the next --------------------------------------------------------
+struct NodeSoA {
+  double *bmin, *bmax;   // [cap * 3]
+  int32_t *flag, *axis;  // [cap]
+  uint32_t *d0, *d1;     // branch: child node slots; leaf: ntris, first index
+};
+
+__global__ void k_emit_level(uint32_t S, Segs cur, SegWork w, const uint32_t *__restrict__ branch_ord, uint32_t node_base,
+                             NodeSoA nodes, Segs next) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const uint32_t slot = cur.node[s], l = cur.l[s], r = cur.r[s], n = r - l;
+  for (int a = 0; a < 3; a++) nodes.bmin[3 * (size_t)slot + a] = w.bmin[3 * (size_t)s + a], nodes.bmax[3 * (size_t)slot + a] = w.bmax[3 * (size_t)s + a];
+  if (w.leaf[s]) {
+    nodes.flag[slot] = 1, nodes.axis[slot] = 0, nodes.d0[slot] = n, nodes.d1[slot] = l;
+    return;
+  }
+  uint32_t mid = l + w.ntrue[s];
+  if (mid == l || mid == r) mid = l + (n >> 1); // object-median fallback, array left as partitioned
+  const uint32_t o = branch_ord[s];
+  const uint32_t c0 = node_base + 2 * o, c1 = c0 + 1;
+  nodes.flag[slot] = 0, nodes.axis[slot] = w.axis[s], nodes.d0[slot] = c0, nodes.d1[slot] = c1;
+  next.l[2 * o] = l, next.r[2 * o] = mid, next.node[2 * o] = c0;
+  next.l[2 * o + 1] = mid, next.r[2 * o + 1] = r, next.node[2 * o + 1] = c1;
+}
+
+// ---- pre-order numbering ---------------------------------------------------------------------------------
+__global__ void k_sizes(uint32_t first, uint32_t count, NodeSoA nodes, uint32_t *size) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t s = first + i;
+  size[s] = nodes.flag[s] ? 1u : 1u + size[nodes.d0[s]] + size[nodes.d1[s]];
+}
+__global__ void k_numbers(uint32_t first, uint32_t count, NodeSoA nodes, const uint32_t *size, uint32_t *num) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t s = first + i;
+  if (nodes.flag[s]) return;
+  num[nodes.d0[s]] = num[s] + 1u;
+  num[nodes.d1[s]] = num[s] + 1u + size[nodes.d0[s]];
+}
+__global__ void k_emit_nodes(uint32_t count, NodeSoA nodes, const uint32_t *num, mb200_bvh_node *out) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= count) return;
+  mb200_bvh_node nd;
+  for (int a = 0; a < 3; a++) nd.bmin[a] = nodes.bmin[3 * (size_t)s + a], nd.bmax[a] = nodes.bmax[3 * (size_t)s + a];
+  nd.flag = nodes.flag[s];
+  nd.axis = nodes.axis[s];
+  if (nd.flag) nd.data[0] = nodes.d0[s], nd.data[1] = nodes.d1[s];
+  else nd.data[0] = num[nodes.d0[s]], nd.data[1] = num[nodes.d1[s]];
+  out[num[s]] = nd;
+}
+
+inline unsigned grid_for(size_t n, int block = kThreads) { return (unsigned)((n + block - 1) / block); }
+
+struct Pool { // device allocations released together
+  std::vector<void *> ptrs;
+  template <class T> cudaError_t get(T **p, size_t count) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, (count ? count : 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    ptrs.push_back(q);
+    *p = (T *)q;
+    return cudaSuccess;
+  }
+  ~Pool() {
+    for (void *p : ptrs) cudaFree(p);
+  }
+};
+
+cudaError_t scan_u32(uint32_t n, const uint32_t *in, uint32_t *out, uint32_t *sums, uint32_t *total, cudaStream_t s) {
+  const uint32_t per = kThreads * kScanItems, nblocks = (n + per - 1) / per;
+  if (n == 0) return cudaMemsetAsync(out, 0, sizeof(uint32_t), s);
+  k_scan_blocks<<<nblocks, kThreads, 0, s>>>(n, in, out, sums);
+  k_scan_sums<<<1, 1024, 0, s>>>(nblocks, sums, total);
+  k_scan_add<<<grid_for(n), kThreads, 0, s>>>(n, out, sums, total);
+  return cudaGetLastError();
+}
+
+cudaError_t build_device(HostBVH &out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
+                         size_t nfaces, const mb200_build_options &opt, int *launches) {
+  CUB(cudaSetDevice(device));
+  cudaStream_t s = nullptr; // default stream: a one-off set-up step
+  const uint32_t nt = (uint32_t)nfaces;
+  Pool pool;
+  double *d_v, *d_lo, *d_hi, *d_cs;
+  uint32_t *d_f, *d_idx, *d_sid, *d_ml, *d_mr, *d_scan_l, *d_scan_r, *d_rlist, *d_sums, *d_total, *d_counter, *d_ord;
+  uint8_t *d_pred;
+  CUB(pool.get(&d_v, 3 * nverts));
+  CUB(pool.get(&d_f, 3 * nfaces));
+  CUB(pool.get(&d_lo, 3 * nfaces));
+  CUB(pool.get(&d_hi, 3 * nfaces));
+  CUB(pool.get(&d_cs, 3 * nfaces));
+  CUB(pool.get(&d_idx, nfaces));
+  CUB(pool.get(&d_sid, nfaces));
+  CUB(pool.get(&d_ml, nfaces));
+  CUB(pool.get(&d_mr, nfaces));
+  CUB(pool.get(&d_scan_l, nfaces + 1));
+  CUB(pool.get(&d_scan_r, nfaces + 1));
+  CUB(pool.get(&d_rlist, nfaces));
+  CUB(pool.get(&d_pred, nfaces));
+  const size_t max_segs = nfaces + 2; // a level never has more segments than triangles
+  CUB(pool.get(&d_sums, max_segs / (kThreads * kScanItems) + 2));
+  CUB(pool.get(&d_total, 1));
+  CUB(pool.get(&d_counter, 1));
+  CUB(pool.get(&d_ord, max_segs + 1));
+  Segs seg[2];
+  for (int k = 0; k < 2; k++) {
+    CUB(pool.get(&seg[k].l, max_segs));
+    CUB(pool.get(&seg[k].r, max_segs));
+    CUB(pool.get(&seg[k].node, max_segs));
+  }
+  SegWork w;
+  CUB(pool.get(&w.kmin, 3 * max_segs));
+  CUB(pool.get(&w.kmax, 3 * max_segs));
+  CUB(pool.get(&w.bmin, 3 * max_segs));
+  CUB(pool.get(&w.bmax, 3 * max_segs));
+  CUB(pool.get(&w.scale, 3 * max_segs));
+  CUB(pool.get(&w.step, 3 * max_segs));
+  CUB(pool.get(&w.leaf, max_segs));
+  CUB(pool.get(&w.hslot, max_segs));
+  CUB(pool.get(&w.axis, max_segs));
+  CUB(pool.get(&w.thresh, max_segs));
+  CUB(pool.get(&w.ntrue, max_segs));
+  CUB(pool.get(&w.mid, max_segs));
+  CUB(pool.get(&w.isbranch, max_segs));
+  const size_t max_nodes = 2 * nfaces + 2;
+  NodeSoA nodes;
+  CUB(pool.get(&nodes.bmin, 3 * max_nodes));
+  CUB(pool.get(&nodes.bmax, 3 * max_nodes));
+  CUB(pool.get(&nodes.flag, max_nodes));
+  CUB(pool.get(&nodes.axis, max_nodes));
+  CUB(pool.get(&nodes.d0, max_nodes));
+  CUB(pool.get(&nodes.d1, max_nodes));
+  const int nb = opt.bin_size;
+  const size_t max_branch = nfaces / (size_t)(opt.min_leaf_primitives > 0 ? opt.min_leaf_primitives : 1) + 2;
+  uint32_t *d_hist;
+  CUB(pool.get(&d_hist, max_branch * 6 * (size_t)nb));
+
+  CUB(cudaMemcpyAsync(d_v, vertices, 3 * nverts * sizeof(double), cudaMemcpyHostToDevice, s));
+  CUB(cudaMemcpyAsync(d_f, faces, 3 * nfaces * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  k_tri_cache<<<grid_for(nt), kThreads, 0, s>>>(d_v, d_f, nt, d_lo, d_hi, d_cs, d_idx);
+  int nl = 1;
+
+  // level 0: one segment, node slot 0
+  const uint32_t zero = 0;
+  CUB(cudaMemcpyAsync(seg[0].l, &zero, 4, cudaMemcpyHostToDevice, s));
+  CUB(cudaMemcpyAsync(seg[0].r, &nt, 4, cudaMemcpyHostToDevice, s));
+  CUB(cudaMemcpyAsync(seg[0].node, &zero, 4, cudaMemcpyHostToDevice, s));
+  std::vector<uint32_t> level_first, level_count; // node slots of every level
+  uint32_t S = 1, node_count = 1;
+  int level = 0, cur = 0;
+  size_t leaves = 0, branches = 0;
+  while (S > 0) {
+    level_first.push_back(node_count - S);
+    level_count.push_back(S);
+    const Segs c = seg[cur], nx = seg[cur ^ 1];
+    k_assign_sid<<<grid_for(nt), kThreads, 0, s>>>(nt, c.l, c.r, S, d_sid);
+    k_init_keys<<<grid_for(3 * (size_t)S), kThreads, 0, s>>>(3 * S, w.kmin, w.kmax);
+    k_bounds<<<grid_for(nt), kThreads, 0, s>>>(nt, nt, d_sid, d_idx, d_lo, d_hi, w.kmin, w.kmax);
+    CUB(cudaMemsetAsync(d_counter, 0, 4, s));
+    k_seg_setup<<<grid_for(S), kThreads, 0, s>>>(S, c.l, c.r, level, opt, w, d_counter);
+    uint32_t nbranch = 0;
+    CUB(cudaMemcpyAsync(&nbranch, d_counter, 4, cudaMemcpyDeviceToHost, s));
+    CUB(cudaStreamSynchronize(s));
+    nl += 5;
+    if (nbranch > 0) {
+      if ((size_t)nbranch > max_branch) return cudaErrorInvalidValue;
+      CUB(cudaMemsetAsync(d_hist, 0, (size_t)nbranch * 6 * nb * sizeof(uint32_t), s));
+      const size_t hsm = (nb <= 512) ? 6 * (size_t)nb * sizeof(uint32_t) : 0;
+      k_histogram<<<grid_for(nt), kThreads, hsm, s>>>(nt, nt, nb, d_sid, d_idx, d_lo, d_hi, w, d_hist);
+      k_sweep<<<grid_for(S, 64), 64, 0, s>>>(S, c.l, c.r, opt, w, d_hist);
+      k_pred<<<grid_for(nt), kThreads, 0, s>>>(nt, nt, d_sid, d_idx, d_cs, w, d_pred);
+      k_misplaced<<<grid_for(nt), kThreads, 0, s>>>(nt, d_sid, c.l, d_pred, w, d_ml, d_mr);
+      CUB(scan_u32(nt, d_ml, d_scan_l, d_sums, d_total, s));
+      CUB(scan_u32(nt, d_mr, d_scan_r, d_sums, d_total, s));
+      k_right_list<<<grid_for(nt), kThreads, 0, s>>>(nt, d_mr, d_scan_r, d_rlist);
+      k_swap<<<grid_for(nt), kThreads, 0, s>>>(nt, d_sid, c.l, c.r, d_ml, d_scan_l, d_scan_r, d_rlist, d_idx);
+      nl += 12;
+    }
+    CUB(scan_u32(S, w.isbranch, d_ord, d_sums, d_total, s));
+    k_emit_level<<<grid_for(S), kThreads, 0, s>>>(S, c, w, d_ord, node_count, nodes, nx);
+    nl += 4;
+    CUB(cudaGetLastError());
+    leaves += S - nbranch;
+    branches += nbranch;
+    node_count += 2 * nbranch;
+    S = 2 * nbranch;
+    cur ^= 1;
+    level++;
+    if (level > 600) return cudaErrorInvalidValue; // max_tree_depth bounds this; defensive
+  }
+
+  // pre-order numbers: sizes bottom-up, numbers top-down (left child = parent + 1), then emit
+  uint32_t *d_size, *d_num;
+  mb200_bvh_node *d_out;
+  CUB(pool.get(&d_size, node_count));
+  CUB(pool.get(&d_num, node_count));
+  CUB(pool.get(&d_out, node_count));
+  for (int lv = (int)level_first.size() - 1; lv >= 0; lv--) {
+    k_sizes<<<grid_for(level_count[lv]), kThreads, 0, s>>>(level_first[lv], level_count[lv], nodes, d_size);
+    nl++;
+  }
+  CUB(cudaMemsetAsync(d_num, 0, sizeof(uint32_t), s));
+  for (size_t lv = 0; lv < level_first.size(); lv++) {
+    k_numbers<<<grid_for(level_count[lv]), kThreads, 0, s>>>(level_first[lv], level_count[lv], nodes, d_size, d_num);
+    nl++;
+  }
+  k_emit_nodes<<<grid_for(node_count), kThreads, 0, s>>>(node_count, nodes, d_num, d_out);
+  nl++;
+  CUB(cudaGetLastError());
+  out.nodes.resize(node_count);
+  out.indices.resize(nfaces);
+  CUB(cudaMemcpyAsync(out.nodes.data(), d_out, (size_t)node_count * sizeof(mb200_bvh_node), cudaMemcpyDeviceToHost, s));
+  CUB(cudaMemcpyAsync(out.indices.data(), d_idx, nfaces * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUB(cudaStreamSynchronize(s));
+  out.stats.max_tree_depth = (int)level_first.size() - 1;
+  out.stats.num_leaf_nodes = (int)leaves;
+  out.stats.num_branch_nodes = (int)branches;
+  if (launches) *launches = nl;
+  return cudaSuccess;
+}
+
+} // namespace
+
+// Entry used by the C ABI (mb200_bvh_build_device).  Validation as host/bvh_build.cc.
+bool build_bvh_device(HostBVH &out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
+                      size_t nfaces, const mb200_build_options &opt, std::string *err, bool *cuda_failure) {
+  if (cuda_failure) *cuda_failure = false;
+  out.nodes.clear();
+  out.indices.clear();
+  out.stats = mb200_build_stats{0, 0, 0};
+  if (opt.bin_size <= 1 || opt.bin_size > 65536) {
+    if (err) *err = "bin_size must be in (1, 65536]";
+    return false;
+  }
+  if (opt.min_leaf_primitives < 2) {
+    if (err) *err = "the device builder needs min_leaf_primitives >= 2 (use mb200_bvh_build)";
+    return false;
+  }
+  if (nfaces > 0x7FFFFFF0ull) {
+    if (err) *err = "too many triangles for the device builder";
+    return false;
+  }
+  for (size_t i = 0; i < 3 * nfaces; i++)
+    if (faces[i] >= nverts) {
+      if (err) *err = "face references a vertex out of range";
+      return false;
+    }
+  if (nfaces == 0) return true; // empty tree: every ray misses
+  int launches = 0;
+  const cudaError_t e = build_device(out, device, vertices, nverts, faces, nfaces, opt, &launches);
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("device BVH build: ") + cudaGetErrorString(e);
+    if (cuda_failure) *cuda_failure = true;
+    out.nodes.clear();
+    out.indices.clear();
+    cudaGetLastError();
+    return false;
+  }
+  return true;
+}
+
+} // namespace mb200

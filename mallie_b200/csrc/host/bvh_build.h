@@ -18,6 +18,10 @@ struct HostBVH {
 
 bool build_bvh(HostBVH &out, const double *vertices, size_t nverts, const uint32_t *faces, size_t nfaces,
                const mb200_build_options &opt, std::string *err);
+// Same tree, grown level by level on the GPU (device/bvh_build_gpu.cu).  *cuda_failure tells a CUDA error from
+// a rejected argument.
+bool build_bvh_device(HostBVH &out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
+                      size_t nfaces, const mb200_build_options &opt, std::string *err, bool *cuda_failure);
 bool dump_bvh(const HostBVH &bvh, const char *path, std::string *err);
 bool load_bvh(HostBVH &out, const char *path, std::string *err);
 
