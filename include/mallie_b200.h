@@ -206,6 +206,16 @@ int mb200_config_load(mb200_config *cfg, const char *path, const char *json_text
 int mb200_scene_create(mb200_scene **out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
                        size_t nfaces, const uint32_t *material_ids, const double *fv_normals, const double *fv_uvs,
                        const mb200_bvh_node *nodes, size_t nnodes, const uint32_t *indices, size_t nindices);
+/* BVHAccel::Build (bvh_accel.cc:445) and the scene upload in one step, entirely on GPU `device`: the tree is grown
+ * there (as mb200_bvh_build_device) and the traversal layout is written from it on the device; only the mesh is
+ * uploaded.  The scene equals mb200_scene_create(mb200_bvh_build(...)) byte for byte.  bvh_out (may be NULL)
+ * receives the reference-layout tree (for BVHAccel::GetNodes / Dump or replicas on other GPUs). */
+int mb200_scene_build(mb200_scene **out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
+                      size_t nfaces, const uint32_t *material_ids, const double *fv_normals, const double *fv_uvs,
+                      const mb200_build_options *opt /* NULL = defaults */, mb200_bvh **bvh_out);
+/* The traversal layout resident on the device (same meaning and sizes as mb200_bvh_device_layout): for checking
+ * a device-built scene against a host-built one.  The output pointers may be NULL (sizes only). */
+int mb200_scene_layout(mb200_scene *scene, mb200_layout_info *info, void *pair_nodes_out, void *tri_records_out);
 void mb200_scene_destroy(mb200_scene *scene);
 /* Scene::BoundingBox (scene.cc:317-333): root node bounds. */
 int mb200_scene_bounds(const mb200_scene *scene, double bmin[3], double bmax[3]);

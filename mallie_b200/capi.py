@@ -30,7 +30,7 @@ CAMERA_PINHOLE, CAMERA_ENV, CAMERA_ENV_STEREO = 0, 1, 2
 # Every symbol include/mallie_b200.h declares (tests/test_abi.py checks the header against this list).
 EXPORTS = [
     "mb200_last_error", "mb200_version", "mb200_device_count", "mb200_launches_issued",
-    "mb200_build_options_default", "mb200_bvh_build", "mb200_bvh_build_device", "mb200_bvh_load", "mb200_bvh_dump",
+    "mb200_build_options_default", "mb200_bvh_build", "mb200_bvh_build_device", "mb200_scene_build", "mb200_scene_layout", "mb200_bvh_load", "mb200_bvh_dump",
     "mb200_bvh_num_nodes", "mb200_bvh_num_indices", "mb200_bvh_nodes", "mb200_bvh_indices",
     "mb200_bvh_stats", "mb200_bvh_destroy",
     "mb200_bvh_device_layout",
@@ -143,6 +143,8 @@ def lib():
         L.mb200_build_options_default.argtypes = [C.POINTER(BuildOptions)]
         L.mb200_bvh_build.argtypes = [C.POINTER(vp), vp, sz, vp, sz, C.POINTER(BuildOptions)]
         L.mb200_bvh_build_device.argtypes = [C.POINTER(vp), C.c_int, vp, sz, vp, sz, C.POINTER(BuildOptions)]
+        L.mb200_scene_build.argtypes = [C.POINTER(vp), C.c_int, vp, sz, vp, sz, vp, vp, vp, C.POINTER(BuildOptions), C.POINTER(vp)]
+        L.mb200_scene_layout.argtypes = [vp, C.POINTER(LayoutInfo), vp, vp]
         L.mb200_bvh_load.argtypes = [C.POINTER(vp), C.c_char_p]
         L.mb200_bvh_dump.argtypes = [vp, C.c_char_p]
         L.mb200_bvh_num_nodes.restype = sz
@@ -386,6 +388,41 @@ class Scene:
                                        self.faces.shape[0], _p(m), _p(n), _p(t), _p(self.nodes),
                                        self.nodes.shape[0], _p(self.indices), self.indices.shape[0]))
         self.h = h
+
+    @classmethod
+    def build(cls, vertices, faces, material_ids=None, normals=None, uvs=None, device=0, want_bvh=True,
+              cost_taabb=0.2, min_leaf=16, max_depth=256, bin_size=64):
+        """mb200_scene_build: BVH build + traversal layout entirely on the GPU.  With want_bvh the reference-layout
+        tree is downloaded too (self.nodes / self.indices)."""
+        self = cls.__new__(cls)
+        self.h = None
+        self.vertices = np.ascontiguousarray(vertices, np.float64).reshape(-1, 3)
+        self.faces = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
+        m = None if material_ids is None else np.ascontiguousarray(material_ids, np.uint32)
+        n = None if normals is None else np.ascontiguousarray(normals, np.float64).reshape(-1)
+        t = None if uvs is None else np.ascontiguousarray(uvs, np.float64).reshape(-1)
+        opt = BuildOptions(cost_taabb, min_leaf, max_depth, bin_size)
+        h, b = C.c_void_p(), C.c_void_p()
+        check(lib().mb200_scene_build(C.byref(h), device, _p(self.vertices), self.vertices.shape[0], _p(self.faces),
+                                      self.faces.shape[0], _p(m), _p(n), _p(t), C.byref(opt),
+                                      C.byref(b) if want_bvh else None))
+        self.h = h
+        self.nodes = self.indices = None
+        if want_bvh:
+            bvh = HostBVH(b)
+            self.nodes, self.indices = bvh.arrays()
+            self.build_stats = bvh.stats()
+            bvh.close()
+        return self
+
+    def layout(self):
+        """mb200_scene_layout: (info dict, pair nodes, triangle records) as resident on the device."""
+        info = LayoutInfo()
+        check(lib().mb200_scene_layout(self.h, C.byref(info), None, None))
+        pairs = np.zeros(info.num_pair_nodes, PAIR_DTYPE)
+        tris = np.zeros(info.num_tri_records, TRI32_DTYPE if info.tri_record_bytes == 48 else TRI64_DTYPE)
+        check(lib().mb200_scene_layout(self.h, C.byref(info), _p(pairs), _p(tris)))
+        return {k: int(getattr(info, k)) for k, _ in info._fields_}, pairs, tris
 
     def close(self):
         if self.h:

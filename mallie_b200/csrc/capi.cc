@@ -315,6 +315,48 @@ int mb200_scene_create(mb200_scene **out, int device, const double *vertices, si
   return MB200_OK;
 }
 
+int mb200_scene_build(mb200_scene **out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
+                      size_t nfaces, const uint32_t *material_ids, const double *fv_normals, const double *fv_uvs,
+                      const mb200_build_options *opt, mb200_bvh **bvh_out) {
+  if (!out) return set_err(MB200_ERR_INVALID_ARG, "out is null");
+  *out = nullptr;
+  if (bvh_out) *bvh_out = nullptr;
+  if ((nfaces && (!vertices || !faces))) return set_err(MB200_ERR_INVALID_ARG, "null mesh array");
+  mb200_build_options o;
+  mb200_build_options_default(&o);
+  if (opt) o = *opt;
+  mb200_bvh *b = bvh_out ? new mb200_bvh : nullptr;
+  std::string err;
+  const int rc = mb200::scene_build_device(out, device, vertices, nverts, faces, nfaces, material_ids, fv_normals, fv_uvs,
+                                           o, b ? &b->bvh : nullptr, &err);
+  if (rc != MB200_OK) {
+    delete b;
+    return set_err(rc, err);
+  }
+  if (bvh_out) *bvh_out = b;
+  return MB200_OK;
+}
+
+int mb200_scene_layout(mb200_scene *scene, mb200_layout_info *info, void *pair_nodes_out, void *tri_records_out) {
+  if (!scene || !info) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  const mb200::SceneView &v = scene->view;
+  memset(info, 0, sizeof(*info));
+  info->num_pair_nodes = v.num_pair_nodes;
+  info->num_tri_records = v.num_tris;
+  info->tri_record_bytes = v.tri_f32 ? (uint32_t)sizeof(mb200::TriRecordF32) : (uint32_t)sizeof(mb200::TriRecordF64);
+  info->root_ref = v.root_ref, info->root_cnt = v.root_cnt;
+  info->depth = scene->tree_depth, info->empty = v.empty;
+  if (v.empty || (!pair_nodes_out && !tri_records_out)) return MB200_OK;
+  cudaError_t e = cudaSetDevice(scene->device);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(scene->stream);
+  if (e == cudaSuccess && pair_nodes_out && v.num_pair_nodes)
+    e = cudaMemcpy(pair_nodes_out, v.nodes, (size_t)v.num_pair_nodes * sizeof(mb200::PairNode), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && tri_records_out && v.num_tris)
+    e = cudaMemcpy(tri_records_out, v.tris, (size_t)v.num_tris * info->tri_record_bytes, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return set_err(MB200_ERR_CUDA, std::string("scene layout download: ") + cudaGetErrorString(e));
+  return MB200_OK;
+}
+
 void mb200_scene_destroy(mb200_scene *scene) { mb200::scene_destroy(scene); }
 
 int mb200_scene_bounds(const mb200_scene *scene, double bmin[3], double bmax[3]) {

@@ -25,13 +25,18 @@
 #include <cuda_runtime.h>
 
 #include <cfloat>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../host/bvh_build.h"
+#include "layout.h"
 #include "mallie_b200.h"
+#include "scene.h"
 
 namespace mb200 {
 
@@ -71,7 +76,6 @@ struct SegWork { // per segment, per level
   int32_t *axis;            // [S]
   double *thresh;           // [S] 3 * cut position
   uint32_t *ntrue;          // [S]
-  uint32_t *mid;            // [S]
   uint32_t *isbranch;       // [S] 0 / 1 (scanned into child ordinals)
 };
 
@@ -438,21 +442,76 @@ __global__ void k_emit_nodes(uint32_t count, NodeSoA nodes, const uint32_t *num,
   out[num[s]] = nd;
 }
 
+// ---- device layout straight from the device tree (what scene.cc::relayout_bvh does on the host) --------
+__global__ void k_branch_flags(uint32_t count, const mb200_bvh_node *__restrict__ nodes, uint32_t *__restrict__ flag) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) flag[i] = nodes[i].flag == 0 ? 1u : 0u;
+}
+// pair_of[i] = number of branch nodes before node i in pre-order: relayout_bvh's numbering
+__global__ void k_emit_pairs(uint32_t count, const mb200_bvh_node *__restrict__ nodes, const uint32_t *__restrict__ pair_of,
+                             PairNode *__restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count || nodes[i].flag != 0) return;
+  PairNode p;
+  for (int c = 0; c < 2; c++) {
+    const uint32_t ci = nodes[i].data[c];
+    const mb200_bvh_node ch = nodes[ci];
+    for (int k = 0; k < 3; k++) p.box[c][k] = ch.bmin[k], p.box[c][3 + k] = ch.bmax[k];
+    if (ch.flag == 0) p.ref[c] = pair_of[ci], p.cnt[c] = kBranch;
+    else p.ref[c] = ch.data[1], p.cnt[c] = ch.data[0];
+  }
+  p.axis = (uint32_t)nodes[i].axis;
+  p.pad_[0] = p.pad_[1] = p.pad_[2] = 0u;
+  out[pair_of[i]] = p;
+}
+__global__ void k_emit_tris32(uint32_t nt, const uint32_t *__restrict__ idx, const double *__restrict__ v,
+                              const uint32_t *__restrict__ f, const uint32_t *__restrict__ mat, TriRecordF32 *__restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nt) return;
+  const uint32_t t = idx[i];
+  const double *a = v + 3 * (size_t)f[3 * (size_t)t + 0], *b = v + 3 * (size_t)f[3 * (size_t)t + 1], *c = v + 3 * (size_t)f[3 * (size_t)t + 2];
+  TriRecordF32 r;
+  for (int k = 0; k < 3; k++) r.p0[k] = (float)a[k], r.p1[k] = (float)b[k], r.p2[k] = (float)c[k];
+  r.face = t;
+  r.mat = mat ? mat[t] : 0xFFFFFFFFu; // bvh_accel.cc:685-689
+  r.pad_ = 0u;
+  out[i] = r;
+}
+__global__ void k_emit_tris64(uint32_t nt, const uint32_t *__restrict__ idx, const double *__restrict__ v,
+                              const uint32_t *__restrict__ f, const uint32_t *__restrict__ mat, TriRecordF64 *__restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nt) return;
+  const uint32_t t = idx[i];
+  const double *a = v + 3 * (size_t)f[3 * (size_t)t + 0], *b = v + 3 * (size_t)f[3 * (size_t)t + 1], *c = v + 3 * (size_t)f[3 * (size_t)t + 2];
+  TriRecordF64 r;
+  for (int k = 0; k < 3; k++) r.p0[k] = a[k], r.e1[k] = b[k] - a[k], r.e2[k] = c[k] - a[k]; // bvh_accel.cc:600-603
+  r.face = t;
+  r.mat = mat ? mat[t] : 0xFFFFFFFFu;
+  out[i] = r;
+}
+
 inline unsigned grid_for(size_t n, int block = kThreads) { return (unsigned)((n + block - 1) / block); }
 
-struct Pool { // device allocations released together
-  std::vector<void *> ptrs;
-  template <class T> cudaError_t get(T **p, size_t count) {
-    void *q = nullptr;
-    cudaError_t e = cudaMalloc(&q, (count ? count : 1) * sizeof(T));
-    if (e != cudaSuccess) return e;
-    ptrs.push_back(q);
-    *p = (T *)q;
-    return cudaSuccess;
+// One cudaMalloc carved into 256-byte aligned pieces.  The carving code runs twice: first to measure
+// (base == nullptr), then for real.
+struct Arena {
+  char *base = nullptr;
+  size_t used = 0;
+  template <class T> void get(T **p, size_t count) {
+    const size_t bytes = ((count ? count : 1) * sizeof(T) + 255) & ~(size_t)255;
+    *p = base ? reinterpret_cast<T *>(base + used) : nullptr;
+    used += bytes;
   }
-  ~Pool() {
-    for (void *p : ptrs) cudaFree(p);
+  cudaError_t commit() {
+    const size_t total = used;
+    used = 0;
+    return cudaMalloc((void **)&base, total ? total : 256);
   }
+  void release() {
+    if (base) cudaFree(base);
+    base = nullptr;
+  }
+  ~Arena() { release(); }
 };
 
 cudaError_t scan_u32(uint32_t n, const uint32_t *in, uint32_t *out, uint32_t *sums, uint32_t *total, cudaStream_t s) {
@@ -464,70 +523,100 @@ cudaError_t scan_u32(uint32_t n, const uint32_t *in, uint32_t *out, uint32_t *su
   return cudaGetLastError();
 }
 
-cudaError_t build_device(HostBVH &out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
-                         size_t nfaces, const mb200_build_options &opt, int *launches) {
-  CUB(cudaSetDevice(device));
-  cudaStream_t s = nullptr; // default stream: a one-off set-up step
-  const uint32_t nt = (uint32_t)nfaces;
-  Pool pool;
-  double *d_v, *d_lo, *d_hi, *d_cs;
-  uint32_t *d_f, *d_idx, *d_sid, *d_ml, *d_mr, *d_scan_l, *d_scan_r, *d_rlist, *d_sums, *d_total, *d_counter, *d_ord;
-  uint8_t *d_pred;
-  CUB(pool.get(&d_v, 3 * nverts));
-  CUB(pool.get(&d_f, 3 * nfaces));
-  CUB(pool.get(&d_lo, 3 * nfaces));
-  CUB(pool.get(&d_hi, 3 * nfaces));
-  CUB(pool.get(&d_cs, 3 * nfaces));
-  CUB(pool.get(&d_idx, nfaces));
-  CUB(pool.get(&d_sid, nfaces));
-  CUB(pool.get(&d_ml, nfaces));
-  CUB(pool.get(&d_mr, nfaces));
-  CUB(pool.get(&d_scan_l, nfaces + 1));
-  CUB(pool.get(&d_scan_r, nfaces + 1));
-  CUB(pool.get(&d_rlist, nfaces));
-  CUB(pool.get(&d_pred, nfaces));
-  const size_t max_segs = nfaces + 2; // a level never has more segments than triangles
-  CUB(pool.get(&d_sums, max_segs / (kThreads * kScanItems) + 2));
-  CUB(pool.get(&d_total, 1));
-  CUB(pool.get(&d_counter, 1));
-  CUB(pool.get(&d_ord, max_segs + 1));
-  Segs seg[2];
-  for (int k = 0; k < 2; k++) {
-    CUB(pool.get(&seg[k].l, max_segs));
-    CUB(pool.get(&seg[k].r, max_segs));
-    CUB(pool.get(&seg[k].node, max_segs));
+struct StageClock { // MB200_BUILD_TIMING=1: stage times on stderr (adds a synchronise per stage)
+  bool on;
+  cudaStream_t s;
+  std::chrono::steady_clock::time_point prev;
+  explicit StageClock(cudaStream_t st) : s(st) {
+    const char *e = getenv("MB200_BUILD_TIMING");
+    on = e && atoi(e) != 0;
+    prev = std::chrono::steady_clock::now();
   }
-  SegWork w;
-  CUB(pool.get(&w.kmin, 3 * max_segs));
-  CUB(pool.get(&w.kmax, 3 * max_segs));
-  CUB(pool.get(&w.bmin, 3 * max_segs));
-  CUB(pool.get(&w.bmax, 3 * max_segs));
-  CUB(pool.get(&w.scale, 3 * max_segs));
-  CUB(pool.get(&w.step, 3 * max_segs));
-  CUB(pool.get(&w.leaf, max_segs));
-  CUB(pool.get(&w.hslot, max_segs));
-  CUB(pool.get(&w.axis, max_segs));
-  CUB(pool.get(&w.thresh, max_segs));
-  CUB(pool.get(&w.ntrue, max_segs));
-  CUB(pool.get(&w.mid, max_segs));
-  CUB(pool.get(&w.isbranch, max_segs));
-  const size_t max_nodes = 2 * nfaces + 2;
-  NodeSoA nodes;
-  CUB(pool.get(&nodes.bmin, 3 * max_nodes));
-  CUB(pool.get(&nodes.bmax, 3 * max_nodes));
-  CUB(pool.get(&nodes.flag, max_nodes));
-  CUB(pool.get(&nodes.axis, max_nodes));
-  CUB(pool.get(&nodes.d0, max_nodes));
-  CUB(pool.get(&nodes.d1, max_nodes));
-  const int nb = opt.bin_size;
-  const size_t max_branch = nfaces / (size_t)(opt.min_leaf_primitives > 0 ? opt.min_leaf_primitives : 1) + 2;
-  uint32_t *d_hist;
-  CUB(pool.get(&d_hist, max_branch * 6 * (size_t)nb));
+  void operator()(const char *name) {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[mb200 build] %-10s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(now - prev).count());
+    prev = now;
+  }
+};
 
-  CUB(cudaMemcpyAsync(d_v, vertices, 3 * nverts * sizeof(double), cudaMemcpyHostToDevice, s));
-  CUB(cudaMemcpyAsync(d_f, faces, 3 * nfaces * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-  k_tri_cache<<<grid_for(nt), kThreads, 0, s>>>(d_v, d_f, nt, d_lo, d_hi, d_cs, d_idx);
+// The tree on the device, reference layout: nodes in pre-order + the permuted index array, with the mesh arrays
+// the build uploaded.  Lives until the arenas go.
+struct DeviceTree {
+  Arena work, result;
+  double *d_v = nullptr;
+  uint32_t *d_f = nullptr, *d_idx = nullptr;
+  mb200_bvh_node *d_nodes = nullptr;
+  uint32_t *d_scratch = nullptr, *d_scan = nullptr, *d_sums = nullptr, *d_total = nullptr; // node_count(+1) each
+  uint32_t node_count = 0;
+  mb200_build_stats stats{0, 0, 0};
+  int launches = 0;
+};
+
+cudaError_t build_tree(DeviceTree &T, cudaStream_t s, const double *vertices, size_t nverts, const uint32_t *faces,
+                       size_t nfaces, const mb200_build_options &opt, StageClock &stage) {
+  const uint32_t nt = (uint32_t)nfaces;
+  const int nb = opt.bin_size;
+  // siblings together hold >= min_leaf_primitives triangles, so a level has at most 2 * nfaces / min_leaf segments
+  const size_t max_segs = 2 * (nfaces / (size_t)opt.min_leaf_primitives) + 4;
+  const size_t max_branch = nfaces / (size_t)opt.min_leaf_primitives + 2;
+  const size_t max_nodes = 2 * nfaces + 2;
+  double *d_lo, *d_hi, *d_cs;
+  uint32_t *d_sid, *d_ml, *d_mr, *d_scan_l, *d_scan_r, *d_rlist, *d_sums, *d_total, *d_counter, *d_ord, *d_hist;
+  uint8_t *d_pred;
+  Segs seg[2];
+  SegWork w;
+  NodeSoA nodes;
+  auto carve = [&](Arena &A) {
+    A.get(&T.d_v, 3 * nverts);
+    A.get(&T.d_f, 3 * nfaces);
+    A.get(&T.d_idx, nfaces);
+    A.get(&d_lo, 3 * nfaces);
+    A.get(&d_hi, 3 * nfaces);
+    A.get(&d_cs, 3 * nfaces);
+    A.get(&d_sid, nfaces);
+    A.get(&d_ml, nfaces);
+    A.get(&d_mr, nfaces);
+    A.get(&d_scan_l, nfaces + 1);
+    A.get(&d_scan_r, nfaces + 1);
+    A.get(&d_rlist, nfaces);
+    A.get(&d_pred, nfaces);
+    A.get(&d_sums, nfaces / (kThreads * kScanItems) + 2);
+    A.get(&d_total, 1);
+    A.get(&d_counter, 1);
+    A.get(&d_ord, max_segs + 1);
+    for (int k = 0; k < 2; k++) A.get(&seg[k].l, max_segs), A.get(&seg[k].r, max_segs), A.get(&seg[k].node, max_segs);
+    A.get(&w.kmin, 3 * max_segs);
+    A.get(&w.kmax, 3 * max_segs);
+    A.get(&w.bmin, 3 * max_segs);
+    A.get(&w.bmax, 3 * max_segs);
+    A.get(&w.scale, 3 * max_segs);
+    A.get(&w.step, 3 * max_segs);
+    A.get(&w.leaf, max_segs);
+    A.get(&w.hslot, max_segs);
+    A.get(&w.axis, max_segs);
+    A.get(&w.thresh, max_segs);
+    A.get(&w.ntrue, max_segs);
+    A.get(&w.isbranch, max_segs);
+    A.get(&nodes.bmin, 3 * max_nodes);
+    A.get(&nodes.bmax, 3 * max_nodes);
+    A.get(&nodes.flag, max_nodes);
+    A.get(&nodes.axis, max_nodes);
+    A.get(&nodes.d0, max_nodes);
+    A.get(&nodes.d1, max_nodes);
+    A.get(&d_hist, max_branch * 6 * (size_t)nb);
+  };
+  carve(T.work);
+  CUB(T.work.commit());
+  carve(T.work);
+  stage("alloc");
+
+  CUB(cudaMemcpyAsync(T.d_v, vertices, 3 * nverts * sizeof(double), cudaMemcpyHostToDevice, s));
+  CUB(cudaMemcpyAsync(T.d_f, faces, 3 * nfaces * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  k_tri_cache<<<grid_for(nt), kThreads, 0, s>>>(T.d_v, T.d_f, nt, d_lo, d_hi, d_cs, T.d_idx);
   int nl = 1;
+  stage("upload");
 
   // level 0: one segment, node slot 0
   const uint32_t zero = 0;
@@ -539,12 +628,13 @@ cudaError_t build_device(HostBVH &out, int device, const double *vertices, size_
   int level = 0, cur = 0;
   size_t leaves = 0, branches = 0;
   while (S > 0) {
+    if ((size_t)S > max_segs) return cudaErrorInvalidValue;
     level_first.push_back(node_count - S);
     level_count.push_back(S);
     const Segs c = seg[cur], nx = seg[cur ^ 1];
     k_assign_sid<<<grid_for(nt), kThreads, 0, s>>>(nt, c.l, c.r, S, d_sid);
     k_init_keys<<<grid_for(3 * (size_t)S), kThreads, 0, s>>>(3 * S, w.kmin, w.kmax);
-    k_bounds<<<grid_for(nt), kThreads, 0, s>>>(nt, nt, d_sid, d_idx, d_lo, d_hi, w.kmin, w.kmax);
+    k_bounds<<<grid_for(nt), kThreads, 0, s>>>(nt, nt, d_sid, T.d_idx, d_lo, d_hi, w.kmin, w.kmax);
     CUB(cudaMemsetAsync(d_counter, 0, 4, s));
     k_seg_setup<<<grid_for(S), kThreads, 0, s>>>(S, c.l, c.r, level, opt, w, d_counter);
     uint32_t nbranch = 0;
@@ -555,14 +645,14 @@ cudaError_t build_device(HostBVH &out, int device, const double *vertices, size_
       if ((size_t)nbranch > max_branch) return cudaErrorInvalidValue;
       CUB(cudaMemsetAsync(d_hist, 0, (size_t)nbranch * 6 * nb * sizeof(uint32_t), s));
       const size_t hsm = (nb <= 512) ? 6 * (size_t)nb * sizeof(uint32_t) : 0;
-      k_histogram<<<grid_for(nt), kThreads, hsm, s>>>(nt, nt, nb, d_sid, d_idx, d_lo, d_hi, w, d_hist);
+      k_histogram<<<grid_for(nt), kThreads, hsm, s>>>(nt, nt, nb, d_sid, T.d_idx, d_lo, d_hi, w, d_hist);
       k_sweep<<<grid_for(S, 64), 64, 0, s>>>(S, c.l, c.r, opt, w, d_hist);
-      k_pred<<<grid_for(nt), kThreads, 0, s>>>(nt, nt, d_sid, d_idx, d_cs, w, d_pred);
+      k_pred<<<grid_for(nt), kThreads, 0, s>>>(nt, nt, d_sid, T.d_idx, d_cs, w, d_pred);
       k_misplaced<<<grid_for(nt), kThreads, 0, s>>>(nt, d_sid, c.l, d_pred, w, d_ml, d_mr);
       CUB(scan_u32(nt, d_ml, d_scan_l, d_sums, d_total, s));
       CUB(scan_u32(nt, d_mr, d_scan_r, d_sums, d_total, s));
       k_right_list<<<grid_for(nt), kThreads, 0, s>>>(nt, d_mr, d_scan_r, d_rlist);
-      k_swap<<<grid_for(nt), kThreads, 0, s>>>(nt, d_sid, c.l, c.r, d_ml, d_scan_l, d_scan_r, d_rlist, d_idx);
+      k_swap<<<grid_for(nt), kThreads, 0, s>>>(nt, d_sid, c.l, c.r, d_ml, d_scan_l, d_scan_r, d_rlist, T.d_idx);
       nl += 12;
     }
     CUB(scan_u32(S, w.isbranch, d_ord, d_sums, d_total, s));
@@ -577,13 +667,22 @@ cudaError_t build_device(HostBVH &out, int device, const double *vertices, size_
     level++;
     if (level > 600) return cudaErrorInvalidValue; // max_tree_depth bounds this; defensive
   }
+  stage("levels");
 
   // pre-order numbers: sizes bottom-up, numbers top-down (left child = parent + 1), then emit
   uint32_t *d_size, *d_num;
-  mb200_bvh_node *d_out;
-  CUB(pool.get(&d_size, node_count));
-  CUB(pool.get(&d_num, node_count));
-  CUB(pool.get(&d_out, node_count));
+  auto carve2 = [&](Arena &A) {
+    A.get(&T.d_nodes, node_count);
+    A.get(&d_size, node_count);
+    A.get(&d_num, node_count);
+    A.get(&T.d_scan, (size_t)node_count + 1);
+    A.get(&T.d_sums, node_count / (kThreads * kScanItems) + 2);
+    A.get(&T.d_total, 1);
+  };
+  carve2(T.result);
+  CUB(T.result.commit());
+  carve2(T.result);
+  T.d_scratch = d_size; // free again once the numbers are out
   for (int lv = (int)level_first.size() - 1; lv >= 0; lv--) {
     k_sizes<<<grid_for(level_count[lv]), kThreads, 0, s>>>(level_first[lv], level_count[lv], nodes, d_size);
     nl++;
@@ -593,30 +692,29 @@ cudaError_t build_device(HostBVH &out, int device, const double *vertices, size_
     k_numbers<<<grid_for(level_count[lv]), kThreads, 0, s>>>(level_first[lv], level_count[lv], nodes, d_size, d_num);
     nl++;
   }
-  k_emit_nodes<<<grid_for(node_count), kThreads, 0, s>>>(node_count, nodes, d_num, d_out);
+  k_emit_nodes<<<grid_for(node_count), kThreads, 0, s>>>(node_count, nodes, d_num, T.d_nodes);
   nl++;
   CUB(cudaGetLastError());
-  out.nodes.resize(node_count);
-  out.indices.resize(nfaces);
-  CUB(cudaMemcpyAsync(out.nodes.data(), d_out, (size_t)node_count * sizeof(mb200_bvh_node), cudaMemcpyDeviceToHost, s));
-  CUB(cudaMemcpyAsync(out.indices.data(), d_idx, nfaces * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  CUB(cudaStreamSynchronize(s));
-  out.stats.max_tree_depth = (int)level_first.size() - 1;
-  out.stats.num_leaf_nodes = (int)leaves;
-  out.stats.num_branch_nodes = (int)branches;
-  if (launches) *launches = nl;
+  stage("numbering");
+  T.node_count = node_count;
+  T.stats.max_tree_depth = (int)level_first.size() - 1;
+  T.stats.num_leaf_nodes = (int)leaves;
+  T.stats.num_branch_nodes = (int)branches;
+  T.launches = nl;
   return cudaSuccess;
 }
 
-} // namespace
+cudaError_t download_tree(const DeviceTree &T, HostBVH &out, size_t nfaces, cudaStream_t s) {
+  out.nodes.resize(T.node_count);
+  out.indices.resize(nfaces);
+  CUB(cudaMemcpyAsync(out.nodes.data(), T.d_nodes, (size_t)T.node_count * sizeof(mb200_bvh_node), cudaMemcpyDeviceToHost, s));
+  CUB(cudaMemcpyAsync(out.indices.data(), T.d_idx, nfaces * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUB(cudaStreamSynchronize(s));
+  out.stats = T.stats;
+  return cudaSuccess;
+}
 
-// Entry used by the C ABI (mb200_bvh_build_device).  Validation as host/bvh_build.cc.
-bool build_bvh_device(HostBVH &out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
-                      size_t nfaces, const mb200_build_options &opt, std::string *err, bool *cuda_failure) {
-  if (cuda_failure) *cuda_failure = false;
-  out.nodes.clear();
-  out.indices.clear();
-  out.stats = mb200_build_stats{0, 0, 0};
+bool check_build_args(const uint32_t *faces, size_t nverts, size_t nfaces, const mb200_build_options &opt, std::string *err) {
   if (opt.bin_size <= 1 || opt.bin_size > 65536) {
     if (err) *err = "bin_size must be in (1, 65536]";
     return false;
@@ -629,14 +727,36 @@ bool build_bvh_device(HostBVH &out, int device, const double *vertices, size_t n
     if (err) *err = "too many triangles for the device builder";
     return false;
   }
-  for (size_t i = 0; i < 3 * nfaces; i++)
-    if (faces[i] >= nverts) {
-      if (err) *err = "face references a vertex out of range";
-      return false;
-    }
+  bool ok = true;
+#pragma omp parallel for schedule(static) reduction(&& : ok)
+  for (long i = 0; i < (long)(3 * nfaces); i++) ok = ok && faces[i] < nverts;
+  if (!ok && err) *err = "face references a vertex out of range";
+  return ok;
+}
+
+} // namespace
+
+// Entry used by the C ABI (mb200_bvh_build_device).  Validation as host/bvh_build.cc.
+bool build_bvh_device(HostBVH &out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
+                      size_t nfaces, const mb200_build_options &opt, std::string *err, bool *cuda_failure) {
+  if (cuda_failure) *cuda_failure = false;
+  out.nodes.clear();
+  out.indices.clear();
+  out.stats = mb200_build_stats{0, 0, 0};
+  if (!check_build_args(faces, nverts, nfaces, opt, err)) return false;
   if (nfaces == 0) return true; // empty tree: every ray misses
-  int launches = 0;
-  const cudaError_t e = build_device(out, device, vertices, nverts, faces, nfaces, opt, &launches);
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) {
+    cudaStream_t s = nullptr; // default stream: a one-off set-up step
+    StageClock stage(s);
+    DeviceTree T;
+    e = build_tree(T, s, vertices, nverts, faces, nfaces, opt, stage);
+    if (e == cudaSuccess) e = download_tree(T, out, nfaces, s);
+    stage("download");
+    T.work.release();
+    T.result.release();
+    stage("free");
+  }
   if (e != cudaSuccess) {
     if (err) *err = std::string("device BVH build: ") + cudaGetErrorString(e);
     if (cuda_failure) *cuda_failure = true;
@@ -646,6 +766,112 @@ bool build_bvh_device(HostBVH &out, int device, const double *vertices, size_t n
     return false;
   }
   return true;
+}
+
+// BVHAccel::Build + the scene upload in one step (mb200_scene_build): the tree is grown on the device and the
+// traversal layout (layout.h) is written from it there; only the mesh goes up and, if asked for, the
+// reference-layout tree comes down.  The result equals scene_create(build_bvh(...)) byte for byte.
+int scene_build_device(mb200_scene **out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
+                       size_t nfaces, const uint32_t *material_ids, const double *fv_normals, const double *fv_uvs,
+                       const mb200_build_options &opt, HostBVH *bvh_out, std::string *err) {
+  *out = nullptr;
+  if (bvh_out) {
+    bvh_out->nodes.clear();
+    bvh_out->indices.clear();
+    bvh_out->stats = mb200_build_stats{0, 0, 0};
+  }
+  if (!check_build_args(faces, nverts, nfaces, opt, err)) return MB200_ERR_INVALID_ARG;
+  if (nfaces == 0) // empty scene: every ray misses
+    return scene_create(out, device, vertices, nverts, faces, 0, material_ids, fv_normals, fv_uvs, nullptr, 0, nullptr, 0, err);
+  mb200_scene *sc = nullptr;
+  int st = scene_open(&sc, device, err);
+  if (st != MB200_OK) return st;
+  cudaStream_t s = sc->stream;
+  StageClock stage(s);
+  cudaError_t e = cudaSuccess;
+  auto cuda_fail = [&](const char *what) {
+    if (err) *err = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();
+    scene_destroy(sc);
+    return (int)(e == cudaErrorMemoryAllocation ? MB200_ERR_OUT_OF_MEMORY : MB200_ERR_CUDA);
+  };
+  DeviceTree T;
+  if ((e = build_tree(T, s, vertices, nverts, faces, nfaces, opt, stage)) != cudaSuccess) return cuda_fail("device BVH build");
+
+  const bool f32 = choose_tri_f32(vertices, 3 * nverts);
+  const uint32_t nt = (uint32_t)nfaces, npairs = (uint32_t)T.stats.num_branch_nodes;
+  auto dev_alloc = [&](void **p, size_t bytes) {
+    e = cudaMalloc(p, bytes ? bytes : 16);
+    if (e == cudaSuccess) sc->allocs.push_back(*p), sc->device_bytes += bytes;
+    return e == cudaSuccess;
+  };
+  PairNode *d_pairs = nullptr;
+  void *d_tris = nullptr, *d_v = nullptr, *d_f = nullptr, *d_n = nullptr, *d_uv = nullptr, *d_mat = nullptr;
+  if (!dev_alloc((void **)&d_pairs, (size_t)npairs * sizeof(PairNode)) ||
+      !dev_alloc(&d_tris, nfaces * (f32 ? sizeof(TriRecordF32) : sizeof(TriRecordF64))) ||
+      !dev_alloc(&d_v, 3 * nverts * sizeof(double)) || !dev_alloc(&d_f, 3 * nfaces * sizeof(uint32_t)) ||
+      (fv_normals && !dev_alloc(&d_n, 9 * nfaces * sizeof(double))) || (fv_uvs && !dev_alloc(&d_uv, 6 * nfaces * sizeof(double))))
+    return cuda_fail("cudaMalloc");
+  if (material_ids) {
+    if ((e = cudaMalloc(&d_mat, nfaces * sizeof(uint32_t))) != cudaSuccess) return cuda_fail("cudaMalloc");
+    e = cudaMemcpyAsync(d_mat, material_ids, nfaces * sizeof(uint32_t), cudaMemcpyHostToDevice, s);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_v, T.d_v, 3 * nverts * sizeof(double), cudaMemcpyDeviceToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_f, T.d_f, 3 * nfaces * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s);
+  if (e == cudaSuccess && d_n) e = cudaMemcpyAsync(d_n, fv_normals, 9 * nfaces * sizeof(double), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess && d_uv) e = cudaMemcpyAsync(d_uv, fv_uvs, 6 * nfaces * sizeof(double), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) {
+    k_branch_flags<<<grid_for(T.node_count), kThreads, 0, s>>>(T.node_count, T.d_nodes, T.d_scratch);
+    e = scan_u32(T.node_count, T.d_scratch, T.d_scan, T.d_sums, T.d_total, s);
+  }
+  if (e == cudaSuccess) {
+    k_emit_pairs<<<grid_for(T.node_count), kThreads, 0, s>>>(T.node_count, T.d_nodes, T.d_scan, d_pairs);
+    if (f32)
+      k_emit_tris32<<<grid_for(nt), kThreads, 0, s>>>(nt, T.d_idx, T.d_v, T.d_f, (const uint32_t *)d_mat, (TriRecordF32 *)d_tris);
+    else
+      k_emit_tris64<<<grid_for(nt), kThreads, 0, s>>>(nt, T.d_idx, T.d_v, T.d_f, (const uint32_t *)d_mat, (TriRecordF64 *)d_tris);
+    e = cudaGetLastError();
+  }
+  mb200_bvh_node root;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&root, T.d_nodes, sizeof(root), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  stage("layout");
+  if (e == cudaSuccess && bvh_out) e = download_tree(T, *bvh_out, nfaces, s);
+  stage("download");
+  if (d_mat) cudaFree(d_mat);
+  T.work.release();
+  T.result.release();
+  stage("free");
+  if (e != cudaSuccess) return cuda_fail("device scene build");
+
+  SceneView &v = sc->view;
+  v.empty = 0;
+  v.tri_f32 = f32 ? 1 : 0;
+  v.num_vertices = (uint32_t)nverts;
+  v.num_faces = nt;
+  v.nodes = d_pairs;
+  v.tris = d_tris;
+  v.num_pair_nodes = npairs;
+  v.num_tris = nt;
+  if (root.flag == 0) v.root_ref = 0u, v.root_cnt = kBranch;
+  else v.root_ref = root.data[1], v.root_cnt = root.data[0];
+  for (int k = 0; k < 3; k++) {
+    v.root_box[k] = sc->root_bmin[k] = root.bmin[k];
+    v.root_box[3 + k] = sc->root_bmax[k] = root.bmax[k];
+  }
+  v.vertices = (const double *)d_v;
+  v.faces = (const uint32_t *)d_f;
+  v.fv_normals = (const double *)d_n;
+  v.fv_uvs = (const double *)d_uv;
+  sc->tree_depth = T.stats.max_tree_depth;
+  sc->stack_cap = T.stats.max_tree_depth + 2;
+  st = scene_finish(sc, err);
+  if (st != MB200_OK) {
+    scene_destroy(sc);
+    return st;
+  }
+  *out = sc;
+  return MB200_OK;
 }
 
 } // namespace mb200

@@ -23,6 +23,13 @@ bool all_float_exact(const double *v, size_t n) {
 
 } // namespace
 
+bool choose_tri_f32(const double *vertices, size_t count) {
+  if (const char *fmt = getenv("MB200_TRI_FORMAT")) { // development knob: "f64" forces the 80-byte edge records
+    if (!strcmp(fmt, "f64")) return false;
+  }
+  return all_float_exact(vertices, count);
+}
+
 int relayout_bvh(Relayout &out, const double *vertices, size_t nverts, const uint32_t *faces, size_t nfaces,
                  const uint32_t *material_ids, const mb200_bvh_node *nodes, size_t nnodes, const uint32_t *indices,
                  size_t nindices, std::string *err) {
@@ -100,10 +107,7 @@ int relayout_bvh(Relayout &out, const double *vertices, size_t nverts, const uin
   }
 
   // ---- triangle records in indices_ order
-  out.f32 = all_float_exact(vertices, 3 * nverts);
-  if (const char *fmt = getenv("MB200_TRI_FORMAT")) { // development knob: "f64" forces the 80-byte edge records
-    if (!strcmp(fmt, "f64")) out.f32 = false;
-  }
+  out.f32 = choose_tri_f32(vertices, 3 * nverts);
   if (out.f32) {
     out.tris32.resize(nindices);
     for (size_t i = 0; i < nindices; i++) {
@@ -163,10 +167,8 @@ struct Uploader {
 
 } // namespace
 
-int scene_create(mb200_scene **out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
-                 size_t nfaces, const uint32_t *material_ids, const double *fv_normals, const double *fv_uvs,
-                 const mb200_bvh_node *nodes, size_t nnodes, const uint32_t *indices, size_t nindices,
-                 std::string *err) {
+// Device checks, the handle and its stream: the common first step of scene_create / scene_build_device.
+int scene_open(mb200_scene **out, int device, std::string *err) {
   *out = nullptr;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -183,23 +185,56 @@ int scene_create(mb200_scene **out, int device, const double *vertices, size_t n
     if (err) *err = "device is not sm_100 class (this library ships sm_100a code only)";
     return MB200_ERR_NO_DEVICE;
   }
-
-  Relayout rl;
-  int st = relayout_bvh(rl, vertices, nverts, faces, nfaces, material_ids, nodes, nnodes, indices, nindices, err);
-  if (st != MB200_OK) return st;
-
   if ((e = cudaSetDevice(device)) != cudaSuccess) {
     if (err) *err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
     return MB200_ERR_CUDA;
   }
   mb200_scene *s = new mb200_scene;
   s->device = device;
+  memset(&s->view, 0, sizeof(s->view));
+  s->view.empty = 1;
   if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     if (err) *err = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
     delete s;
     return MB200_ERR_CUDA;
   }
+  *out = s;
+  return MB200_OK;
+}
 
+// The work counter / statistics words, then wait for the uploads.
+int scene_finish(mb200_scene *s, std::string *err) {
+  void *d = nullptr;
+  cudaError_t e = cudaMalloc(&d, 8 * sizeof(unsigned long long));
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+    return MB200_ERR_CUDA;
+  }
+  s->allocs.push_back(d);
+  s->d_work = (unsigned long long *)d;
+  s->d_counters = s->d_work + 1;
+  cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), s->stream);
+  if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) {
+    if (err) *err = std::string("upload: ") + cudaGetErrorString(e);
+    return MB200_ERR_CUDA;
+  }
+  return MB200_OK;
+}
+
+int scene_create(mb200_scene **out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
+                 size_t nfaces, const uint32_t *material_ids, const double *fv_normals, const double *fv_uvs,
+                 const mb200_bvh_node *nodes, size_t nnodes, const uint32_t *indices, size_t nindices,
+                 std::string *err) {
+  mb200_scene *s = nullptr;
+  int st = scene_open(&s, device, err);
+  if (st != MB200_OK) return st;
+  *out = nullptr;
+  Relayout rl;
+  st = relayout_bvh(rl, vertices, nverts, faces, nfaces, material_ids, nodes, nnodes, indices, nindices, err);
+  if (st != MB200_OK) {
+    scene_destroy(s);
+    return st;
+  }
   Uploader up{s, err};
   SceneView &v = s->view;
   memset(&v, 0, sizeof(v));
@@ -229,22 +264,7 @@ int scene_create(mb200_scene **out, int device, const double *vertices, size_t n
   s->tree_depth = rl.depth;
   s->stack_cap = rl.depth + 2;
 
-  if (up.status == MB200_OK) {
-    void *d = nullptr;
-    if ((e = cudaMalloc(&d, 8 * sizeof(unsigned long long))) != cudaSuccess) {
-      up.status = MB200_ERR_CUDA;
-      if (err) *err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
-    } else {
-      s->allocs.push_back(d);
-      s->d_work = (unsigned long long *)d;
-      s->d_counters = s->d_work + 1;
-      cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), s->stream);
-    }
-  }
-  if (up.status == MB200_OK && (e = cudaStreamSynchronize(s->stream)) != cudaSuccess) {
-    up.status = MB200_ERR_CUDA;
-    if (err) *err = std::string("upload: ") + cudaGetErrorString(e);
-  }
+  if (up.status == MB200_OK) up.status = scene_finish(s, err);
   if (up.status != MB200_OK) {
     scene_destroy(s);
     return up.status;

@@ -51,6 +51,11 @@ int scene_create(mb200_scene **out, int device, const double *vertices, size_t n
                  const mb200_bvh_node *nodes, size_t nnodes, const uint32_t *indices, size_t nindices,
                  std::string *err);
 void scene_destroy(mb200_scene *s);
+// Pieces shared with the device-side build (bvh_build_gpu.cu): device checks + handle + stream; work counters + sync;
+// which triangle record the vertices allow.
+int scene_open(mb200_scene **out, int device, std::string *err);
+int scene_finish(mb200_scene *s, std::string *err);
+bool choose_tri_f32(const double *vertices, size_t count);
 
 // Host-side relayout only (no CUDA): exposed for CPU tests of the layout logic.
 struct Relayout {

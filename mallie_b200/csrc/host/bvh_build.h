@@ -22,6 +22,11 @@ bool build_bvh(HostBVH &out, const double *vertices, size_t nverts, const uint32
 // a rejected argument.
 bool build_bvh_device(HostBVH &out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
                       size_t nfaces, const mb200_build_options &opt, std::string *err, bool *cuda_failure);
+// BVHAccel::Build + scene upload in one step, all on the device; bvh_out (may be null) receives the
+// reference-layout tree.  Returns an mb200_status.
+int scene_build_device(mb200_scene **out, int device, const double *vertices, size_t nverts, const uint32_t *faces,
+                       size_t nfaces, const uint32_t *material_ids, const double *fv_normals, const double *fv_uvs,
+                       const mb200_build_options &opt, HostBVH *bvh_out, std::string *err);
 bool dump_bvh(const HostBVH &bvh, const char *path, std::string *err);
 bool load_bvh(HostBVH &out, const char *path, std::string *err);
 

@@ -67,3 +67,51 @@ def test_device_build_matches_host_1m():
     same_tree(v, f)                 # first call pays context + allocation warm-up
     dt, nn = same_tree(v, f)
     print(f"\n1M triangles: {nn} nodes, host build {host*1e3:.0f} ms, device build {dt*1e3:.0f} ms (incl. copies)")
+
+
+def same_scene(m, **opt):
+    """mb200_scene_build against mb200_scene_create(mb200_bvh_build): resident layout, tree and hit records."""
+    v, f = m["vertices"], m["faces"]
+    host = M.Scene(v, f, m.get("material_ids"), m.get("normals"), m.get("uvs"))
+    dev = M.Scene.build(v, f, m.get("material_ids"), m.get("normals"), m.get("uvs"), **opt)
+    try:
+        hi, hp, ht = host.layout()
+        di, dp, dt = dev.layout()
+        assert hi == di
+        assert hp.tobytes() == dp.tobytes(), "pair nodes differ"
+        assert ht.tobytes() == dt.tobytes(), "triangle records differ"
+        if not opt:
+            assert host.nodes.tobytes() == dev.nodes.tobytes() and np.array_equal(host.indices, dev.indices)
+        assert host.uses_f32_vertices() == dev.uses_f32_vertices()
+        lo, hi_ = host.bounds()
+        dlo, dhi = dev.bounds()
+        assert np.array_equal(lo, dlo) and np.array_equal(hi_, dhi)
+        c = (lo + hi_) / 2
+        ext = float(np.max(hi_ - lo))
+        fr = M.camera_frame(c + np.array([0.1 * ext, 0.2 * ext, 1.6 * ext]), c, width=160, height=120)
+        rays = host.generate_rays_grid(fr, 0, 0, 160, 120)
+        a, b = host.trace_closest(rays), dev.trace_closest(rays)
+        assert a.tobytes() == b.tobytes()
+        assert int((a["faceID"] != 0xFFFFFFFF).sum()) > 0
+        ia, ib = host.trace_closest_full(rays), dev.trace_closest_full(rays)   # BuildIntersection: normals / uvs / materials
+        for x, y in zip(ia if isinstance(ia, tuple) else (ia,), ib if isinstance(ib, tuple) else (ib,)):
+            assert np.asarray(x).tobytes() == np.asarray(y).tobytes()
+    finally:
+        host.close()
+        dev.close()
+
+
+@pytest.mark.parametrize("name", ["cornellbox", "teapot", "sphere40"])
+def test_device_scene_matches_host_scene(name):
+    same_scene(T.load_mesh(name))
+
+
+def test_device_scene_f64_records_and_empty():
+    m = dict(T.load_mesh("sphere40"))
+    m["vertices"] = m["vertices"] + 1e-11 * np.arange(m["vertices"].size).reshape(-1, 3)   # not float-exact -> 80-byte records
+    same_scene(m)
+    e = M.Scene.build(m["vertices"], m["faces"][:0])
+    assert e.layout()[0]["empty"] == 1
+    e.close()
+    with pytest.raises(M.MallieB200Error):
+        M.Scene.build(m["vertices"], m["faces"], device=99)
