@@ -8,6 +8,8 @@
 // (false / error message) when no device scene can be created.
 #include "mallie_api.h"
 
+#include <cstdlib>
+
 #include <cassert>
 #include <cfloat>
 #include <chrono>
@@ -53,8 +55,10 @@ bool BVHAccel::DeviceScenes(const Mesh *mesh, int count, std::vector<mb200_scene
   return true;
 }
 
-// BVHAccel::Build (bvh_accel.cc:445-482): binned SAH on the host; the tree is bit-identical to the
-// reference's (builder: host/bvh_build.cc).
+// BVHAccel::Build (bvh_accel.cc:445-482).  With a GPU present the tree is grown on the device and the traversal
+// layout is written from it there (mb200_scene_build; the reference-layout tree is downloaded into nodes_ /
+// indices_ for GetNodes / Dump); without one -- or with MB200_HOST_BUILD=1, or minLeafPrimitives < 2 -- the host
+// builder runs and the upload happens on first use.  Either way the tree is bit-identical to the reference's.
 bool BVHAccel::Build(const Mesh *mesh, const BVHBuildOptions &options) {
   assert(mesh);
   options_ = options;
@@ -65,7 +69,18 @@ bool BVHAccel::Build(const Mesh *mesh, const BVHBuildOptions &options) {
   o.max_tree_depth = options.maxTreeDepth;
   o.bin_size = options.binSize;
   mb200_bvh *b = nullptr;
-  if (mb200_bvh_build(&b, mesh->vertices, mesh->numVertices, mesh->faces, mesh->numFaces, &o) != MB200_OK) {
+  const char *force_host = getenv("MB200_HOST_BUILD");
+  const bool on_device = !(force_host && atoi(force_host) != 0) && o.min_leaf_primitives >= 2 && mesh->numFaces > 0 &&
+                         mb200_device_count() > device_;
+  if (on_device) {
+    if (mb200_scene_build(&dev_, device_, mesh->vertices, mesh->numVertices, mesh->faces, mesh->numFaces, mesh->materialIDs,
+                          mesh->facevarying_normals, mesh->facevarying_uvs, &o, &b) != MB200_OK) {
+      printf("Mallie:err\tmsg:BVH build failed: %s\n", mb200_last_error());
+      dev_ = nullptr;
+      return false;
+    }
+    devMesh_ = mesh;
+  } else if (mb200_bvh_build(&b, mesh->vertices, mesh->numVertices, mesh->faces, mesh->numFaces, &o) != MB200_OK) {
     printf("Mallie:err\tmsg:BVH build failed: %s\n", mb200_last_error());
     return false;
   }

@@ -159,7 +159,8 @@ public:
   BVHAccel();
   ~BVHAccel();
 
-  // Binned-SAH build on the host (bit-identical tree to bvh_accel.cc:445), then upload to `device`.
+  // Binned-SAH build, bit-identical tree to bvh_accel.cc:445: on the GPU together with the scene upload
+  // (mb200_scene_build) when one is present, else on the host (upload on first use).  SetDevice() first.
   bool Build(const Mesh *mesh, const BVHBuildOptions &options);
   BVHBuildStatistics GetStatistics() const { return stats_; }
   bool Dump(const char *filename);
@@ -174,7 +175,10 @@ public:
   const std::vector<unsigned int> &GetIndices() const { return indices_; }
 
   // --- additions -----------------------------------------------------------
-  void SetDevice(int device) { device_ = device; }
+  void SetDevice(int device) {
+    if (device != device_) ReleaseDevice(); // re-created from nodes_ / indices_ on the new GPU at first use
+    device_ = device;
+  }
   // Device replica; created lazily from (mesh, nodes_, indices_) on first use.
   mb200_scene *DeviceScene(const Mesh *mesh);
   // `count` replicas on GPUs device, device + 1, ... (element 0 is DeviceScene()); false if one cannot be made.
