@@ -216,6 +216,9 @@ int mb200_scene_build(mb200_scene **out, int device, const double *vertices, siz
 /* The traversal layout resident on the device (same meaning and sizes as mb200_bvh_device_layout): for checking
  * a device-built scene against a host-built one.  The output pointers may be NULL (sizes only). */
 int mb200_scene_layout(mb200_scene *scene, mb200_layout_info *info, void *pair_nodes_out, void *tri_records_out);
+/* A replica of `src` on GPU `device` (the per-GPU copies of the multi-GPU frame): the resident arrays are copied
+ * device to device, over NVLink when the GPUs are peers; nothing is rebuilt or re-laid out on the host. */
+int mb200_scene_clone(mb200_scene **out, mb200_scene *src, int device);
 void mb200_scene_destroy(mb200_scene *scene);
 /* Scene::BoundingBox (scene.cc:317-333): root node bounds. */
 int mb200_scene_bounds(const mb200_scene *scene, double bmin[3], double bmax[3]);

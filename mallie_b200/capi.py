@@ -30,7 +30,7 @@ CAMERA_PINHOLE, CAMERA_ENV, CAMERA_ENV_STEREO = 0, 1, 2
 # Every symbol include/mallie_b200.h declares (tests/test_abi.py checks the header against this list).
 EXPORTS = [
     "mb200_last_error", "mb200_version", "mb200_device_count", "mb200_launches_issued",
-    "mb200_build_options_default", "mb200_bvh_build", "mb200_bvh_build_device", "mb200_scene_build", "mb200_scene_layout", "mb200_bvh_load", "mb200_bvh_dump",
+    "mb200_build_options_default", "mb200_bvh_build", "mb200_bvh_build_device", "mb200_scene_build", "mb200_scene_layout", "mb200_scene_clone", "mb200_bvh_load", "mb200_bvh_dump",
     "mb200_bvh_num_nodes", "mb200_bvh_num_indices", "mb200_bvh_nodes", "mb200_bvh_indices",
     "mb200_bvh_stats", "mb200_bvh_destroy",
     "mb200_bvh_device_layout",
@@ -144,6 +144,7 @@ def lib():
         L.mb200_bvh_build.argtypes = [C.POINTER(vp), vp, sz, vp, sz, C.POINTER(BuildOptions)]
         L.mb200_bvh_build_device.argtypes = [C.POINTER(vp), C.c_int, vp, sz, vp, sz, C.POINTER(BuildOptions)]
         L.mb200_scene_build.argtypes = [C.POINTER(vp), C.c_int, vp, sz, vp, sz, vp, vp, vp, C.POINTER(BuildOptions), C.POINTER(vp)]
+        L.mb200_scene_clone.argtypes = [C.POINTER(vp), vp, C.c_int]
         L.mb200_scene_layout.argtypes = [vp, C.POINTER(LayoutInfo), vp, vp]
         L.mb200_bvh_load.argtypes = [C.POINTER(vp), C.c_char_p]
         L.mb200_bvh_dump.argtypes = [vp, C.c_char_p]
@@ -414,6 +415,17 @@ class Scene:
             self.build_stats = bvh.stats()
             bvh.close()
         return self
+
+    def clone(self, device):
+        """mb200_scene_clone: a replica on GPU `device`, copied device to device."""
+        other = Scene.__new__(Scene)
+        other.h = None
+        other.vertices, other.faces = self.vertices, self.faces
+        other.nodes, other.indices = getattr(self, "nodes", None), getattr(self, "indices", None)
+        h = C.c_void_p()
+        check(lib().mb200_scene_clone(C.byref(h), self.h, device))
+        other.h = h
+        return other
 
     def layout(self):
         """mb200_scene_layout: (info dict, pair nodes, triangle records) as resident on the device."""

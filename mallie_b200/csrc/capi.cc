@@ -357,6 +357,14 @@ int mb200_scene_layout(mb200_scene *scene, mb200_layout_info *info, void *pair_n
   return MB200_OK;
 }
 
+int mb200_scene_clone(mb200_scene **out, mb200_scene *src, int device) {
+  if (!out || !src) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  std::string err;
+  const int rc = mb200::scene_clone(out, src, device, &err);
+  if (rc != MB200_OK) return set_err(rc, err);
+  return MB200_OK;
+}
+
 void mb200_scene_destroy(mb200_scene *scene) { mb200::scene_destroy(scene); }
 
 int mb200_scene_bounds(const mb200_scene *scene, double bmin[3], double bmax[3]) {

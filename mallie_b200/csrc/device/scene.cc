@@ -273,6 +273,61 @@ int scene_create(mb200_scene **out, int device, const double *vertices, size_t n
   return MB200_OK;
 }
 
+// A replica of `src` on GPU `device`: the resident arrays are copied device to device (NVLink when the GPUs are
+// peers), nothing is rebuilt or re-laid out on the host.
+int scene_clone(mb200_scene **out, mb200_scene *src, int device, std::string *err) {
+  *out = nullptr;
+  cudaError_t e = cudaSetDevice(src->device);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(src->stream);
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("source scene: ") + cudaGetErrorString(e);
+    return MB200_ERR_CUDA;
+  }
+  mb200_scene *s = nullptr;
+  int st = scene_open(&s, device, err);
+  if (st != MB200_OK) return st;
+  const SceneView &sv = src->view;
+  SceneView &v = s->view;
+  v = sv;
+  v.nodes = nullptr, v.tris = nullptr, v.vertices = nullptr, v.faces = nullptr, v.fv_normals = nullptr, v.fv_uvs = nullptr;
+  auto copy = [&](const void *from, size_t bytes) -> const void * {
+    if (st != MB200_OK || !from || bytes == 0) return nullptr;
+    void *d = nullptr;
+    if ((e = cudaMalloc(&d, bytes)) != cudaSuccess) {
+      st = (e == cudaErrorMemoryAllocation) ? MB200_ERR_OUT_OF_MEMORY : MB200_ERR_CUDA;
+      if (err) *err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+      return nullptr;
+    }
+    s->allocs.push_back(d);
+    s->device_bytes += bytes;
+    if ((e = cudaMemcpyPeerAsync(d, device, from, src->device, bytes, s->stream)) != cudaSuccess) {
+      st = MB200_ERR_CUDA;
+      if (err) *err = std::string("cudaMemcpyPeer: ") + cudaGetErrorString(e);
+      return nullptr;
+    }
+    return d;
+  };
+  if (!sv.empty) {
+    const size_t nf = sv.num_faces, nv = sv.num_vertices;
+    v.nodes = (const PairNode *)copy(sv.nodes, (size_t)sv.num_pair_nodes * sizeof(PairNode));
+    v.tris = copy(sv.tris, (size_t)sv.num_tris * (sv.tri_f32 ? sizeof(TriRecordF32) : sizeof(TriRecordF64)));
+    v.vertices = (const double *)copy(sv.vertices, 3 * nv * sizeof(double));
+    v.faces = (const uint32_t *)copy(sv.faces, 3 * nf * sizeof(uint32_t));
+    v.fv_normals = (const double *)copy(sv.fv_normals, 9 * nf * sizeof(double));
+    v.fv_uvs = (const double *)copy(sv.fv_uvs, 6 * nf * sizeof(double));
+  }
+  for (int k = 0; k < 3; k++) s->root_bmin[k] = src->root_bmin[k], s->root_bmax[k] = src->root_bmax[k];
+  s->tree_depth = src->tree_depth;
+  s->stack_cap = src->stack_cap;
+  if (st == MB200_OK) st = scene_finish(s, err);
+  if (st != MB200_OK) {
+    scene_destroy(s);
+    return st;
+  }
+  *out = s;
+  return MB200_OK;
+}
+
 void scene_destroy(mb200_scene *s) {
   if (!s) return;
   cudaSetDevice(s->device);

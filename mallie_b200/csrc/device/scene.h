@@ -51,6 +51,7 @@ int scene_create(mb200_scene **out, int device, const double *vertices, size_t n
                  const mb200_bvh_node *nodes, size_t nnodes, const uint32_t *indices, size_t nindices,
                  std::string *err);
 void scene_destroy(mb200_scene *s);
+int scene_clone(mb200_scene **out, mb200_scene *src, int device, std::string *err);
 // Pieces shared with the device-side build (bvh_build_gpu.cu): device checks + handle + stream; work counters + sync;
 // which triangle record the vertices allow.
 int scene_open(mb200_scene **out, int device, std::string *err);

@@ -40,10 +40,7 @@ bool BVHAccel::DeviceScenes(const Mesh *mesh, int count, std::vector<mb200_scene
   out.push_back(first);
   while ((int)replicas_.size() < count - 1) {
     mb200_scene *r = nullptr;
-    const int rc = mb200_scene_create(&r, device_ + 1 + (int)replicas_.size(), mesh->vertices, mesh->numVertices,
-                                      mesh->faces, mesh->numFaces, mesh->materialIDs, mesh->facevarying_normals,
-                                      mesh->facevarying_uvs, reinterpret_cast<const mb200_bvh_node *>(nodes_.data()),
-                                      nodes_.size(), indices_.data(), indices_.size());
+    const int rc = mb200_scene_clone(&r, first, device_ + 1 + (int)replicas_.size()); // device-to-device copy
     if (rc != MB200_OK) {
       printf("Mallie:err\tmsg:cannot create the scene replica on GPU %d: %s\n", device_ + 1 + (int)replicas_.size(),
              mb200_last_error());

@@ -115,3 +115,23 @@ def test_device_scene_f64_records_and_empty():
     e.close()
     with pytest.raises(M.MallieB200Error):
         M.Scene.build(m["vertices"], m["faces"], device=99)
+
+
+def test_scene_clone_same_device():
+    """mb200_scene_clone onto the same GPU (the 2-GPU case is in test_gpu_multi.py): an independent, identical scene."""
+    m = T.load_mesh("cornellbox")
+    a = M.Scene.build(m["vertices"], m["faces"], m["material_ids"], m["normals"], m["uvs"])
+    b = a.clone(0)
+    ia, pa, ta = a.layout()
+    ib, pb, tb = b.layout()
+    assert ia == ib and pa.tobytes() == pb.tobytes() and ta.tobytes() == tb.tobytes()
+    assert a.device_bytes() == b.device_bytes()
+    fr = M.camera_frame((0, 0, 20), (0, 0, 0), width=96, height=96)
+    rays = a.generate_rays_grid(fr, 0, 0, 96, 96)
+    want = a.trace_closest_full(rays)
+    a.close()                                  # the clone owns its memory
+    got = b.trace_closest_full(rays)
+    assert want[0].tobytes() == got[0].tobytes() and np.array_equal(want[1], got[1])
+    b.close()
+    with pytest.raises(M.MallieB200Error):
+        M.Scene.build(m["vertices"], m["faces"]).clone(77)

@@ -60,3 +60,22 @@ def test_cpp_render_with_num_gpus(tmp_path):
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         outs.append(open(out, "rb").read())
     assert outs[0] == outs[1]
+
+
+def test_cloned_replicas_render_the_same_frame():
+    """Replicas made by mb200_scene_clone (device-to-device copy of a device-built scene) instead of N host uploads."""
+    need_gpus(2)
+    G = min(M.device_count(), 4)
+    W, H = 200, 120
+    m = T.load_mesh("teapot")
+    first = M.Scene.build(m["vertices"], m["faces"], m["material_ids"], m["normals"], m["uvs"])
+    scenes = [first] + [first.clone(g) for g in range(1, G)]
+    for s in scenes[1:]:
+        assert s.layout()[1].tobytes() == first.layout()[1].tobytes() and s.layout()[2].tobytes() == first.layout()[2].tobytes()
+    fg = M.camera_frame((5, 40, 150), (5, 40, 0), width=W, height=H)
+    p = first.render_params(fg, W, H, shader=M.SHADER_PRIMARY_SHADOW, light=(100.0, 200.0, 150.0), pass_index=1)
+    want, wcnt, _ = first.render_frame(p, 2)
+    img, cnt, _ = M.render_frame_multi(scenes, p, 2, band_rows=4)
+    assert img.tobytes() == want.tobytes() and np.array_equal(cnt, wcnt)
+    for s in scenes:
+        s.close()

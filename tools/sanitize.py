@@ -28,4 +28,16 @@ sc.render_pass(p)
 p = sc.render_params(fg, W, H, shader=M.SHADER_PRIMARY_SHADOW, light=(2, 4, 3), bands=(4, 3, 1), compact=True)
 sc.render_pass(p)
 sc.close()
+# the device builder: a mesh large enough for single-segment CTAs (block-wide reductions, shared-memory histograms)
+# at the top levels and many small segments (per-element atomics) below; then the device-side layout and a clone
+v2, f2 = bumpy_sphere(40)
+db = M.HostBVH.build_device(v2, f2)
+hb = M.HostBVH.build(v2, f2)
+assert db.arrays()[0].tobytes() == hb.arrays()[0].tobytes() and (db.arrays()[1] == hb.arrays()[1]).all()
+ds = M.Scene.build(v2 + 1e-11, f2, min_leaf=4, bin_size=16)          # f64 records
+ds2 = M.Scene.build(v2, f2)
+cl = ds2.clone(0)
+assert cl.trace_closest(rays).tobytes() == ds2.trace_closest(rays).tobytes()
+for s in (ds, ds2, cl):
+    s.close()
 print("sanitize workload done:", int((hits["faceID"] != 0xFFFFFFFF).sum()), "hits", cnt)
