@@ -32,6 +32,25 @@ def test_device_build_matches_host_small(name):
     same_tree(m["vertices"], m["faces"])
 
 
+@pytest.mark.parametrize("mesh,entry", [("cornellbox", "cornellbox_512"), ("teapot", "teapot_1080p"),
+                                        ("sphere40", "sphere40_256"), ("sphere500", "sphere500_1080p")])
+def test_device_builder_is_the_reference_builder(mesh, entry):
+    """Against the committed fingerprints of the REFERENCE's own trees (tests/golden/golden.json, generated from
+    oracle/_ref) and, for the small scenes, against the oracle's builder node by node."""
+    g = T.golden()[entry]
+    m = T.load_mesh(mesh)
+    db = M.HostBVH.build_device(m["vertices"], m["faces"])
+    nodes, idx = db.arrays()
+    assert db.stats() == g["stats"]
+    assert len(nodes) == g["num_nodes"] and len(idx) == g["num_indices"]
+    assert T.fnv(idx) == g["indices_fnv"] and T.fnv(T.mask_leaf_axis(nodes)) == g["nodes_fnv"]
+    if mesh != "sphere500":
+        _, ob = T.oracle_scene(mesh)
+        on, oi = ob.arrays()
+        assert np.array_equal(oi, idx) and T.mask_leaf_axis(on).tobytes() == T.mask_leaf_axis(nodes).tobytes()
+    db.close()
+
+
 @pytest.mark.parametrize("opt", [dict(bin_size=16), dict(min_leaf=4), dict(max_depth=5), dict(cost_taabb=0.5, bin_size=128),
                                  dict(min_leaf=2, bin_size=8)])
 def test_device_build_options(opt):
