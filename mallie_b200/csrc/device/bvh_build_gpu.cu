@@ -665,7 +665,7 @@ cudaError_t build_tree(DeviceTree &T, cudaStream_t s, const double *vertices, si
     S = 2 * nbranch;
     cur ^= 1;
     level++;
-    if (level > 600) return cudaErrorInvalidValue; // max_tree_depth bounds this; defensive
+    if (level > opt.max_tree_depth + 1) return cudaErrorInvalidValue; // cannot happen: depth >= max_tree_depth makes leaves
   }
   stage("levels");
 
@@ -798,6 +798,11 @@ int scene_build_device(mb200_scene **out, int device, const double *vertices, si
   DeviceTree T;
   if ((e = build_tree(T, s, vertices, nverts, faces, nfaces, opt, stage)) != cudaSuccess) return cuda_fail("device BVH build");
 
+  if (T.stats.max_tree_depth > 500) { // as relayout_bvh: the traversal stack holds 512 entries
+    if (err) *err = "BVH deeper than 500 levels (reference stack is 512, bvh_accel.cc:548)";
+    scene_destroy(sc);
+    return MB200_ERR_INVALID_ARG;
+  }
   const bool f32 = choose_tri_f32(vertices, 3 * nverts);
   const uint32_t nt = (uint32_t)nfaces, npairs = (uint32_t)T.stats.num_branch_nodes;
   auto dev_alloc = [&](void **p, size_t bytes) {
