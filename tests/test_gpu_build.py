@@ -58,6 +58,39 @@ def test_device_build_options(opt):
     same_tree(m["vertices"], m["faces"], **opt)
 
 
+def soup(n, seed, scale=1.0, offset=0.0, tri=0.05):
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-1, 1, (n, 1, 3))
+    v = ((c + rng.uniform(-tri, tri, (n, 3, 3))) * scale + offset).reshape(-1, 3)
+    return v.astype(np.float32).astype(np.float64), np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+
+
+@pytest.mark.parametrize("case", [
+    dict(n=5000, seed=1),                                   # overlapping triangles, many straddle the planes
+    dict(n=5000, seed=2, tri=0.8),                          # huge triangles: most bins shared, frequent median fallback
+    dict(n=3000, seed=3, scale=1e-12),                      # extents below kEPS * 1024: bin scale 0 (bvh_accel.cc:105-112)
+    dict(n=3000, seed=4, scale=1e6, offset=-3e6),           # large negative coordinates
+    dict(n=4000, seed=5, opt=dict(bin_size=1024)),          # more bins than the shared-memory histogram holds
+    dict(n=4000, seed=6, opt=dict(bin_size=2)),             # a single candidate plane per axis
+    dict(n=4000, seed=7, opt=dict(max_depth=1)),
+    dict(n=15, seed=8), dict(n=16, seed=9), dict(n=17, seed=10), dict(n=1, seed=11),
+])
+def test_device_build_triangle_soups(case):
+    v, f = soup(case["n"], case["seed"], case.get("scale", 1.0), case.get("offset", 0.0), case.get("tri", 0.05))
+    same_tree(v, f, **case.get("opt", {}))
+
+
+def test_device_build_quantised_centroids():
+    """Many triangles with exactly equal centroid sums and bounds (a regular grid): ties in the predicate and in the
+    SAH costs; the plane / axis choice and the partition order must still follow the reference."""
+    g = np.arange(65, dtype=np.float64)
+    vv = np.stack([np.repeat(g, 65), np.tile(g, 65), np.zeros(65 * 65)], axis=1)
+    q = np.array([[i * 65 + j, i * 65 + j + 1, (i + 1) * 65 + j] for i in range(64) for j in range(64)], np.uint32)
+    q = np.concatenate([q, q[::-1]])                         # every triangle twice
+    same_tree(vv, q)
+    same_tree(vv[:, [2, 0, 1]].copy(), q, min_leaf=2)
+
+
 def test_device_build_degenerate_inputs():
     # all triangles identical: no plane separates them -> object-median fallback at every level
     v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float64)
