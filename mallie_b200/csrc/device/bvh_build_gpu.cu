@@ -220,11 +220,16 @@ __device__ __forceinline__ double half_area2(const double lo[3], const double hi
   return 2.0 * (dx * dy + dy * dz + dz * dx);
 }
 
-// ---- SAH sweep, one thread per branch segment (FindCutFromBinBuffer, bvh_accel.cc:156-255) -------------
-__global__ void k_sweep(uint32_t S, const uint32_t *__restrict__ sl, const uint32_t *__restrict__ sr,
-                        mb200_build_options opt, SegWork w, const uint32_t *__restrict__ hist) {
-  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= S || w.leaf[s]) return;
+// ---- SAH sweep, one warp per branch segment (FindCutFromBinBuffer, bvh_accel.cc:156-255) ------------------
+// The reference walks the nb - 1 candidate planes of an axis in order, carrying the running counts, and keeps the
+// first plane whose cost is strictly below everything before it.  A plane's cost depends only on its own prefix
+// counts, so the planes are evaluated 32 at a time (warp scan of the bin counts + carry) and the winner is the
+// (cost, plane index) minimum -- lower index on equal cost, NaN costs never win, exactly as the sequential `<`.
+__global__ void __launch_bounds__(kThreads) k_sweep(uint32_t S, const uint32_t *__restrict__ sl, const uint32_t *__restrict__ sr,
+                                                   mb200_build_options opt, SegWork w, const uint32_t *__restrict__ hist) {
+  const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (s >= S || w.leaf[s]) return; // warp-uniform
   const int nb = opt.bin_size;
   const uint32_t *h = hist + (size_t)w.hslot[s] * 6 * nb;
   double lo[3], hi[3];
@@ -236,25 +241,41 @@ __global__ void k_sweep(uint32_t S, const uint32_t *__restrict__ sl, const uint3
   double best_cost[3], best_pos[3];
   for (int a = 0; a < 3; a++) {
     const double step = w.step[3 * (size_t)s + a];
-    best_pos[a] = lo[a] + 0.5 * step;
-    best_cost[a] = DBL_MAX;
-    size_t nl = 0, nr = n;
+    double bc = DBL_MAX;
+    int bi = -1; // no plane yet
+    uint32_t carry_l = 0, carry_r = 0;
     double llo[3] = {lo[0], lo[1], lo[2]}, lhi[3] = {hi[0], hi[1], hi[2]};
     double rlo[3] = {lo[0], lo[1], lo[2]}, rhi[3] = {hi[0], hi[1], hi[2]};
-    for (int i = 0; i < nb - 1; ++i) {
-      nl += h[(a * 2 + 0) * nb + i];
-      nr -= h[(a * 2 + 1) * nb + i];
-      const double pos = lo[a] + (i + 0.5) * step;
-      lhi[a] = pos;
-      rlo[a] = pos;
-      const double al = half_area2(llo, lhi), ar = half_area2(rlo, rhi);
-      const double cost = 2.0f * t_box + (al * inv_whole) * (double)(nl)*t_tri + (ar * inv_whole) * (double)(nr)*t_tri;
-      if (cost < best_cost[a]) {
-        best_cost[a] = cost;
-        best_pos[a] = pos;
+    for (int base = 0; base < nb - 1; base += 32) {
+      const int i = base + (int)lane;
+      const bool act = i < nb - 1;
+      uint32_t cl = act ? h[(a * 2 + 0) * nb + i] : 0u, cr = act ? h[(a * 2 + 1) * nb + i] : 0u;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t yl = __shfl_up_sync(0xFFFFFFFFu, cl, o), yr = __shfl_up_sync(0xFFFFFFFFu, cr, o);
+        if ((int)lane >= o) cl += yl, cr += yr;
+      }
+      const size_t nl = (size_t)carry_l + cl, nr = n - ((size_t)carry_r + cr);
+      carry_l += __shfl_sync(0xFFFFFFFFu, cl, 31);
+      carry_r += __shfl_sync(0xFFFFFFFFu, cr, 31);
+      if (act) {
+        const double pos = lo[a] + (i + 0.5) * step;
+        lhi[a] = pos;
+        rlo[a] = pos;
+        const double al = half_area2(llo, lhi), ar = half_area2(rlo, rhi);
+        const double cost = 2.0f * t_box + (al * inv_whole) * (double)(nl)*t_tri + (ar * inv_whole) * (double)(nr)*t_tri;
+        if (cost < bc) bc = cost, bi = i;
       }
     }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double oc = __shfl_xor_sync(0xFFFFFFFFu, bc, o);
+      const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+      // a lane without a plane (bi < 0) holds DBL_MAX and every real plane is strictly below it
+      if (oi >= 0 && (bi < 0 || oc < bc || (oc == bc && oi < bi))) bc = oc, bi = oi;
+    }
+    best_cost[a] = bc;
+    best_pos[a] = lo[a] + ((bi < 0 ? 0 : bi) + 0.5) * step; // no plane: the first plane's position (bvh_accel.cc:170)
   }
+  if (lane != 0) return;
   int axis = 0;
   double c = best_cost[0];
   if (c > best_cost[1]) axis = 1, c = best_cost[1];
@@ -290,69 +311,71 @@ __global__ void __launch_bounds__(kThreads) k_pred(uint32_t n, uint32_t nt, cons
   }
 }
 
-// misplaced flags: left part holds a "right" triangle / right part holds a "left" triangle
+// misplaced flags, packed: high word = left part holds a "right" triangle, low word = right part holds a "left" one
+// (one 64-bit scan then ranks both kinds)
 __global__ void k_misplaced(uint32_t n, const uint32_t *__restrict__ sid, const uint32_t *__restrict__ sl,
-                            const uint8_t *__restrict__ pred, SegWork w, uint32_t *__restrict__ ml,
-                            uint32_t *__restrict__ mr) {
+                            const uint8_t *__restrict__ pred, SegWork w, unsigned long long *__restrict__ mis) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t s = sid[i];
-  uint32_t a = 0, b = 0;
+  unsigned long long m = 0ull;
   if (s != kNoSeg && !w.leaf[s]) {
     const uint32_t mid = sl[s] + w.ntrue[s];
-    if (i < mid) a = pred[i] ? 0u : 1u;
-    else b = pred[i] ? 1u : 0u;
+    if (i < mid) m = pred[i] ? 0ull : (1ull << 32);
+    else m = pred[i] ? 1ull : 0ull;
   }
-  ml[i] = a, mr[i] = b;
+  mis[i] = m;
 }
 
-// ---- exclusive scan of uint32 (three phases; out has n + 1 entries, out[n] = total) --------------------
+// ---- exclusive scan (three phases; out has n + 1 entries, out[n] = total) ------------------------------
 constexpr int kScanItems = 8; // per thread
-__global__ void __launch_bounds__(kThreads) k_scan_blocks(uint32_t n, const uint32_t *__restrict__ in,
-                                                         uint32_t *__restrict__ out, uint32_t *__restrict__ sums) {
-  __shared__ uint32_t s_w[kThreads / 32];
+template <class V>
+__global__ void __launch_bounds__(kThreads) k_scan_blocks(uint32_t n, const V *__restrict__ in, V *__restrict__ out,
+                                                         V *__restrict__ sums) {
+  __shared__ V s_w[kThreads / 32];
   const uint32_t base = blockIdx.x * (kThreads * kScanItems) + threadIdx.x * kScanItems;
-  uint32_t v[kScanItems], t = 0;
+  V v[kScanItems], t = 0;
   for (int k = 0; k < kScanItems; k++) {
-    v[k] = (base + k < n) ? in[base + k] : 0u;
+    v[k] = (base + k < n) ? in[base + k] : (V)0;
     t += v[k];
   }
-  uint32_t x = t; // inclusive scan of the per-thread totals
+  V x = t; // inclusive scan of the per-thread totals
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+    const V y = __shfl_up_sync(0xFFFFFFFFu, x, o);
     if ((int)lane >= o) x += y;
   }
   if (lane == 31) s_w[warp] = x;
   __syncthreads();
-  uint32_t woff = 0;
+  V woff = 0;
   for (unsigned k = 0; k < warp; k++) woff += s_w[k];
-  uint32_t run = woff + x - t;
+  V run = woff + x - t;
   for (int k = 0; k < kScanItems; k++) {
     if (base + k < n) out[base + k] = run;
     run += v[k];
   }
   if (threadIdx.x == kThreads - 1) sums[blockIdx.x] = woff + x;
 }
-__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t nblocks, uint32_t *sums, uint32_t *total) { // <<<1, 1024>>>
-  __shared__ uint32_t s_w[32];
-  __shared__ uint32_t s_run;
+template <class V>
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t nblocks, V *sums, V *total) { // <<<1, 1024>>>
+  __shared__ V s_w[32];
+  __shared__ V s_run;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_run = 0;
   __syncthreads();
   for (uint32_t base = 0; base < nblocks; base += 1024) {
     const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < nblocks ? sums[i] : 0u;
-    uint32_t x = v;
+    const V v = i < nblocks ? sums[i] : (V)0;
+    V x = v;
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+      const V y = __shfl_up_sync(0xFFFFFFFFu, x, o);
       if ((int)lane >= o) x += y;
     }
     if (lane == 31) s_w[warp] = x;
     __syncthreads();
-    uint32_t woff = 0;
+    V woff = 0;
     for (unsigned k = 0; k < warp; k++) woff += s_w[k];
-    const uint32_t run = s_run;
+    const V run = s_run;
     if (i < nblocks) sums[i] = run + woff + x - v;
     __syncthreads();
     if (threadIdx.x == 1023) s_run = run + woff + x;
@@ -360,31 +383,31 @@ __global__ void __launch_bounds__(1024) k_scan_sums(uint32_t nblocks, uint32_t *
   }
   if (threadIdx.x == 0) *total = s_run;
 }
-__global__ void k_scan_add(uint32_t n, uint32_t *__restrict__ out, const uint32_t *__restrict__ sums,
-                           const uint32_t *__restrict__ total) {
+template <class V>
+__global__ void k_scan_add(uint32_t n, V *__restrict__ out, const V *__restrict__ sums, const V *__restrict__ total) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] += sums[i / (kThreads * kScanItems)];
   if (i == 0) out[n] = *total;
 }
 
 // right-misplaced positions, compacted in position order
-__global__ void k_right_list(uint32_t n, const uint32_t *__restrict__ mr, const uint32_t *__restrict__ scan_r,
+__global__ void k_right_list(uint32_t n, const unsigned long long *__restrict__ mis, const unsigned long long *__restrict__ scan,
                              uint32_t *__restrict__ rlist) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && mr[i]) rlist[scan_r[i]] = i;
+  if (i < n && (uint32_t)mis[i]) rlist[(uint32_t)scan[i]] = i;
 }
 
 // k-th misplaced from the left <-> k-th misplaced from the right (libstdc++ bidirectional __partition)
 __global__ void k_swap(uint32_t n, const uint32_t *__restrict__ sid, const uint32_t *__restrict__ sl,
-                       const uint32_t *__restrict__ sr, const uint32_t *__restrict__ ml,
-                       const uint32_t *__restrict__ scan_l, const uint32_t *__restrict__ scan_r,
-                       const uint32_t *__restrict__ rlist, uint32_t *idx) {
+                       const uint32_t *__restrict__ sr, const unsigned long long *__restrict__ mis,
+                       const unsigned long long *__restrict__ scan, const uint32_t *__restrict__ rlist, uint32_t *idx) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || !ml[i]) return;
+  if (i >= n || !(mis[i] >> 32)) return;
   const uint32_t s = sid[i];
-  const uint32_t k = scan_l[i] - scan_l[sl[s]];
-  const uint32_t m = scan_l[sr[s]] - scan_l[sl[s]]; // misplaced on either side of this segment
-  const uint32_t j = rlist[scan_r[sl[s]] + (m - 1u - k)];
+  const unsigned long long at_l = scan[sl[s]], at_r = scan[sr[s]];
+  const uint32_t k = (uint32_t)(scan[i] >> 32) - (uint32_t)(at_l >> 32);
+  const uint32_t m = (uint32_t)(at_r >> 32) - (uint32_t)(at_l >> 32); // misplaced on either side of this segment
+  const uint32_t j = rlist[(uint32_t)at_l + (m - 1u - k)];
   const uint32_t a = idx[i], b = idx[j];
   idx[i] = b, idx[j] = a;
 }
@@ -514,12 +537,12 @@ struct Arena {
   ~Arena() { release(); }
 };
 
-cudaError_t scan_u32(uint32_t n, const uint32_t *in, uint32_t *out, uint32_t *sums, uint32_t *total, cudaStream_t s) {
+template <class V> cudaError_t scan_excl(uint32_t n, const V *in, V *out, V *sums, V *total, cudaStream_t s) {
   const uint32_t per = kThreads * kScanItems, nblocks = (n + per - 1) / per;
-  if (n == 0) return cudaMemsetAsync(out, 0, sizeof(uint32_t), s);
-  k_scan_blocks<<<nblocks, kThreads, 0, s>>>(n, in, out, sums);
-  k_scan_sums<<<1, 1024, 0, s>>>(nblocks, sums, total);
-  k_scan_add<<<grid_for(n), kThreads, 0, s>>>(n, out, sums, total);
+  if (n == 0) return cudaMemsetAsync(out, 0, sizeof(V), s);
+  k_scan_blocks<V><<<nblocks, kThreads, 0, s>>>(n, in, out, sums);
+  k_scan_sums<V><<<1, 1024, 0, s>>>(nblocks, sums, total);
+  k_scan_add<V><<<grid_for(n), kThreads, 0, s>>>(n, out, sums, total);
   return cudaGetLastError();
 }
 
@@ -563,7 +586,8 @@ cudaError_t build_tree(DeviceTree &T, cudaStream_t s, const double *vertices, si
   const size_t max_branch = nfaces / (size_t)opt.min_leaf_primitives + 2;
   const size_t max_nodes = 2 * nfaces + 2;
   double *d_lo, *d_hi, *d_cs;
-  uint32_t *d_sid, *d_ml, *d_mr, *d_scan_l, *d_scan_r, *d_rlist, *d_sums, *d_total, *d_counter, *d_ord, *d_hist;
+  uint32_t *d_sid, *d_rlist, *d_sums, *d_total, *d_counter, *d_ord, *d_hist;
+  unsigned long long *d_mis, *d_mscan, *d_sums64, *d_total64;
   uint8_t *d_pred;
   Segs seg[2];
   SegWork w;
@@ -576,13 +600,13 @@ cudaError_t build_tree(DeviceTree &T, cudaStream_t s, const double *vertices, si
     A.get(&d_hi, 3 * nfaces);
     A.get(&d_cs, 3 * nfaces);
     A.get(&d_sid, nfaces);
-    A.get(&d_ml, nfaces);
-    A.get(&d_mr, nfaces);
-    A.get(&d_scan_l, nfaces + 1);
-    A.get(&d_scan_r, nfaces + 1);
+    A.get(&d_mis, nfaces);
+    A.get(&d_mscan, nfaces + 1);
+    A.get(&d_sums64, nfaces / (kThreads * kScanItems) + 2);
+    A.get(&d_total64, 1);
     A.get(&d_rlist, nfaces);
     A.get(&d_pred, nfaces);
-    A.get(&d_sums, nfaces / (kThreads * kScanItems) + 2);
+    A.get(&d_sums, max_segs / (kThreads * kScanItems) + 2);
     A.get(&d_total, 1);
     A.get(&d_counter, 1);
     A.get(&d_ord, max_segs + 1);
@@ -646,16 +670,15 @@ cudaError_t build_tree(DeviceTree &T, cudaStream_t s, const double *vertices, si
       CUB(cudaMemsetAsync(d_hist, 0, (size_t)nbranch * 6 * nb * sizeof(uint32_t), s));
       const size_t hsm = (nb <= 512) ? 6 * (size_t)nb * sizeof(uint32_t) : 0;
       k_histogram<<<grid_for(nt), kThreads, hsm, s>>>(nt, nt, nb, d_sid, T.d_idx, d_lo, d_hi, w, d_hist);
-      k_sweep<<<grid_for(S, 64), 64, 0, s>>>(S, c.l, c.r, opt, w, d_hist);
+      k_sweep<<<grid_for((size_t)S * 32), kThreads, 0, s>>>(S, c.l, c.r, opt, w, d_hist);
       k_pred<<<grid_for(nt), kThreads, 0, s>>>(nt, nt, d_sid, T.d_idx, d_cs, w, d_pred);
-      k_misplaced<<<grid_for(nt), kThreads, 0, s>>>(nt, d_sid, c.l, d_pred, w, d_ml, d_mr);
-      CUB(scan_u32(nt, d_ml, d_scan_l, d_sums, d_total, s));
-      CUB(scan_u32(nt, d_mr, d_scan_r, d_sums, d_total, s));
-      k_right_list<<<grid_for(nt), kThreads, 0, s>>>(nt, d_mr, d_scan_r, d_rlist);
-      k_swap<<<grid_for(nt), kThreads, 0, s>>>(nt, d_sid, c.l, c.r, d_ml, d_scan_l, d_scan_r, d_rlist, T.d_idx);
-      nl += 12;
+      k_misplaced<<<grid_for(nt), kThreads, 0, s>>>(nt, d_sid, c.l, d_pred, w, d_mis);
+      CUB(scan_excl(nt, d_mis, d_mscan, d_sums64, d_total64, s));
+      k_right_list<<<grid_for(nt), kThreads, 0, s>>>(nt, d_mis, d_mscan, d_rlist);
+      k_swap<<<grid_for(nt), kThreads, 0, s>>>(nt, d_sid, c.l, c.r, d_mis, d_mscan, d_rlist, T.d_idx);
+      nl += 9;
     }
-    CUB(scan_u32(S, w.isbranch, d_ord, d_sums, d_total, s));
+    CUB(scan_excl(S, w.isbranch, d_ord, d_sums, d_total, s));
     k_emit_level<<<grid_for(S), kThreads, 0, s>>>(S, c, w, d_ord, node_count, nodes, nx);
     nl += 4;
     CUB(cudaGetLastError());
@@ -827,7 +850,7 @@ int scene_build_device(mb200_scene **out, int device, const double *vertices, si
   if (e == cudaSuccess && d_uv) e = cudaMemcpyAsync(d_uv, fv_uvs, 6 * nfaces * sizeof(double), cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) {
     k_branch_flags<<<grid_for(T.node_count), kThreads, 0, s>>>(T.node_count, T.d_nodes, T.d_scratch);
-    e = scan_u32(T.node_count, T.d_scratch, T.d_scan, T.d_sums, T.d_total, s);
+    e = scan_excl(T.node_count, T.d_scratch, T.d_scan, T.d_sums, T.d_total, s);
   }
   if (e == cudaSuccess) {
     k_emit_pairs<<<grid_for(T.node_count), kThreads, 0, s>>>(T.node_count, T.d_nodes, T.d_scan, d_pairs);
