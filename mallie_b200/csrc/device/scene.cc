@@ -13,12 +13,13 @@ namespace mb200 {
 namespace {
 
 bool all_float_exact(const double *v, size_t n) {
-  for (size_t i = 0; i < n; i++) {
+  bool ok = true;
+#pragma omp parallel for schedule(static) reduction(&& : ok) if (n > (1u << 16))
+  for (long i = 0; i < (long)n; i++) {
     const double x = v[i];
-    if (!std::isfinite(x)) return false;
-    if ((double)(float)x != x) return false;
+    ok = ok && std::isfinite(x) && (double)(float)x == x;
   }
-  return true;
+  return ok;
 }
 
 } // namespace
