@@ -214,7 +214,29 @@ def test_no_gpu_means_loud_failure_not_fallback():
     with pytest.raises(M.MallieB200Error) as e:
         M.Scene(m["vertices"], m["faces"])
     assert "error -3" in str(e.value)            # MB200_ERR_NO_DEVICE
+    with pytest.raises(M.MallieB200Error) as e:
+        M.Scene.build(m["vertices"], m["faces"])   # device-side build + layout: same answer, no host substitute
+    assert "error -3" in str(e.value)
+    with pytest.raises(M.MallieB200Error) as e:
+        M.HostBVH.build_device(m["vertices"], m["faces"])
+    assert "error -2" in str(e.value)            # MB200_ERR_CUDA
     assert capi.launches_issued() == 0
+
+
+def test_device_builder_rejects_bad_arguments_before_touching_the_gpu():
+    m = T.load_mesh("sphere40")
+    v, f = m["vertices"], m["faces"]
+    for call in (lambda: M.HostBVH.build_device(v, f, min_leaf=1), lambda: M.Scene.build(v, f, min_leaf=1),
+                 lambda: M.HostBVH.build_device(v, f, bin_size=1), lambda: M.Scene.build(v, f, bin_size=70000),
+                 lambda: M.HostBVH.build_device(v, np.array([[0, 1, 10 ** 6]], np.uint32)),
+                 lambda: M.Scene.build(v, np.array([[0, 1, 10 ** 6]], np.uint32))):
+        with pytest.raises(M.MallieB200Error) as e:
+            call()
+        assert "error -1" in str(e.value)        # MB200_ERR_INVALID_ARG
+    L = capi.lib()
+    assert L.mb200_scene_build(None, 0, None, 0, None, 0, None, None, None, None, None) == -1
+    assert L.mb200_bvh_build_device(None, 0, None, 0, None, 0, None) == -1
+    assert L.mb200_scene_clone(None, None, 0) == -1 and L.mb200_scene_layout(None, None, None, None) == -1
 
 
 @pytest.mark.parametrize("mesh", ["cornellbox", "teapot", "sphere40"])
