@@ -750,6 +750,11 @@ bool check_build_args(const uint32_t *faces, size_t nverts, size_t nfaces, const
     if (err) *err = "too many triangles for the device builder";
     return false;
   }
+  // one histogram per open branch node of a level: (nfaces / min_leaf) x 3 axes x 2 x bin_size counters
+  if ((double)(nfaces / (size_t)opt.min_leaf_primitives + 2) * 6.0 * opt.bin_size * sizeof(uint32_t) > 16e9) {
+    if (err) *err = "bin_size x triangle count needs more than 16 GB of histograms on the device (use mb200_bvh_build)";
+    return false;
+  }
   bool ok = true;
 #pragma omp parallel for schedule(static) reduction(&& : ok)
   for (long i = 0; i < (long)(3 * nfaces); i++) ok = ok && faces[i] < nverts;
