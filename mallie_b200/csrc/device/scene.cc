@@ -287,6 +287,14 @@ int scene_clone(mb200_scene **out, mb200_scene *src, int device, std::string *er
   mb200_scene *s = nullptr;
   int st = scene_open(&s, device, err);
   if (st != MB200_OK) return st;
+  if (device != src->device) { // direct NVLink copies need the peer mapping; without it the copy is staged through the host
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, device, src->device) == cudaSuccess && can) {
+      const cudaError_t pe = cudaDeviceEnablePeerAccess(src->device, 0); // current device is `device` (scene_open)
+      (void)pe;                                                           // already enabled is fine
+    }
+    cudaGetLastError();
+  }
   const SceneView &sv = src->view;
   SceneView &v = s->view;
   v = sv;
