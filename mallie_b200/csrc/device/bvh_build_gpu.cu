@@ -2,8 +2,9 @@
 //
 // The reference builder is a depth-first recursion; its result, however, is a pure function of the
 // triangle set of every node, so the same tree can be grown LEVEL BY LEVEL with all nodes of a level
-// processed side by side (host/bvh_build.cc is the sequential statement of the same algorithm and the
-// oracle for this file; tests compare the two bit for bit):
+// processed side by side (host/bvh_build.cc is the sequential statement of the same algorithm; tests hold
+// this file against it, against the oracle's builder and against the reference's tree fingerprints, bit
+// for bit; tests/lsbuild_model.py is a numpy model of the steps below):
 //
 //   per level, over all active segments [l, r) of the index array:
 //     bounds      min / max of the cached triangle bounds, +- kEPS            (bvh_accel.cc:285-315)
@@ -22,6 +23,11 @@
 // Segmented reductions take a block-wide fast path when a whole CTA lies inside one segment (always true
 // near the root, where contention on per-segment atomics would otherwise serialise) and fall back to
 // per-element atomics elsewhere (deep levels: many small segments, no contention).
+//
+// scene_build_device (mb200_scene_build) continues on the device: branch ranks number the 128-byte pair
+// nodes, both children's boxes are written into the parent and the leaf-ordered triangle records are
+// emitted -- what scene.cc::relayout_bvh does on the host, byte for byte -- so that only the mesh crosses
+// PCIe on the way in and nothing has to come back.
 #include <cuda_runtime.h>
 
 #include <cfloat>
