@@ -89,3 +89,46 @@ def random_rays(rng, n, bmin, bmax):
     dr = tgt - org
     dr /= np.linalg.norm(dr, axis=1, keepdims=True)
     return np.concatenate([org, dr], axis=1)
+
+
+# ---- builder edge cases shared by tests/golden/make_build_golden.py (reference fingerprints), the CPU tests of the
+# host builder / oracle and the GPU tests of the device builder
+def soup(n, seed, scale=1.0, offset=0.0, tri=0.05):
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-1, 1, (n, 1, 3))
+    v = ((c + rng.uniform(-tri, tri, (n, 3, 3))) * scale + offset).reshape(-1, 3)
+    return v.astype(np.float32).astype(np.float64), np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+
+
+def doubled_grid(n=64):
+    """A regular grid, every triangle twice: exactly equal bounds / centroid sums, ties everywhere."""
+    g = np.arange(n + 1, dtype=np.float64)
+    vv = np.stack([np.repeat(g, n + 1), np.tile(g, n + 1), np.zeros((n + 1) ** 2)], axis=1)
+    q = np.array([[i * (n + 1) + j, i * (n + 1) + j + 1, (i + 1) * (n + 1) + j] for i in range(n) for j in range(n)], np.uint32)
+    return vv, np.concatenate([q, q[::-1]])
+
+
+def build_cases():
+    """name -> (vertices, faces); default BVHBuildOptions (what the reference harness builds with)."""
+    cases = {
+        "soup_overlapping": soup(5000, 1),
+        "soup_huge_triangles": soup(5000, 2, tri=0.8),
+        "soup_tiny_extent": soup(3000, 3, scale=1e-12),
+        "soup_large_negative": soup(3000, 4, scale=1e6, offset=-3e6),
+        "soup_15": soup(15, 8), "soup_16": soup(16, 9), "soup_17": soup(17, 10), "soup_1": soup(1, 11),
+        "doubled_grid": doubled_grid(),
+        "identical_100": (np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float64), np.tile(np.array([[0, 1, 2]], np.uint32), (100, 1))),
+    }
+    vv, q = doubled_grid()
+    cases["doubled_grid_yz"] = (vv[:, [2, 0, 1]].copy(), q)
+    return cases
+
+
+@functools.lru_cache(maxsize=None)
+def build_golden():
+    with open(os.path.join(GOLDEN, "build_golden.json")) as fp:
+        return json.load(fp)
+
+
+def tree_fingerprint(nodes, idx):
+    return dict(num_nodes=int(len(nodes)), nodes_fnv=fnv(mask_leaf_axis(nodes)), indices_fnv=fnv(idx))

@@ -58,11 +58,18 @@ def test_device_build_options(opt):
     same_tree(m["vertices"], m["faces"], **opt)
 
 
-def soup(n, seed, scale=1.0, offset=0.0, tri=0.05):
-    rng = np.random.default_rng(seed)
-    c = rng.uniform(-1, 1, (n, 1, 3))
-    v = ((c + rng.uniform(-tri, tri, (n, 3, 3))) * scale + offset).reshape(-1, 3)
-    return v.astype(np.float32).astype(np.float64), np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+soup = T.soup
+
+
+@pytest.mark.parametrize("name", sorted(T.build_cases()))
+def test_device_builder_edge_cases_match_the_reference_tree(name):
+    """Fingerprints of the reference's own trees for these inputs (tests/golden/build_golden.json)."""
+    v, f = T.build_cases()[name]
+    g = T.build_golden()[name]
+    db = M.HostBVH.build_device(v, f)
+    assert T.tree_fingerprint(*db.arrays()) == {k: g[k] for k in ("num_nodes", "nodes_fnv", "indices_fnv")}
+    assert db.stats() == g["stats"]
+    db.close()
 
 
 @pytest.mark.parametrize("case", [
