@@ -132,3 +132,40 @@ def build_golden():
 
 def tree_fingerprint(nodes, idx):
     return dict(num_nodes=int(len(nodes)), nodes_fnv=fnv(mask_leaf_axis(nodes)), indices_fnv=fnv(idx))
+
+
+def edge_case_rays(mesh="cornellbox"):
+    """Axis-parallel directions (1/0 = inf, 0*inf = NaN in the slab test), -0.0 components, origins exactly on box
+    planes / corners, rays along mesh edges, through vertices and in a triangle's plane, un-normalised, zero and huge
+    values.  Shared by the oracle-vs-reference test (CPU) and the GPU-vs-oracle test."""
+    _, ob = oracle_scene(mesh)
+    m = load_mesh(mesh)
+    v, f = m["vertices"], m["faces"]
+    rng = np.random.default_rng(3)
+    rays = []
+    axes = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], np.float64)
+    for vert in v[rng.choice(len(v), 300, replace=False)]:   # through vertices, axis-parallel
+        for a in axes:
+            rays.append(np.concatenate([vert - 50.0 * a, a]))
+            rays.append(np.concatenate([vert - 50.0 * a, np.where(a == 0, -0.0, a)]))   # -0.0 components
+    nodes, _ = ob.arrays()
+    for nd in nodes[:60]:                                     # origins exactly on box planes / corners
+        for a in axes:
+            rays.append(np.concatenate([nd["bmin"], a]))
+            rays.append(np.concatenate([nd["bmax"], -a]))
+            rays.append(np.concatenate([[nd["bmin"][0], 0.3, 40.0], [0.0, 0.0, -1.0]]))
+    for tri in f[rng.choice(len(f), 300, replace=False)]:     # along edges and at edge midpoints
+        p0, p1, p2 = v[tri[0]], v[tri[1]], v[tri[2]]
+        mid = 0.5 * (p0 + p1)
+        org = np.array([0.0, 0.0, 20.0])
+        for tgt in (p0, mid, (p0 + p1 + p2) / 3.0):
+            d = tgt - org
+            rays.append(np.concatenate([org, d / np.linalg.norm(d)]))
+            rays.append(np.concatenate([org, d]))             # un-normalised direction
+        e = p1 - p0
+        if np.linalg.norm(e) > 0:
+            rays.append(np.concatenate([p0 - e, e]))          # in the triangle's plane (det ~ 0)
+    rays.append(np.array([0, 0, 20, 0, 0, 0], np.float64))    # zero direction: inv = inf, nothing hit
+    rays.append(np.array([0, 0, 20, 0, 0, -0.0], np.float64))
+    rays.append(np.array([1e300, 0, 0, -1, 0, 0], np.float64))
+    return np.array(rays)

@@ -84,6 +84,23 @@ def test_traverse_bit_identical_on_random_rays(seed, n):
         assert np.ascontiguousarray(o["isects"][fld][m]).tobytes() == np.ascontiguousarray(r["isects"][fld][m]).tobytes(), fld
 
 
+def test_traverse_bit_identical_on_edge_case_rays():
+    """The very ray set the GPU parity test uses (tests/common.py::edge_case_rays: inf / NaN slabs, -0.0 components,
+    origins on box planes, rays in a triangle's plane, zero and huge values): oracle == reference here, GPU == oracle
+    in tests/test_gpu_parity.py::test_edge_case_rays."""
+    m = T.load_mesh("cornellbox")
+    rs = R.RefScene.from_arrays(m["vertices"], m["faces"], m["material_ids"], m["normals"], m["uvs"])
+    rs.build()
+    _, ob = T.oracle_scene("cornellbox")
+    rays = T.edge_case_rays("cornellbox")
+    with np.errstate(all="ignore"):
+        r = rs.trace(rays, full=True)
+        o = ob.trace(rays, full=True)
+    T.assert_hits_equal(o["hits"], r["hits"], "oracle vs reference, edge cases")
+    assert np.array_equal(r["mask"], o["mask"]) and r["mask"].sum() > 100
+    rs.close()
+
+
 def test_camera_frame_bit_identical_incl_quaternions():
     rng = np.random.default_rng(21)
     cases = [((0, 0, 20), (0, 0, 0), (0, 1, 0), 45.0, (0, 0, 0, 0), 512, 512),
