@@ -4,7 +4,9 @@
 // records (layout.h) and uploads it together with the verbatim mesh arrays.
 #include "scene.h"
 
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -40,13 +42,28 @@ int relayout_bvh(Relayout &out, const double *vertices, size_t nverts, const uin
   };
   out = Relayout();
   if (nnodes == 0) return MB200_OK; // empty scene: every ray misses
+  const char *tenv = getenv("MB200_BUILD_TIMING");
+  const bool timing = tenv && atoi(tenv) != 0;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto stage = [&](const char *name) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[mb200 relayout] %-10s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   if (!nodes || !indices || !vertices || !faces) return fail("null mesh/BVH array");
   if (nnodes >= 0xFFFFFFF0ull || nindices >= 0xFFFFFFF0ull) return fail("BVH too large for 32-bit references");
-  for (size_t i = 0; i < nindices; i++)
-    if (indices[i] >= nfaces) return fail("BVH index array references a face out of range");
-  for (size_t i = 0; i < 3 * nfaces; i++)
-    if (faces[i] >= nverts) return fail("face references a vertex out of range");
+  {
+    bool idx_ok = true, face_ok = true;
+#pragma omp parallel for schedule(static) reduction(&& : idx_ok) if (nindices > (1u << 16))
+    for (long i = 0; i < (long)nindices; i++) idx_ok = idx_ok && indices[i] < nfaces;
+#pragma omp parallel for schedule(static) reduction(&& : face_ok) if (nfaces > (1u << 15))
+    for (long i = 0; i < (long)(3 * nfaces); i++) face_ok = face_ok && faces[i] < nverts;
+    if (!idx_ok) return fail("BVH index array references a face out of range");
+    if (!face_ok) return fail("face references a vertex out of range");
+  }
 
+  stage("validate");
   // ---- pass 1: walk the tree (pre-order, explicit stack), validate, number the branches
   std::vector<uint32_t> pair_of(nnodes, 0xFFFFFFFFu);
   std::vector<unsigned char> seen(nnodes, 0);
@@ -77,10 +94,11 @@ int relayout_bvh(Relayout &out, const double *vertices, size_t nverts, const uin
   }
   if (max_depth > 500) return fail("BVH deeper than 500 levels (reference stack is 512, bvh_accel.cc:548)");
 
+  stage("walk");
   // ---- pass 2: emit PairNodes
   out.empty = false;
   out.depth = max_depth;
-  out.pairs.resize(npairs);
+  if (!out.pairs.resize(npairs)) return fail("out of host memory");
   auto child_ref = [&](uint32_t node, uint32_t &ref, uint32_t &cnt) {
     const mb200_bvh_node &c = nodes[node];
     if (c.flag == 0) {
@@ -92,7 +110,8 @@ int relayout_bvh(Relayout &out, const double *vertices, size_t nverts, const uin
     }
   };
   child_ref(0, out.root_ref, out.root_cnt);
-  for (size_t i = 0; i < nnodes; i++) {
+#pragma omp parallel for schedule(static) if (nnodes > (1u << 14))
+  for (long i = 0; i < (long)nnodes; i++) {
     if (!seen[i] || nodes[i].flag != 0) continue;
     PairNode &p = out.pairs[pair_of[i]];
     memset(&p, 0, sizeof(p));
@@ -107,11 +126,13 @@ int relayout_bvh(Relayout &out, const double *vertices, size_t nverts, const uin
     p.axis = (uint32_t)nodes[i].axis;
   }
 
+  stage("pairs");
   // ---- triangle records in indices_ order
   out.f32 = choose_tri_f32(vertices, 3 * nverts);
   if (out.f32) {
-    out.tris32.resize(nindices);
-    for (size_t i = 0; i < nindices; i++) {
+    if (!out.tris32.resize(nindices)) return fail("out of host memory");
+#pragma omp parallel for schedule(static) if (nindices > (1u << 14))
+    for (long i = 0; i < (long)nindices; i++) {
       const uint32_t f = indices[i];
       TriRecordF32 &t = out.tris32[i];
       const double *a = vertices + 3 * (size_t)faces[3 * (size_t)f + 0];
@@ -123,8 +144,9 @@ int relayout_bvh(Relayout &out, const double *vertices, size_t nverts, const uin
       t.pad_ = 0;
     }
   } else {
-    out.tris64.resize(nindices);
-    for (size_t i = 0; i < nindices; i++) {
+    if (!out.tris64.resize(nindices)) return fail("out of host memory");
+#pragma omp parallel for schedule(static) if (nindices > (1u << 14))
+    for (long i = 0; i < (long)nindices; i++) {
       const uint32_t f = indices[i];
       TriRecordF64 &t = out.tris64[i];
       const double *a = vertices + 3 * (size_t)faces[3 * (size_t)f + 0];
@@ -135,6 +157,7 @@ int relayout_bvh(Relayout &out, const double *vertices, size_t nverts, const uin
       t.mat = material_ids ? material_ids[f] : 0xFFFFFFFFu;
     }
   }
+  stage("triangles");
   return MB200_OK;
 }
 

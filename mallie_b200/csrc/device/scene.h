@@ -4,6 +4,7 @@
 
 #include <cuda_runtime_api.h>
 
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -58,11 +59,43 @@ int scene_open(mb200_scene **out, int device, std::string *err);
 int scene_finish(mb200_scene *s, std::string *err);
 bool choose_tri_f32(const double *vertices, size_t count);
 
+// Uninitialised host array (std::vector would zero-fill tens of MB on one thread before the parallel loops that
+// write every byte touch them).
+template <class T> struct RawArray {
+  T *p = nullptr;
+  size_t n = 0;
+  RawArray() = default;
+  RawArray(const RawArray &) = delete;
+  RawArray &operator=(const RawArray &) = delete;
+  RawArray(RawArray &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr, o.n = 0; }
+  RawArray &operator=(RawArray &&o) noexcept {
+    if (this != &o) {
+      free(p);
+      p = o.p, n = o.n;
+      o.p = nullptr, o.n = 0;
+    }
+    return *this;
+  }
+  ~RawArray() { free(p); }
+  bool resize(size_t k) {
+    free(p);
+    p = k ? static_cast<T *>(aligned_alloc(128, ((k * sizeof(T) + 127) / 128) * 128)) : nullptr;
+    n = p ? k : 0;
+    return k == 0 || p != nullptr;
+  }
+  T *data() { return p; }
+  const T *data() const { return p; }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  T &operator[](size_t i) { return p[i]; }
+  const T &operator[](size_t i) const { return p[i]; }
+};
+
 // Host-side relayout only (no CUDA): exposed for CPU tests of the layout logic.
 struct Relayout {
-  std::vector<PairNode> pairs;
-  std::vector<TriRecordF32> tris32;
-  std::vector<TriRecordF64> tris64;
+  RawArray<PairNode> pairs;
+  RawArray<TriRecordF32> tris32;
+  RawArray<TriRecordF64> tris64;
   bool f32 = false;
   uint32_t root_ref = 0, root_cnt = 0;
   int depth = 0;
