@@ -245,6 +245,16 @@ typedef struct {
 int mb200_scene_timing(mb200_scene *scene, int enable);
 int mb200_scene_kernel_times(mb200_scene *scene, mb200_kernel_times *out);
 
+/* Measured ceilings of GPU `device` (diagnostics for roofline reports; a few hundred milliseconds, 2 GiB of
+ * scratch): FP64 pipe lane-operations / s (independent DADD / DMUL chains; the kernels are built without FMA
+ * contraction), bytes / s of 256-bit loads over an L2-resident 64 MB buffer, bytes / s (read + write) of a 1 GiB
+ * copy.  What the reference's timerutil is to its render loop (render.cc:630-707), for the device's limits. */
+typedef struct {
+  double fp64_lane_ops_per_s, l2_read_bytes_per_s, hbm_copy_bytes_per_s;
+  int sm_count;
+} mb200_peaks;
+int mb200_probe_peaks(int device, mb200_peaks *out);
+
 /* -------------------------------------------------------------------------
  * Queries: replace bool Scene::Trace(Intersection&, Ray&) (scene.cc:253-315) ->
  * BVHAccel::Traverse (bvh_accel.cc:773-844), batched.
@@ -329,6 +339,11 @@ typedef struct {
   uint64_t bounce_rays;   /* closest-hit queries for path continuation         */
   uint64_t shadow_rays;   /* occlusion queries                                 */
   uint64_t zombie_segments; /* post-escape segments resolved in closed form, NOT counted as rays */
+  /* Work the traversal kernel did for the frame, counted as mb200_counters counts it (box tests / triangles run
+   * through TriangleIsect), split by ray kind.  Filled for MB200_SHADER_PRIMARY_SHADOW / _PRIMARY_ONLY frames;
+   * 0 for the path-tracing shaders.  The shadow figures are what the any-hit walk really visited
+   * (it stops at the first t < tmax), i.e. at most the closest-hit Traverse counts that define the query. */
+  uint64_t camera_nodes_tested, camera_tris_tested, shadow_nodes_tested, shadow_tris_tested;
 } mb200_render_stats;
 
 void mb200_render_params_default(mb200_render_params *p, int width, int height);
@@ -360,6 +375,37 @@ int mb200_render_frame_multi(mb200_scene *const *scenes, int num_scenes, const m
                              int num_passes, int band_rows, float *image, int *count, mb200_render_stats *stats);
 /* Rows of the image a banded call owns (== y1-y0 when bands are disabled). */
 int mb200_band_local_rows(const mb200_render_params *params);
+
+/* -------------------------------------------------------------------------
+ * One process per GPU: every rank holds a replica of the scene, renders the row bands
+ * b with b % ranks == rank, and ONE NCCL all-gather per frame assembles the framebuffer; the rows are put in
+ * place by this library's own kernel on the scene's stream.  The reference has no counterpart (its MPI is an
+ * init / finalize stub, main.cc:213-236); what it replaces is DoMainConsole's single-process Render call
+ * (main_console.cc:57-75) when the host is launched once per GPU.
+ * NCCL is bound at run time (dlopen of libnccl.so.2); without it these return MB200_ERR_UNSUPPORTED.
+ * ---------------------------------------------------------------------- */
+typedef struct mb200_comm mb200_comm;
+#define MB200_COMM_ID_BYTES 128 /* == NCCL_UNIQUE_ID_BYTES */
+/* ncclGetUniqueId: rank 0 creates the id and hands it to the other ranks by any means it has (file, socket, MPI). */
+int mb200_comm_unique_id(unsigned char id[MB200_COMM_ID_BYTES]);
+/* ncclCommInitRank on the scene's GPU (collective: every rank calls it). */
+int mb200_comm_init(mb200_comm **out, mb200_scene *scene, int nranks, int rank, const unsigned char id[MB200_COMM_ID_BYTES]);
+/* Uses a communicator the host already has (nccl_comm is its ncclComm_t); it is not destroyed by mb200_comm_destroy. */
+int mb200_comm_adopt(mb200_comm **out, mb200_scene *scene, void *nccl_comm);
+int mb200_comm_size(const mb200_comm *comm);
+int mb200_comm_rank(const mb200_comm *comm);
+void mb200_comm_destroy(mb200_comm *comm);
+/* All-gather + row placement.  d_bands: this rank's compact band buffer (device, float[channels*width*
+ * mb200_band_local_rows()], what a band_compact render call wrote); image: float[channels*width*height], device
+ * pointer (enqueue-only on the scene's stream) or host pointer (blocks until readable), or NULL on a rank that
+ * does not need the assembled frame (it still takes part in the collective). */
+int mb200_gather_framebuffer(mb200_comm *comm, int width, int height, int channels, int band_rows, const float *d_bands,
+                             float *image);
+/* mb200_render_frame for a frame split over the communicator's ranks: renders this rank's bands of the whole-image
+ * `params` straight into the NCCL send buffer, gathers, and delivers the assembled frame to `image` (as above; count
+ * receives num_passes everywhere and may be NULL).  stats: this rank's share. */
+int mb200_render_frame_gathered(mb200_comm *comm, const mb200_render_params *params, int num_passes, int band_rows,
+                                float *image, int *count, mb200_render_stats *stats);
 
 #ifdef __cplusplus
 }

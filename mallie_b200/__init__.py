@@ -7,6 +7,6 @@ intersection, shading).  This package is only its ctypes face for tests and benc
 """
 from . import capi  # noqa: F401
 from .capi import (HostBVH, Scene, MallieB200Error, camera_frame, plane_from_bounds, device_count,  # noqa: F401
-                   load_mesh, load_config, Config, render_frame_multi,
+                   load_mesh, load_config, Config, render_frame_multi, Comm,
                    SHADER_PATHTRACE, SHADER_PRIMARY_SHADOW, SHADER_PRIMARY_ONLY, SHADER_PATHTRACE_ENV,
                    CAMERA_PINHOLE, CAMERA_ENV, CAMERA_ENV_STEREO)

@@ -36,11 +36,13 @@ EXPORTS = [
     "mb200_bvh_device_layout",
     "mb200_scene_create", "mb200_scene_destroy", "mb200_scene_bounds", "mb200_scene_device_bytes",
     "mb200_scene_stream", "mb200_scene_device", "mb200_scene_uses_f32_vertices", "mb200_scene_synchronize",
-    "mb200_scene_timing", "mb200_scene_kernel_times",
+    "mb200_scene_timing", "mb200_scene_kernel_times", "mb200_probe_peaks",
     "mb200_trace_closest", "mb200_trace_closest_full", "mb200_trace_occluded", "mb200_trace_closest_async",
     "mb200_camera_frame_build", "mb200_generate_rays", "mb200_generate_rays_env", "mb200_generate_rays_grid",
     "mb200_render_params_default", "mb200_plane_from_bounds", "mb200_render_pass", "mb200_render_accumulate",
     "mb200_render_frame", "mb200_render_frame_multi", "mb200_band_local_rows",
+    "mb200_comm_unique_id", "mb200_comm_init", "mb200_comm_adopt", "mb200_comm_size", "mb200_comm_rank",
+    "mb200_comm_destroy", "mb200_gather_framebuffer", "mb200_render_frame_gathered",
     "mb200_mesh_load_obj", "mb200_mesh_load_eson", "mb200_mesh_transform", "mb200_mesh_num_vertices",
     "mb200_mesh_num_faces", "mb200_mesh_vertices", "mb200_mesh_faces", "mb200_mesh_material_ids",
     "mb200_mesh_fv_normals", "mb200_mesh_fv_uvs", "mb200_mesh_destroy", "mb200_config_default", "mb200_config_load",
@@ -80,7 +82,8 @@ class RenderParams(C.Structure):
 
 class RenderStats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("bounce_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
-                ("zombie_segments", C.c_uint64)]
+                ("zombie_segments", C.c_uint64), ("camera_nodes_tested", C.c_uint64), ("camera_tris_tested", C.c_uint64),
+                ("shadow_nodes_tested", C.c_uint64), ("shadow_tris_tested", C.c_uint64)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
@@ -105,6 +108,11 @@ class KernelTimes(C.Structure):
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Peaks(C.Structure):
+    _fields_ = [("fp64_lane_ops_per_s", C.c_double), ("l2_read_bytes_per_s", C.c_double),
+                ("hbm_copy_bytes_per_s", C.c_double), ("sm_count", C.c_int)]
 
 
 class LayoutInfo(C.Structure):
@@ -171,6 +179,7 @@ def lib():
         L.mb200_scene_synchronize.argtypes = [vp]
         L.mb200_scene_timing.argtypes = [vp, i32]
         L.mb200_scene_kernel_times.argtypes = [vp, C.POINTER(KernelTimes)]
+        L.mb200_probe_peaks.argtypes = [i32, C.POINTER(Peaks)]
         L.mb200_trace_closest.argtypes = [vp, vp, sz, vp, C.POINTER(Counters)]
         L.mb200_trace_closest_full.argtypes = [vp, vp, sz, vp, vp]
         L.mb200_trace_occluded.argtypes = [vp, vp, vp, sz, vp, C.POINTER(Counters)]
@@ -187,6 +196,14 @@ def lib():
         L.mb200_band_local_rows.argtypes = [C.POINTER(RenderParams)]
         L.mb200_render_frame_multi.argtypes = [C.POINTER(vp), i32, C.POINTER(RenderParams), i32, i32, vp, vp,
                                                C.POINTER(RenderStats)]
+        L.mb200_comm_unique_id.argtypes = [vp]
+        L.mb200_comm_init.argtypes = [C.POINTER(vp), vp, i32, i32, vp]
+        L.mb200_comm_adopt.argtypes = [C.POINTER(vp), vp, vp]
+        L.mb200_comm_size.argtypes = [vp]
+        L.mb200_comm_rank.argtypes = [vp]
+        L.mb200_comm_destroy.argtypes = [vp]
+        L.mb200_gather_framebuffer.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+        L.mb200_render_frame_gathered.argtypes = [vp, C.POINTER(RenderParams), i32, i32, vp, vp, C.POINTER(RenderStats)]
         L.mb200_mesh_load_obj.argtypes = [C.POINTER(vp), C.c_char_p]
         L.mb200_mesh_load_eson.argtypes = [C.POINTER(vp), C.c_char_p]
         L.mb200_mesh_transform.argtypes = [vp, dbl, i32]
@@ -225,6 +242,13 @@ def launches_issued():
     return int(lib().mb200_launches_issued())
 
 
+def probe_peaks(device=0):
+    """mb200_probe_peaks: measured FP64-pipe, L2-read and HBM-copy ceilings of the GPU (diagnostics)."""
+    pk = Peaks()
+    check(lib().mb200_probe_peaks(device, C.byref(pk)))
+    return {k: getattr(pk, k) for k, _ in pk._fields_}
+
+
 def render_frame_multi(scenes, params, num_passes, band_rows=8, image=None, count=None, stats=True):
     """mb200_render_frame_multi: one frame over several single-GPU Scene replicas from one host thread."""
     if image is None:
@@ -236,6 +260,46 @@ def render_frame_multi(scenes, params, num_passes, band_rows=8, image=None, coun
     check(lib().mb200_render_frame_multi(arr, len(scenes), C.byref(params), num_passes, band_rows, _p(image), _p(count),
                                          C.byref(st) if stats else None))
     return image, count, (st.as_dict() if stats else None)
+
+
+class Comm:
+    """mb200_comm: the NCCL communicator of a frame split over one process per GPU (one Scene replica each)."""
+
+    def __init__(self, scene, nranks, rank, unique_id):
+        self.h = None
+        self.scene = scene
+        h = C.c_void_p()
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        check(lib().mb200_comm_init(C.byref(h), scene.h, nranks, rank, buf))
+        self.h, self.nranks, self.rank = h, nranks, rank
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_ubyte * 128)()
+        check(lib().mb200_comm_unique_id(buf))
+        return bytes(buf)
+
+    def gather(self, width, height, band_rows, d_bands, image, channels=3):
+        """d_bands: device address (int) of this rank's compact band buffer; image: device address, numpy array or None."""
+        check(lib().mb200_gather_framebuffer(self.h, width, height, channels, band_rows, _p(d_bands), _p(image)))
+
+    def render_frame(self, params, num_passes, band_rows, image=None, count=None, stats=False):
+        """mb200_render_frame_gathered: image / count may be device addresses (ints), numpy arrays or None."""
+        st = RenderStats()
+        check(lib().mb200_render_frame_gathered(self.h, C.byref(params), num_passes, band_rows, _p(image), _p(count),
+                                                C.byref(st) if stats else None))
+        return st.as_dict() if stats else None
+
+    def close(self):
+        if self.h:
+            lib().mb200_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def device_layout(vertices, faces, nodes, indices, material_ids=None):

@@ -5,6 +5,7 @@
 // is NO CPU fallback: without a GPU every compute entry returns MB200_ERR_NO_DEVICE.
 #include <cuda_runtime_api.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -100,6 +101,9 @@ int stage_out_enqueue(mb200_scene *s, mb200_scene::Staging &st, size_t bytes) {
   return MB200_OK;
 }
 
+// the traversal kernels index rays with 32-bit work items (trace_sm.cuh)
+constexpr size_t kMaxRaysPerCall = 0xFFFFFFE0ull;
+
 int read_counters(mb200_scene *s, unsigned long long out[4]) {
   CU(cudaMemcpyAsync(out, s->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
@@ -107,6 +111,10 @@ int read_counters(mb200_scene *s, unsigned long long out[4]) {
 }
 
 } // namespace
+
+namespace mb200 {
+int capi_set_error(int code, const std::string &msg) { return set_err(code, msg); }
+} // namespace mb200
 
 extern "C" {
 
@@ -417,6 +425,7 @@ int mb200_scene_synchronize(mb200_scene *scene) {
 // ---------------------------------------------------------------------------- queries
 int mb200_trace_closest_async(mb200_scene *s, const mb200_ray *d_rays, size_t n, mb200_hit *d_hits) {
   if (!s || (n && (!d_rays || !d_hits))) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  if (n > kMaxRaysPerCall) return set_err(MB200_ERR_INVALID_ARG, "more than 0xFFFFFFE0 rays in one call");
   if (n == 0) return MB200_OK;
   CU(cudaSetDevice(s->device));
   CU(mb200::launch_trace_closest(s->view, s->stack_cap, d_rays, n, d_hits, s->d_work, nullptr, s->stream, &s->timer));
@@ -425,6 +434,7 @@ int mb200_trace_closest_async(mb200_scene *s, const mb200_ray *d_rays, size_t n,
 
 int mb200_trace_closest(mb200_scene *s, const mb200_ray *rays, size_t n, mb200_hit *hits, mb200_counters *counters) {
   if (!s || (n && (!rays || !hits))) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  if (n > kMaxRaysPerCall) return set_err(MB200_ERR_INVALID_ARG, "more than 0xFFFFFFE0 rays in one call");
   if (counters) memset(counters, 0, sizeof(*counters));
   if (n == 0) return MB200_OK;
   CU(cudaSetDevice(s->device));
@@ -451,6 +461,7 @@ int mb200_trace_closest(mb200_scene *s, const mb200_ray *rays, size_t n, mb200_h
 int mb200_trace_closest_full(mb200_scene *s, const mb200_ray *rays, size_t n, mb200_isect *isects,
                              uint8_t *hit_mask) {
   if (!s || (n && (!rays || !isects))) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  if (n > kMaxRaysPerCall) return set_err(MB200_ERR_INVALID_ARG, "more than 0xFFFFFFE0 rays in one call");
   if (n == 0) return MB200_OK;
   CU(cudaSetDevice(s->device));
   const void *d_rays;
@@ -478,6 +489,7 @@ int mb200_trace_closest_full(mb200_scene *s, const mb200_ray *rays, size_t n, mb
 int mb200_trace_occluded(mb200_scene *s, const mb200_ray *rays, const double *tmax, size_t n, uint8_t *occluded,
                          mb200_counters *counters) {
   if (!s || (n && (!rays || !tmax || !occluded))) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  if (n > kMaxRaysPerCall) return set_err(MB200_ERR_INVALID_ARG, "more than 0xFFFFFFE0 rays in one call");
   if (counters) memset(counters, 0, sizeof(*counters));
   if (n == 0) return MB200_OK;
   CU(cudaSetDevice(s->device));
@@ -632,7 +644,7 @@ static int render_common(mb200_scene *s, const mb200_render_params *p, int num_p
       CU(cudaMemcpyAsync(d_cnt, src, cnt_bytes, cudaMemcpyHostToDevice, s->stream));
     }
   }
-  if (stats) CU(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream));
+  if (stats) CU(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), s->stream));
   CU(mb200::launch_frame(s->view, s->stack_cap, *p, num_passes, mode, d_img, d_cnt, s->frame_scratch,
                          stats ? s->d_counters : nullptr, s->stream, &s->timer, &s->pipe));
   if (img_kind != kDevice)
@@ -641,7 +653,7 @@ static int render_common(mb200_scene *s, const mb200_render_params *p, int num_p
   if (cnt_kind != kDevice)
     CU(cudaMemcpyAsync(cnt_kind == kPinned ? (void *)count : s->out1.pinned, d_cnt, cnt_bytes, cudaMemcpyDeviceToHost,
                        s->stream));
-  unsigned long long c[4] = {0, 0, 0, 0};
+  unsigned long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (stats || img_kind != kDevice || cnt_kind != kDevice) {
     if (stats) CU(cudaMemcpyAsync(c, s->d_counters, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
@@ -650,29 +662,33 @@ static int render_common(mb200_scene *s, const mb200_render_params *p, int num_p
   if (cnt_kind == kPageable) memcpy(count, s->out1.pinned, cnt_bytes);
   if (stats) {
     stats->primary_rays = c[0], stats->bounce_rays = c[1], stats->shadow_rays = c[2], stats->zombie_segments = c[3];
+    stats->camera_nodes_tested = c[4], stats->camera_tris_tested = c[5];
+    stats->shadow_nodes_tested = c[6], stats->shadow_tris_tested = c[7];
   }
   return MB200_OK;
 }
 
 // Can `dev` address memory of `root`?  Enables peer access on first use.
 static bool peer_ok(int dev, int root) {
-  static int state[64][64]; // 0 unknown, 1 yes, 2 no
+  static std::atomic<int> state[64][64]; // 0 unknown, 1 yes, 2 no; hosts may drive frames from several threads
   if (dev == root) return true;
   if (dev < 0 || root < 0 || dev >= 64 || root >= 64) return false;
-  if (state[dev][root] == 0) {
+  int st = state[dev][root].load(std::memory_order_acquire);
+  if (st == 0) { // two threads asking at once both probe; enabling twice is harmless (AlreadyEnabled)
     int can = 0;
-    state[dev][root] = 2;
+    st = 2;
     if (cudaDeviceCanAccessPeer(&can, dev, root) == cudaSuccess && can) {
       int cur = 0;
       cudaGetDevice(&cur);
       cudaSetDevice(dev);
       const cudaError_t e = cudaDeviceEnablePeerAccess(root, 0);
-      if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) state[dev][root] = 1;
+      if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) st = 1;
       cudaGetLastError();
       cudaSetDevice(cur);
     }
+    state[dev][root].store(st, std::memory_order_release);
   }
-  return state[dev][root] == 1;
+  return st == 1;
 }
 
 int mb200_render_frame_multi(mb200_scene *const *scenes, int n, const mb200_render_params *p, int num_passes,
@@ -728,11 +744,11 @@ int mb200_render_frame_multi(mb200_scene *const *scenes, int n, const mb200_rend
       rows = (size_t)mb200_band_local_rows(&pg);
       if (ensure(s->in0, rows * W * 3 * sizeof(float), false) != MB200_OK || ensure(s->in1, rows * W * sizeof(int), false) != MB200_OK) {
         cleanup();
-        return MB200_ERR_OUT_OF_MEMORY;
+        return set_err(MB200_ERR_OUT_OF_MEMORY, "mb200_render_frame_multi: band buffers: " + g_err);
       }
       t_img = (float *)s->in0.dev, t_cnt = (int *)s->in1.dev;
     }
-    if (e == cudaSuccess && stats) e = cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream);
+    if (e == cudaSuccess && stats) e = cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), s->stream);
     if (e == cudaSuccess)
       e = mb200::launch_frame(s->view, s->stack_cap, pg, num_passes, 2, t_img, t_cnt, s->frame_scratch,
                               stats ? s->d_counters : nullptr, s->stream, &s->timer, &s->pipe);
@@ -770,10 +786,12 @@ int mb200_render_frame_multi(mb200_scene *const *scenes, int n, const mb200_rend
   if (cnt_kind == kPageable) memcpy(count, root->out1.pinned, cnt_bytes);
   if (stats) {
     for (int g = 0; g < n; g++) {
-      unsigned long long c[4] = {0, 0, 0, 0};
+      unsigned long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       CU(cudaSetDevice(scenes[g]->device));
       CU(cudaMemcpy(c, scenes[g]->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
       stats->primary_rays += c[0], stats->bounce_rays += c[1], stats->shadow_rays += c[2], stats->zombie_segments += c[3];
+      stats->camera_nodes_tested += c[4], stats->camera_tris_tested += c[5];
+      stats->shadow_nodes_tested += c[6], stats->shadow_tris_tested += c[7];
     }
     CU(cudaSetDevice(root->device));
   }

@@ -18,7 +18,6 @@
 #include <cstring>
 
 #include "shade.cuh"
-#include "trace_mr.cuh"
 #include "trace_sm.cuh"
 #include "traverse.cuh"
 
@@ -29,14 +28,13 @@ namespace {
 constexpr int kBlock = 128; // threads per CTA of the traversal kernels
 
 // production configuration of the traversal state machine (A/B history: DESIGN.md §5)
-// (measured on B200, 1 M-triangle scene, 1080p 16 spp primary+shadow frame; history in DESIGN.md §5:
-//  4/2/16/5/32/0 = 28.98 ms -> 8 CTAs per SM at 64 registers 26.98 -> + refill 8 26.08 -> + no prefetch 23.05)
 constexpr int kRefillMin = 8;   // idle lanes that trigger a refill
-constexpr int kPolicy = 2;      // both step bodies every iteration
+constexpr int kShadeMin = 8;    // parked lanes that trigger a shade step (fused frames)
 constexpr int kSmemStack = 12;  // stack entries per thread kept in shared memory (24 KB per CTA)
+constexpr int kSmemStackFused = 10; // fused frames: two more 16-byte units per thread hold the lane slot
 constexpr int kMinBlocks = 8;   // resident CTAs per SM the register allocation targets (64 registers)
 constexpr unsigned kChunk = 32; // ray indices per atomicAdd
-constexpr int kVar = 1 + 2 + 8; // wide node loads, sign mask, no software prefetch (trace_sm.cuh)
+constexpr int kVar = 0;         // code-generation variants (trace_sm.cuh)
 
 __device__ __forceinline__ unsigned int lane_id() { return threadIdx.x & 31u; }
 
@@ -89,30 +87,19 @@ __global__ void __launch_bounds__(256) k_generate_rays_env(const __grid_constant
 // K2 / K4: the persistent-warp traversal state machine (trace_sm.cuh) as a kernel.
 // n_dev (nullable): the ray count lives in device memory (a queue filled by the previous kernel).
 // ---------------------------------------------------------------------------
-template <class IO, bool F32, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int POLICY, int S, int MINB, unsigned CHUNK, int VAR>
+template <class IO, int TRI, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int SHADE_MIN, int S, int MINB, unsigned CHUNK, int VAR>
 __global__ void __launch_bounds__(kBlock, MINB)
     k_trace_sm(const __grid_constant__ SceneView sc, const __grid_constant__ IO io, unsigned long long n,
                const unsigned int *__restrict__ n_dev, unsigned long long *__restrict__ work,
                unsigned long long *__restrict__ gcounters) {
-  extern __shared__ uint4 smem_stack[];
+  extern __shared__ uint4 smem_stack[]; // [S stack entries (+ 2 lane-slot units)][kBlock], column layout
   TravStack<S, CAP> st;
   st.init(smem_stack + threadIdx.x, kBlock);
+  LaneSlot slot;
+  slot.addr0 = st.sm_addr + (uint32_t)S * st.stride_bytes;
+  slot.addr1 = slot.addr0 + st.stride_bytes;
   if (n_dev) n = __ldg(n_dev);
-  trace_state_machine<IO, F32, S, CAP, ANYHIT, COUNT, REFILL_MIN, POLICY, CHUNK, VAR>(sc, io, n, work, st, gcounters);
-}
-
-// The K-rays-per-lane machine (trace_mr.cuh): ray slots in dynamic shared memory, MINB CTAs per SM.
-template <class IO, bool F32, int K, int S, bool ANYHIT, bool COUNT, int REFILL_MIN, int MINB, unsigned CHUNK>
-__global__ void __launch_bounds__(kBlock, MINB)
-    k_trace_mr(const __grid_constant__ SceneView sc, const __grid_constant__ IO io, unsigned long long n,
-               const unsigned int *__restrict__ n_dev, unsigned long long *__restrict__ work,
-               unsigned long long *__restrict__ gcounters) {
-  extern __shared__ uint4 smem_slots[];
-  SlotMem<K, S> sm;
-  sm.base = smem_slots + threadIdx.x;
-  sm.stride = kBlock;
-  if (n_dev) n = __ldg(n_dev);
-  trace_multi_ray<IO, F32, K, S, 64, ANYHIT, COUNT, REFILL_MIN, CHUNK>(sc, io, n, work, sm, gcounters);
+  trace_state_machine<IO, TRI, S, CAP, ANYHIT, COUNT, REFILL_MIN, SHADE_MIN, CHUNK, VAR>(sc, io, n, work, st, slot, gcounters);
 }
 
 // ---------------------------------------------------------------------------
@@ -454,27 +441,73 @@ __global__ void __launch_bounds__(1024) k_build_order(unsigned char *__restrict_
 }
 
 // stats of a batch -> the caller's accumulated stats (shadow rays traced = fill of the shadow queue)
+// tcount: the traversal launches' counters, camera [0..3] and shadow [4..7] (nodes, tris, rays, max stack)
 __global__ void k_add_stats(const unsigned long long *__restrict__ batch, const unsigned int *__restrict__ shadow_count,
-                            unsigned long long *__restrict__ total) {
+                            const unsigned long long *__restrict__ tcount, unsigned long long *__restrict__ total) {
   // batches of a frame run on two streams: accumulate atomically
   if (threadIdx.x < 4 && batch[threadIdx.x]) atomicAdd(&total[threadIdx.x], batch[threadIdx.x]);
   if (threadIdx.x == 2 && shadow_count && *shadow_count) atomicAdd(&total[2], (unsigned long long)*shadow_count);
+  const int map[4] = {0, 1, 4, 5}; // -> total[4..7] = camera nodes, camera tris, shadow nodes, shadow tris
+  if (threadIdx.x >= 4 && threadIdx.x < 8 && tcount[map[threadIdx.x - 4]]) atomicAdd(&total[threadIdx.x], tcount[map[threadIdx.x - 4]]);
+}
+
+// fused batch: counters of the state machine (trace_sm.cuh: [0..3] camera nodes, tris, rays, max stack; [4..6] shadow
+// nodes, tris, rays) -> the caller's stats [primary, bounce, shadow, zombie, camera nodes, camera tris, shadow
+// nodes, shadow tris]
+__global__ void k_add_stats_fused(const unsigned long long *__restrict__ batch, unsigned long long *__restrict__ total) {
+  const int map[8] = {2, -1, 6, -1, 0, 1, 4, 5};
+  const int t = threadIdx.x;
+  if (t < 8 && map[t] >= 0 && batch[map[t]]) atomicAdd(&total[t], batch[map[t]]);
+}
+
+// Traversal copies of the triangle records (layout.h: TriKind).  One thread per record.
+__global__ void __launch_bounds__(256) k_pad_tris(const void *__restrict__ src, int src_f32, uint32_t n, int kind,
+                                                  void *__restrict__ dst) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (kind == kTriF32x64) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(reinterpret_cast<const TriRecordF32 *>(src) + i);
+    uint4 *o = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(dst) + (size_t)i * 64u);
+    o[0] = p[0], o[1] = p[1], o[2] = p[2], o[3] = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  double v[12];
+  uint32_t face, mat;
+  if (src_f32) {
+    const TriRecordF32 t = reinterpret_cast<const TriRecordF32 *>(src)[i];
+    for (int c = 0; c < 3; c++) {
+      v[c] = (double)t.p0[c];
+      v[3 + c] = (double)t.p1[c] - (double)t.p0[c]; // TriangleIsect's e1, e2 (bvh_accel.cc:600-603)
+      v[6 + c] = (double)t.p2[c] - (double)t.p0[c];
+    }
+    face = t.face, mat = t.mat;
+  } else {
+    const TriRecordF64 t = reinterpret_cast<const TriRecordF64 *>(src)[i];
+    for (int c = 0; c < 3; c++) v[c] = t.p0[c], v[3 + c] = t.e1[c], v[6 + c] = t.e2[c];
+    face = t.face, mat = t.mat;
+  }
+  v[9] = __longlong_as_double((long long)(((unsigned long long)mat << 32) | face));
+  v[10] = v[11] = 0.0;
+  double *o = reinterpret_cast<double *>(reinterpret_cast<char *>(dst) + (size_t)i * 96u);
+  for (int c = 0; c < 12; c++) o[c] = v[c];
 }
 
 // ---------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------
-int g_num_sms = 0;
-std::atomic<int> g_launches{0}; // hosts may drive one scene per thread
+std::atomic<int> g_num_sms[64]; // per device ordinal; hosts may drive one scene per thread
+std::atomic<int> g_launches{0};
 
 int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = (dev >= 0 && dev < 64) ? dev : 0;
+  int n = g_num_sms[slot].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    g_num_sms[slot].store(n, std::memory_order_relaxed);
   }
-  return g_num_sms;
+  return n;
 }
 
 int env_int(const char *name, int dflt) {
@@ -513,25 +546,11 @@ cudaError_t persistent_grid(Kernel k, size_t smem, int minb, int grids[64], int 
 }
 
 // One persistent wave: a whole number of CTAs per SM.
-template <class IO, bool F32, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int POLICY, int S, int MINB, unsigned CHUNK, int VAR>
+template <class IO, int TRI, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int SHADE_MIN, int S, int MINB, unsigned CHUNK, int VAR>
 cudaError_t launch_sm(const SceneView &sc, const IO &io, size_t n, const unsigned int *n_dev,
                       unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
-  auto k = k_trace_sm<IO, F32, CAP, ANYHIT, COUNT, REFILL_MIN, POLICY, S, MINB, CHUNK, VAR>;
-  const size_t smem = (size_t)S * kBlock * sizeof(uint4);
-  static int grids[64]; // per instantiation, per device
-  int grid = 0;
-  const cudaError_t ge = persistent_grid(k, smem, MINB, grids, &grid);
-  if (ge != cudaSuccess) return ge;
-  k<<<grid, kBlock, smem, s>>>(sc, io, (unsigned long long)n, n_dev, work, counters);
-  g_launches++;
-  return cudaGetLastError();
-}
-
-template <class IO, bool F32, int K, int S, bool ANYHIT, bool COUNT, int REFILL_MIN, int MINB, unsigned CHUNK>
-cudaError_t launch_mr(const SceneView &sc, const IO &io, size_t n, const unsigned int *n_dev,
-                      unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
-  auto k = k_trace_mr<IO, F32, K, S, ANYHIT, COUNT, REFILL_MIN, MINB, CHUNK>;
-  const size_t smem = (size_t)K * (kSlotUnits + S) * kBlock * sizeof(uint4);
+  auto k = k_trace_sm<IO, TRI, CAP, ANYHIT, COUNT, REFILL_MIN, SHADE_MIN, S, MINB, CHUNK, VAR>;
+  const size_t smem = (size_t)(S + (IO::kFused ? 2 : 0)) * kBlock * sizeof(uint4);
   static int grids[64]; // per instantiation, per device
   int grid = 0;
   const cudaError_t ge = persistent_grid(k, smem, MINB, grids, &grid);
@@ -542,108 +561,60 @@ cudaError_t launch_mr(const SceneView &sc, const IO &io, size_t n, const unsigne
 }
 
 // Picks the kernel instantiation: production parameters, or (development builds, -DMB200_DEV_VARIANTS)
-// the A/B variants selected with MB200_TRACE_POLICY / MB200_TRACE_OCC / MB200_TRACE_CHUNK.
-template <class IO, bool F32, int CAP, bool ANYHIT, bool COUNT>
+// the A/B variants selected with MB200_TRACE_VAR.
+template <class IO, int TRI, int CAP, bool ANYHIT, bool COUNT>
 cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const unsigned int *n_dev,
                               unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
-#define MB200_SM(R, P, S, B, C, V) launch_sm<IO, F32, CAP, ANYHIT, COUNT, R, P, S, B, C, V>(sc, io, n, n_dev, work, counters, s)
+  constexpr int S = IO::kFused ? kSmemStackFused : kSmemStack;
+#define MB200_SM(R, H, SS, B, C, V) launch_sm<IO, TRI, CAP, ANYHIT, COUNT, R, H, SS, B, C, V>(sc, io, n, n_dev, work, counters, s)
 #ifdef MB200_DEV_VARIANTS
-  if (CAP <= 64) {
-    static const int mr = env_int("MB200_TRACE_MR", 0); // K * 100 + CTAs per SM * 10 + (refill >= 16 ? 1 : 0)
-#define MB200_MR(K, S, R, B) launch_mr<IO, F32, K, S, ANYHIT, COUNT, R, B, 32>(sc, io, n, n_dev, work, counters, s)
-    if (mr == 440) return MB200_MR(4, 0, 16, 4);
-    if (mr == 333) return MB200_MR(3, 3, 16, 4);
-    if (mr == 327) return MB200_MR(2, 7, 16, 4);
-    if (mr == 325) return MB200_MR(2, 5, 16, 5);
-    if (mr == 336) return MB200_MR(3, 6, 16, 3);
-    if (mr == 248) return MB200_MR(4, 8, 16, 2);
-#undef MB200_MR
-  }
-  if (!COUNT && CAP <= 64) {
-    // -1 = not set: only an explicitly requested variant replaces the production instantiation
-    static const int policy = env_int("MB200_TRACE_POLICY", -1), occ = env_int("MB200_TRACE_OCC", -1),
-                     chunk = env_int("MB200_TRACE_CHUNK", -1), refill = env_int("MB200_TRACE_REFILL", -1),
-                     var = env_int("MB200_TRACE_VAR", -1);
-    if (policy == 0) return MB200_SM(8, 0, 12, 8, 32, 11);
-    if (policy == 3) return MB200_SM(8, 3, 12, 8, 32, 11);
-    if (policy == 4) return MB200_SM(8, 4, 12, 8, 32, 11);
-    if (policy == 6) return MB200_SM(8, 6, 12, 8, 32, 11);
-    if (occ == 4) return MB200_SM(4, 2, 16, 4, 32, 0);
-    if (occ == 6) return MB200_SM(4, 2, 16, 6, 32, 0);
-    if (occ == 8) return MB200_SM(4, 2, 12, 8, 32, 0);
-    if (occ == 83) return MB200_SM(4, 2, 12, 8, 32, 3);
-    if (occ == 88) return MB200_SM(8, 2, 12, 8, 32, 3);
-    if (occ == 9) return MB200_SM(4, 2, 12, 9, 32, 3);
-    if (occ == 10) return MB200_SM(4, 2, 10, 10, 32, 3);
-    if (occ == 108) return MB200_SM(8, 2, 10, 10, 32, 3);
-    if (occ == 12) return MB200_SM(4, 2, 8, 12, 32, 3);
-    if (chunk == 64) return MB200_SM(4, 2, 16, 5, 64, 0);
-    if (refill == 1) return MB200_SM(1, 2, 16, 5, 32, 0);
-    if (refill == 8) return MB200_SM(8, 2, 16, 5, 32, 0);
-    // on top of refill 8 / 12 smem stack entries / 8 CTAs per SM / wide nodes + sign mask:
-    if (var == 3) return MB200_SM(8, 2, 12, 8, 32, 3);
-    if (var == 7) return MB200_SM(8, 2, 12, 8, 32, 3 + 4);
-    if (var == 11) return MB200_SM(8, 2, 12, 8, 32, 3 + 8);
-    if (var == 19) return MB200_SM(8, 2, 12, 8, 32, 3 + 16);
-    if (var == 35) return MB200_SM(8, 2, 12, 8, 32, 3 + 32);
-    if (var == 67) return MB200_SM(8, 2, 12, 8, 32, 3 + 64);
-    if (var == 87) return MB200_SM(8, 2, 12, 8, 32, 3 + 4 + 16 + 64);
-    if (var == 119) return MB200_SM(8, 2, 12, 8, 32, 3 + 4 + 16 + 32 + 64);
-    if (var == 123) return MB200_SM(8, 2, 12, 8, 32, 3 + 8 + 16 + 32 + 64);
-    // stack split between shared memory and (L1-cached) local memory, no prefetch
-    if (var == 2009) return MB200_SM(8, 2, 0, 9, 32, 11);
-    if (var == 2129) return MB200_SM(8, 2, 12, 9, 32, 11);
-    if (var == 2010) return MB200_SM(8, 2, 0, 10, 32, 11);
-    if (var == 3016) return MB200_SM(8, 2, 12, 8, 16, 11);
-    if (var == 3008) return MB200_SM(8, 2, 12, 8, 8, 11);
-    if (var == 3116) return MB200_SM(16, 2, 12, 8, 16, 11);
-    if (var == 3404) return MB200_SM(4, 2, 12, 8, 4, 11);
-    if (var == 1035) return MB200_SM(8, 2, 12, 8, 32, 11 + 1024);
-    if (var == 267) return MB200_SM(8, 2, 12, 8, 32, 11 + 256);
-    if (var == 523) return MB200_SM(8, 2, 12, 8, 32, 11 + 512);
-    if (var == 1100) return MB200_SM(8, 2, 0, 8, 32, 11);
-    if (var == 1104) return MB200_SM(8, 2, 4, 8, 32, 11);
-    if (var == 1108) return MB200_SM(8, 2, 8, 8, 32, 11);
-    if (var == 1116) return MB200_SM(8, 2, 16, 8, 32, 11);
-    if (var == 1109) return MB200_SM(8, 2, 8, 9, 32, 11);
-    if (var == 1110) return MB200_SM(8, 2, 8, 10, 32, 11);
-    if (var == 1143) return MB200_SM(8, 2, 12, 8, 32, 11 + 32);
-    if (var == 1127) return MB200_SM(8, 2, 12, 8, 32, 11 + 16);
-    if (var == 1112) return MB200_SM(12, 2, 12, 8, 32, 11);
-    if (var == 1164) return MB200_SM(8, 2, 12, 8, 64, 11);
+  if constexpr (!COUNT && CAP <= 64) {
+    static const int var = env_int("MB200_TRACE_VAR", -1); // -1 = not set: the production instantiation
+    if (var == 1) return MB200_SM(kRefillMin, kShadeMin, S, kMinBlocks, kChunk, kVarOctant);
+    if (var == 104) return MB200_SM(kRefillMin, 4, S, kMinBlocks, kChunk, 0);      // shade step at 4 parked lanes
+    if (var == 116) return MB200_SM(kRefillMin, 16, S, kMinBlocks, kChunk, 0);     // ... at 16
+    if (var == 212) return MB200_SM(12, 12, S, kMinBlocks, kChunk, 0);             // refill and shade at 12
+    if (var == 308) return MB200_SM(kRefillMin, kShadeMin, 8, kMinBlocks, kChunk, 0);  // 8 stack entries in shared memory
+    if (var == 306) return MB200_SM(kRefillMin, kShadeMin, 6, kMinBlocks, kChunk, 0);  // 6 (more L1)
   }
 #endif
-  return MB200_SM(kRefillMin, kPolicy, kSmemStack, kMinBlocks, kChunk, kVar);
+  return MB200_SM(kRefillMin, kShadeMin, S, kMinBlocks, kChunk, kVar);
 #undef MB200_SM
 }
 
-// dispatch on the scene's triangle record kind and on the stack capacity the tree needs
+// dispatch on the triangle records the traversal reads and on the stack capacity the tree needs.  The padded
+// record kinds exist for the frame kernels and the plain queries alike; counting launches (diagnostics) use them too.
+template <class IO, bool ANYHIT, bool COUNT>
+cudaError_t launch_trace_kind(const SceneView &sc, int stack_cap, const IO &io, size_t n, const unsigned int *n_dev,
+                              unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
+#define MB200_KIND(K)                                                                                        \
+  case K:                                                                                                    \
+    return stack_cap <= 64 ? launch_sm_variant<IO, K, 64, ANYHIT, COUNT>(sc, io, n, n_dev, work, counters, s) \
+                           : launch_sm_variant<IO, K, 512, ANYHIT, COUNT>(sc, io, n, n_dev, work, counters, s);
+  switch (sc.tri_kind) {
+    MB200_KIND(kTriF32)
+    MB200_KIND(kTriF64)
+#ifdef MB200_DEV_VARIANTS // A/B: padded traversal records (MB200_TRI_LAYOUT, scene.cc)
+    MB200_KIND(kTriF32x64)
+    MB200_KIND(kTriF64x96)
+#endif
+  }
+#undef MB200_KIND
+  return cudaErrorInvalidValue;
+}
+
 template <class IO, bool ANYHIT>
 cudaError_t launch_trace(const SceneView &sc, int stack_cap, const IO &io, size_t n, const unsigned int *n_dev,
                          unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
-  if (counters) {
-    if (sc.tri_f32)
-      return stack_cap <= 64 ? launch_sm_variant<IO, true, 64, ANYHIT, true>(sc, io, n, n_dev, work, counters, s)
-                             : launch_sm_variant<IO, true, 512, ANYHIT, true>(sc, io, n, n_dev, work, counters, s);
-    return stack_cap <= 64 ? launch_sm_variant<IO, false, 64, ANYHIT, true>(sc, io, n, n_dev, work, counters, s)
-                           : launch_sm_variant<IO, false, 512, ANYHIT, true>(sc, io, n, n_dev, work, counters, s);
-  }
-  if (sc.tri_f32)
-    return stack_cap <= 64 ? launch_sm_variant<IO, true, 64, ANYHIT, false>(sc, io, n, n_dev, work, counters, s)
-                           : launch_sm_variant<IO, true, 512, ANYHIT, false>(sc, io, n, n_dev, work, counters, s);
-  return stack_cap <= 64 ? launch_sm_variant<IO, false, 64, ANYHIT, false>(sc, io, n, n_dev, work, counters, s)
-                         : launch_sm_variant<IO, false, 512, ANYHIT, false>(sc, io, n, n_dev, work, counters, s);
+  if (counters) return launch_trace_kind<IO, ANYHIT, true>(sc, stack_cap, io, n, n_dev, work, counters, s);
+  return launch_trace_kind<IO, ANYHIT, false>(sc, stack_cap, io, n, n_dev, work, nullptr, s);
 }
 
-// frame-internal traces never count
+// frame-internal traces of the wavefront path never count
 template <class IO, bool ANYHIT>
 cudaError_t launch_trace_nocount(const SceneView &sc, int stack_cap, const IO &io, size_t n, const unsigned int *n_dev,
                                  unsigned long long *work, cudaStream_t s) {
-  if (sc.tri_f32)
-    return stack_cap <= 64 ? launch_sm_variant<IO, true, 64, ANYHIT, false>(sc, io, n, n_dev, work, nullptr, s)
-                           : launch_sm_variant<IO, true, 512, ANYHIT, false>(sc, io, n, n_dev, work, nullptr, s);
-  return stack_cap <= 64 ? launch_sm_variant<IO, false, 64, ANYHIT, false>(sc, io, n, n_dev, work, nullptr, s)
-                         : launch_sm_variant<IO, false, 512, ANYHIT, false>(sc, io, n, n_dev, work, nullptr, s);
+  return launch_trace_kind<IO, ANYHIT, false>(sc, stack_cap, io, n, n_dev, work, nullptr, s);
 }
 
 int flat_grid(size_t n, int block) {
@@ -656,6 +627,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 } // namespace
 
 int launches_issued() { return g_launches.load(); }
+void note_launch() { g_launches++; }
 
 // ---------------------------------------------------------------------------
 // KernelTimer
@@ -885,14 +857,22 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
   const FrameMap m0 = make_frame_map(p, p.pass, 1);
   const size_t tiles = frame_map_tiles(m0);
   if (tiles == 0 || num_passes < 1) return cudaSuccess;
-  if (tiles * 32 > 0xFFFFFFE0ull) return cudaErrorInvalidValue;
   const bool path = (p.shader == MB200_SHADER_PATHTRACE || p.shader == MB200_SHADER_PATHTRACE_ENV) && p.max_path_length > 1;
-  const bool shadow = p.shader == MB200_SHADER_PRIMARY_SHADOW;
+  // primary+shadow and primary-only samples need no path state, so the lane that traces the camera ray can shade it
+  // and trace its shadow ray itself (trace_sm.cuh: IOFrameFusedT; MB200_FRAME_FUSED=1).  Measured: one
+  // launch per batch and no hit-record / queue traffic, but the shade step runs inside the traversal kernel with
+  // ~8 of 32 lanes and costs more issue slots than the wavefront form's full-width shade kernel, which hides behind
+  // the other stream's traversal launch: 23.3 vs 21.8 ms per bench frame.  The wavefront form is the default.
+  static const bool fused_on = env_int("MB200_FRAME_FUSED", 0) != 0;
+  const bool fused = fused_on && (p.shader == MB200_SHADER_PRIMARY_SHADOW || p.shader == MB200_SHADER_PRIMARY_ONLY);
+  const bool shadow = p.shader == MB200_SHADER_PRIMARY_SHADOW && !fused;
+  const size_t item_limit = fused ? 0x7FFFFFE0ull : 0xFFFFFFE0ull; // fused: bit 31 of the item marks the shadow ray
+  if (tiles * 32 > item_limit) return cudaErrorInvalidValue;
 
   size_t per_batch = batch_item_budget() / (tiles * 32);
   if (per_batch < 1) per_batch = 1;
   if (per_batch > (size_t)num_passes) per_batch = (size_t)num_passes;
-  while (per_batch > 1 && tiles * 32 * per_batch > 0xFFFFFFE0ull) per_batch--;
+  while (per_batch > 1 && tiles * 32 * per_batch > item_limit) per_batch--;
   // Two streams need at least two batches to overlap one batch's drain with the other's kernels.
   static const bool pipeline_off = env_int("MB200_FRAME_PIPELINE", 1) == 0;
   const bool piped = pipe && !pipeline_off && num_passes >= 2;
@@ -901,8 +881,8 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
 
   // scratch carve-up (one slot per stream)
   const size_t n_traces = path ? (size_t)p.max_path_length : 2;
-  const size_t ctl_bytes = align_up(sizeof(unsigned long long) * (4 + n_traces) + sizeof(unsigned int) * (n_traces + 1), 256);
-  const size_t hits_bytes = align_up(max_items * sizeof(mb200_hit), 256);
+  const size_t ctl_bytes = align_up(sizeof(unsigned long long) * (16 + n_traces) + sizeof(unsigned int) * (n_traces + 1), 256);
+  const size_t hits_bytes = fused ? 0 : align_up(max_items * sizeof(mb200_hit), 256);
   const size_t contrib_bytes = align_up(max_items * sizeof(float), 256);
   const size_t queue_bytes = (path || shadow) ? align_up(max_items * sizeof(QRay), 256) : 0;
   const size_t state_bytes = path ? align_up(max_items * sizeof(PathState), 256) : 0;
@@ -948,8 +928,9 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
     const cudaStream_t st = slot ? pipe->aux : s;
     aux_used |= slot != 0;
     char *base = reinterpret_cast<char *>(scratch.base) + (size_t)slot * slot_bytes;
-    unsigned long long *bstats = reinterpret_cast<unsigned long long *>(base);           // [4]
-    unsigned long long *work = bstats + 4;                                               // [n_traces]
+    unsigned long long *bstats = reinterpret_cast<unsigned long long *>(base);           // [8]
+    unsigned long long *tcount = bstats + 8;  // [8] traversal counters: fused launch, or camera [0..3] + shadow [4..7]
+    unsigned long long *work = tcount + 8;                                               // [n_traces]
     unsigned int *qcount = reinterpret_cast<unsigned int *>(work + n_traces);            // [n_traces + 1]
     mb200_hit *hits = reinterpret_cast<mb200_hit *>(base + ctl_bytes);
     float *contrib = reinterpret_cast<float *>(base + ctl_bytes + hits_bytes);
@@ -966,24 +947,46 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
     const uint32_t items = (uint32_t)(tiles * 32 * (size_t)nb);
     if ((e = cudaMemsetAsync(base, 0, ctl_bytes, st)) != cudaSuccess) return e;
 
-    // camera rays: K1 fused into K2
-    const IOCamera cam{p, m, hits};
-    {
+    if (fused) {
+      // one launch per batch: camera ray -> shade -> shadow ray in the lane; only contrib[] leaves the kernel
       TimedScope ts(timer, kKCameraTrace, st);
-      e = launch_trace_nocount<IOCamera, false>(sc, stack_cap, cam, items, nullptr, work + 0, st);
+      if (p.camera_mode == MB200_CAMERA_PINHOLE) {
+        const IOFrameFusedT<true> io{p, m, contrib};
+        e = stats ? launch_trace_kind<IOFrameFusedT<true>, false, true>(sc, stack_cap, io, items, nullptr, work + 0, tcount, st)
+                  : launch_trace_kind<IOFrameFusedT<true>, false, false>(sc, stack_cap, io, items, nullptr, work + 0, nullptr, st);
+      } else {
+        const IOFrameFusedT<false> io{p, m, contrib};
+        e = stats ? launch_trace_kind<IOFrameFusedT<false>, false, true>(sc, stack_cap, io, items, nullptr, work + 0, tcount, st)
+                  : launch_trace_kind<IOFrameFusedT<false>, false, false>(sc, stack_cap, io, items, nullptr, work + 0, nullptr, st);
+      }
+      if (e != cudaSuccess) return e;
+    } else {
+      // camera rays: K1 fused into K2
+      {
+        TimedScope ts(timer, kKCameraTrace, st);
+        // a frame whose caller asked for stats also counts box / triangle tests (primary+shadow frames only)
+        unsigned long long *cc = (stats && !path) ? tcount : nullptr;
+        if (p.camera_mode == MB200_CAMERA_PINHOLE) {
+          const IOCameraT<true> cam{p, m, hits};
+          e = launch_trace<IOCameraT<true>, false>(sc, stack_cap, cam, items, nullptr, work + 0, cc, st);
+        } else {
+          const IOCameraT<false> cam{p, m, hits};
+          e = launch_trace<IOCameraT<false>, false>(sc, stack_cap, cam, items, nullptr, work + 0, cc, st);
+        }
+      }
+      if (e != cudaSuccess) return e;
+      {
+        TimedScope ts(timer, kKShade, st);
+        k_shade_primary<<<(items + 255) / 256, 256, 0, st>>>(sc, p, m, items, hits, contrib, queue[0], qcount + 0, states, bstats);
+      }
+      g_launches++;
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    if (e != cudaSuccess) return e;
-    {
-      TimedScope ts(timer, kKShade, st);
-      k_shade_primary<<<(items + 255) / 256, 256, 0, st>>>(sc, p, m, items, hits, contrib, queue[0], qcount + 0, states, bstats);
-    }
-    g_launches++;
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
     if (shadow) {
       const IOQueueShadow io{queue[0], contrib, m};
       TimedScope ts(timer, kKShadowTrace, st);
-      if ((e = launch_trace_nocount<IOQueueShadow, true>(sc, stack_cap, io, 0, qcount + 0, work + 1, st)) != cudaSuccess) return e;
+      if ((e = launch_trace<IOQueueShadow, true>(sc, stack_cap, io, 0, qcount + 0, work + 1, stats ? tcount + 4 : nullptr, st)) != cudaSuccess) return e;
     } else if (path) {
       for (int len = 2; len <= p.max_path_length; len++) {
         const int qi = len & 1; // segment `len` reads queue[qi], writes queue[qi ^ 1]
@@ -1012,7 +1015,8 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
     g_launches++;
     if (piped && (e = cudaEventRecord(pipe->resolved[batch & 1], st)) != cudaSuccess) return e;
     if (stats) {
-      k_add_stats<<<1, 32, 0, st>>>(bstats, shadow ? qcount : nullptr, stats);
+      if (fused) k_add_stats_fused<<<1, 32, 0, st>>>(tcount, stats);
+      else k_add_stats<<<1, 32, 0, st>>>(bstats, shadow ? qcount : nullptr, tcount, stats);
       g_launches++;
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -1024,6 +1028,13 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
     if ((e = cudaStreamWaitEvent(s, pipe->join, 0)) != cudaSuccess) return e;
   }
   return cudaSuccess;
+}
+
+cudaError_t launch_pad_tris(const void *src, int src_f32, size_t n, int kind, void *dst, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  k_pad_tris<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, src_f32, (uint32_t)n, kind, dst);
+  g_launches++;
+  return cudaGetLastError();
 }
 
 } // namespace mb200

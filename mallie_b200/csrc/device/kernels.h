@@ -87,15 +87,20 @@ void frame_scratch_release(FrameScratch &fs);
 // mode 0: image = last pass, count += passes (one pass: render.cc:673-679)
 // mode 1: image += passes, count += passes    (AccumImage, main_sdl.cc:138-143)
 // mode 2: image = sum of passes, count = passes (fresh frame; nothing read)
-// stats: device unsigned long long[4] primary, bounce, shadow, zombie (accumulated).
+// stats: device unsigned long long[8] primary, bounce, shadow, zombie, then (fused primary+shadow / primary-only
+// frames) camera nodes, camera triangles, shadow nodes, shadow triangles tested (accumulated).
 cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_params &p, int num_passes, int mode,
                          float *image, int *count, FrameScratch &scratch, unsigned long long *stats, cudaStream_t s,
                          KernelTimer *timer = nullptr, FramePipe *pipe = nullptr);
+
+// Traversal copy of the triangle records in a padded layout (layout.h: TriKind kTriF32x64 / kTriF64x96).
+cudaError_t launch_pad_tris(const void *src, int src_f32, size_t n, int kind, void *dst, cudaStream_t s);
 
 // Rows owned by one band index (see mb200_render_params::band_rows).
 int band_rows_owned(int rows, int band_rows, int count, int index);
 // Number of kernel launches issued by this library in this process (bench.py's gpu_launches).
 int launches_issued();
+void note_launch(); // a kernel of this library launched outside kernels.cu (gather.cu)
 
 } // namespace mb200
 

@@ -65,6 +65,21 @@ struct alignas(16) TriRecordF64 {
 };
 static_assert(sizeof(TriRecordF64) == 80, "TriRecordF64");
 
+// Traversal copies of the records, padded to a whole number of 32-byte sectors so that one triangle is two or
+// three 256-bit loads (the traversal kernel is bound by L1 wavefronts and issue slots, not by bytes: DESIGN.md §5):
+//   kTriF32x64  64 B : the f32 record + 16 B of padding                      -> 2 x LDG.256 instead of 3 x LDG.128
+//   kTriF64x96  96 B : p0, e1, e2 as doubles | faceID, materialID | padding  -> 3 x LDG.256, no conversions and no
+//                      edge subtractions in the kernel (e = (double)p1 - (double)p0 is formed once, by the layout
+//                      kernel, with the same single IEEE subtraction TriangleIsect performs, bvh_accel.cc:600-603)
+enum TriKind : int { kTriF32 = 0, kTriF64 = 1, kTriF32x64 = 2, kTriF64x96 = 3 };
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+    inline unsigned
+    tri_kind_bytes(int kind) {
+  return kind == kTriF32 ? 48u : kind == kTriF64 ? 80u : kind == kTriF32x64 ? 64u : 96u;
+}
+
 // ---- wavefront buffers of the frame kernels (kernels.cu) ------------------------------------------------
 // A queued secondary ray (shadow ray or path continuation): 64 B = four 16-byte vector loads.
 //   item  = the work item (sample of a pixel) the ray belongs to
@@ -100,6 +115,8 @@ struct SceneView {
   uint32_t num_tris;
   int empty;                 // no nodes at all: every ray misses
   int tri_f32;               // 1 = TriRecordF32
+  const void *trav_tris;     // what the traversal kernels read: `tris`, or a padded copy of it (TriKind)
+  int tri_kind;              // TriKind of trav_tris
   // verbatim mesh (mesh.h:7-18) for BuildIntersection
   const double *vertices;    // [3*nv]
   const uint32_t *faces;     // [3*nf]

@@ -226,18 +226,48 @@ int scene_open(mb200_scene **out, int device, std::string *err) {
   return MB200_OK;
 }
 
-// The work counter / statistics words, then wait for the uploads.
+// Which triangle records the traversal kernels read.  Default: the canonical ones (48-byte float-exact vertices
+// or 80-byte p0 + edges).  MB200_TRI_LAYOUT=64 | 96 (development builds: the kernels for them are compiled with
+// make DEV=1) makes a padded traversal copy on the device -- 64 B: the f32 record as two 256-bit loads; 96 B:
+// p0 + edges in double as three 256-bit loads.
+static int wanted_tri_kind(const SceneView &v) {
+  const char *e = getenv("MB200_TRI_LAYOUT");
+  const int want = e ? atoi(e) : 0;
+  if (want == 96) return kTriF64x96;
+  if (want == 64 && v.tri_f32) return kTriF32x64;
+  return v.tri_f32 ? kTriF32 : kTriF64;
+}
+
+// The work counter / statistics words and the traversal copy of the triangle records, then wait for the uploads.
 int scene_finish(mb200_scene *s, std::string *err) {
   void *d = nullptr;
-  cudaError_t e = cudaMalloc(&d, 8 * sizeof(unsigned long long));
+  cudaError_t e = cudaMalloc(&d, 16 * sizeof(unsigned long long));
   if (e != cudaSuccess) {
     if (err) *err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
     return MB200_ERR_CUDA;
   }
   s->allocs.push_back(d);
   s->d_work = (unsigned long long *)d;
-  s->d_counters = s->d_work + 1;
-  cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), s->stream);
+  s->d_counters = s->d_work + 1; // [8] traversal counters / render stats
+  cudaMemsetAsync(d, 0, 16 * sizeof(unsigned long long), s->stream);
+  SceneView &v = s->view;
+  v.trav_tris = v.tris;
+  v.tri_kind = v.tri_f32 ? kTriF32 : kTriF64;
+  const int kind = wanted_tri_kind(v);
+  if (!v.empty && v.num_tris && kind != v.tri_kind) {
+    void *pad = nullptr;
+    const size_t bytes = (size_t)v.num_tris * tri_kind_bytes(kind);
+    if ((e = cudaMalloc(&pad, bytes)) == cudaSuccess) {
+      s->allocs.push_back(pad);
+      s->device_bytes += bytes;
+      e = launch_pad_tris(v.tris, v.tri_f32, v.num_tris, kind, pad, s->stream);
+    }
+    if (e != cudaSuccess) {
+      if (err) *err = std::string("traversal triangle records: ") + cudaGetErrorString(e);
+      return e == cudaErrorMemoryAllocation ? MB200_ERR_OUT_OF_MEMORY : MB200_ERR_CUDA;
+    }
+    v.trav_tris = pad, v.tri_kind = kind;
+  }
   if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) {
     if (err) *err = std::string("upload: ") + cudaGetErrorString(e);
     return MB200_ERR_CUDA;
@@ -321,7 +351,7 @@ int scene_clone(mb200_scene **out, mb200_scene *src, int device, std::string *er
   const SceneView &sv = src->view;
   SceneView &v = s->view;
   v = sv;
-  v.nodes = nullptr, v.tris = nullptr, v.vertices = nullptr, v.faces = nullptr, v.fv_normals = nullptr, v.fv_uvs = nullptr;
+  v.nodes = nullptr, v.tris = nullptr, v.trav_tris = nullptr, v.vertices = nullptr, v.faces = nullptr, v.fv_normals = nullptr, v.fv_uvs = nullptr;
   auto copy = [&](const void *from, size_t bytes) -> const void * {
     if (st != MB200_OK || !from || bytes == 0) return nullptr;
     void *d = nullptr;

@@ -93,6 +93,8 @@ __device__ __forceinline__ void generate_env_ray(const double origin[3], int wid
 
 // The camera ray of sample `pass` of pixel (px, py): PathTrace's / PathTraceEnv's prologue
 // (render.cc:386-393, 524-533).  Leaves rng positioned after the two jitter draws.
+// PINHOLE_ONLY: the caller guarantees p.camera_mode == MB200_CAMERA_PINHOLE (the panorama code is not compiled in).
+template <bool PINHOLE_ONLY = false>
 __device__ __forceinline__ void camera_sample(const mb200_render_params &p, int px, int py, uint32_t pass,
                                               Xorshift128 &rng, double &ox, double &oy, double &oz, double &dx,
                                               double &dy, double &dz) {
@@ -104,7 +106,7 @@ __device__ __forceinline__ void camera_sample(const mb200_render_params &p, int 
     fu = (double)((float)px + ju); // int + float is a float add (render.cc:391)
     fv = (double)((float)py + jv);
   }
-  if (p.camera_mode == MB200_CAMERA_PINHOLE) {
+  if (PINHOLE_ONLY || p.camera_mode == MB200_CAMERA_PINHOLE) {
     ox = p.frame.origin[0], oy = p.frame.origin[1], oz = p.frame.origin[2];
     generate_ray(p.frame, fu, fv, dx, dy, dz);
   } else {

@@ -1,4 +1,5 @@
-// trace_sm.cuh -- the persistent-warp traversal state machine (K2 closest hit / K4 any hit).
+// trace_sm.cuh -- the persistent-warp traversal state machine (K2 closest hit / K4 any hit), and its
+// fused form that carries a sample from its camera ray through shading to its shadow ray in one lane.
 //
 // Why a state machine.  BVHAccel::Traverse (bvh_accel.cc:773-844) alternates two very different
 // pieces of arithmetic per ray -- slab tests on inner nodes and Moeller-Trumbore on leaf triangles --
@@ -7,21 +8,36 @@
 // whole 1..15-triangle loop of a leaf for whichever lanes happen to be there: measured on the
 // 1 M-triangle scene that kernel executed the triangle code with 4 of 32 lanes active and the whole
 // kernel with 8 (profiles/r1_trace_baseline.md).  Here every lane owns one ray and is in one of
-// three states,
+// these states,
 //     INNER  (rc == kBranch)   next step = one PairNode visit (two slab tests)
-//     LEAF   (1 <= rc < kIdle) next step = ONE triangle test of the rc left in the leaf
+//     LEAF   (1 <= rc < kShade) next step = ONE triangle test of the rc left in the leaf
+//     SHADE  (rc == kShade)    fused frames only: the lane's camera ray is finished and waits for the
+//                              warp's next shade step (BuildIntersection + the shadow-ray set-up)
 //     IDLE   (rc == kIdle)     no ray
-// and every warp iteration performs at most one step per lane, so no lane ever waits for another
-// lane's leaf loop.  Lanes whose ray has finished are refilled from a per-warp pool of consecutive
-// ray indices (one atomicAdd per CHUNK rays), compacted with __ballot_sync/__popc over the idle
-// lanes, so a warp never drains.  POLICY selects how the two step bodies are scheduled:
-//     2 (production) both bodies every iteration, each under its own predicate ("if-if");
-//     0              a warp vote picks the body more lanes are waiting for, the others wait
-//                    (kept for A/B runs: fewer instructions, but measured slower -- DESIGN.md).
+// and every warp iteration performs at most one step per lane (both step bodies every iteration, each
+// under its own predicate), so no lane ever waits for another lane's leaf loop.  Lanes whose ray has
+// finished are refilled from a per-warp pool of consecutive ray indices (one atomicAdd per CHUNK
+// rays), compacted with __ballot_sync/__popc over the idle lanes, so a warp never drains.
+//
+// Fused frames (IO::kFused; render.cc:401-426 for one sample).  The wavefront form of a primary+shadow
+// frame wrote a 32-byte hit record per camera ray, re-read it in a shade kernel that regenerated the
+// camera ray, queued a 64-byte shadow ray and traced the queue in a second launch.  Here the lane
+// that traced the camera ray keeps it: accepted hits go to a 32-byte per-lane slot in shared memory,
+// a finished camera ray parks in SHADE, and once enough lanes of the warp are parked (or idle) one
+// shade step runs BuildIntersection and the shadow-ray set-up for all of them; the lane then walks
+// the tree again as an any-hit ray and deposits its sample's contribution.  Nothing but contrib[item]
+// (4 bytes) leaves the kernel.
 //
 // Exactness.  The per-ray sequence of node visits, triangle tests and pop-time culling decisions is
 // the reference's (proof sketch in traverse.cuh); only the interleaving BETWEEN rays changes, and
 // rays do not interact.  Hit records stay bit-identical.
+//
+// Any hit, exactly.  "occluded" is DEFINED as "closest-hit Traverse returns t < tmax".  An any-hit ray
+// therefore runs the closest-hit walk unchanged (hitT starts at DBL_MAX, every accepted triangle lowers
+// it, boxes are culled against it) and stops at the first accepted t < tmax: up to that point its state
+// equals the closest-hit walk's, whose hitT only decreases afterwards, so the two agree on every input.
+// (Round 1 started hitT at tmax, which also culls boxes beyond tmax; that is the same predicate only
+// while the boxes' kEPS padding dominates the slab test's rounding, i.e. not for coordinates >~ 1e3.)
 #ifndef MALLIE_B200_TRACE_SM_CUH_
 #define MALLIE_B200_TRACE_SM_CUH_
 
@@ -30,19 +46,10 @@
 
 namespace mb200 {
 
-constexpr uint32_t kIdle = 0xFFFFFFFEu; // lane holds no ray
+constexpr uint32_t kIdle = 0xFFFFFFFEu;  // lane holds no ray
+constexpr uint32_t kShade = 0xFFFFFFFDu; // fused frames: camera ray finished, waiting for the shade step
 constexpr uint32_t kFullMask = 0xFFFFFFFFu;
-
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
-// All 128-byte lines of a leaf's triangle records (<= 15 records of 48 or 80 bytes: at most 10 lines).
-template <bool F32> __device__ __forceinline__ void prefetch_leaf(const void *tris, uint32_t ref, uint32_t cnt) {
-  const size_t rec = F32 ? sizeof(TriRecordF32) : sizeof(TriRecordF64);
-  const char *p = reinterpret_cast<const char *>(tris) + (size_t)ref * rec;
-  const char *end = p + (size_t)cnt * rec;
-  for (const char *q = reinterpret_cast<const char *>(reinterpret_cast<size_t>(p) & ~(size_t)127); q < end; q += 128)
-    prefetch_l1(q);
-}
+constexpr uint32_t kShadowBit = 0x80000000u; // fused frames: bit 31 of `item` = the lane's ray is the sample's shadow ray
 
 __device__ __forceinline__ void store_hit(mb200_hit *dst, double t, double u, double v, uint32_t face, uint32_t mat) {
   double2 *o = reinterpret_cast<double2 *>(dst);
@@ -53,38 +60,27 @@ __device__ __forceinline__ void store_hit(mb200_hit *dst, double t, double u, do
 __device__ __forceinline__ void store_miss(mb200_hit *dst) { store_hit(dst, DBL_MAX, 0.0, 0.0, 0xFFFFFFFFu, 0xFFFFFFFFu); }
 
 // ---- ray sources / result sinks -------------------------------------------------------------------
-// load(i, ...) returns false when item i carries no ray; otherwise it yields the ray and the initial
-// hitT and writes the "miss" result.  accept() is called on every accepted triangle (a handful per
-// ray: traversal is front to back) and overwrites the result in place, so u, v, faceID and
-// materialID never occupy registers between steps.  finish() ends the ray.
-
-// Every source also has a per-thread chunk context (empty unless the source can share work between the
-// rays of one 32-item chunk): prepare(ctx, base) is called by all lanes when the warp takes a new chunk.
-struct NoChunk {};
-
-// K2 over a caller's ray buffer (mb200_trace_closest).
+// load(i, ...) returns false when item i carries no ray; otherwise it yields the ray and tmax (any-hit
+// sources; ignored for closest hit) and writes the "miss" result.  accept() is called on every accepted
+// triangle (a handful per ray: traversal is front to back) and overwrites the result in place, so u, v,
+// faceID and materialID never occupy registers between steps.  finish() ends the ray.
 struct NoCostMap {
   uint32_t hot_steps;
 };
 
+// K2 over a caller's ray buffer (mb200_trace_closest).
 struct IOClosest {
-  static constexpr bool kTracksCost = false;
+  static constexpr bool kTracksCost = false, kFused = false;
   NoCostMap m;
   __device__ __forceinline__ void mark_hot(uint32_t) const {}
-  typedef NoChunk Chunk;
-  __device__ __forceinline__ void prepare(Chunk &, uint32_t) const {}
-  __device__ __forceinline__ bool load(const Chunk &, uint32_t i, double &ox, double &oy, double &oz, double &dx,
-                                       double &dy, double &dz, double &t0) const {
-    return load(i, ox, oy, oz, dx, dy, dz, t0);
-  }
   const mb200_ray *rays;
   mb200_hit *hits;
   __device__ __forceinline__ bool load(uint32_t i, double &ox, double &oy, double &oz, double &dx, double &dy,
-                                       double &dz, double &t0) const {
+                                       double &dz, double &tmax) const {
     const double2 *p = reinterpret_cast<const double2 *>(rays + i);
     const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
     ox = a.x, oy = a.y, oz = b.x, dx = b.y, dy = c.x, dz = c.y;
-    t0 = DBL_MAX; // bvh_accel.cc:783
+    tmax = DBL_MAX;
     store_miss(hits + i);
     return true;
   }
@@ -96,15 +92,9 @@ struct IOClosest {
 
 // K4 over a caller's ray buffer (mb200_trace_occluded).
 struct IOOccluded {
-  static constexpr bool kTracksCost = false;
+  static constexpr bool kTracksCost = false, kFused = false;
   NoCostMap m;
   __device__ __forceinline__ void mark_hot(uint32_t) const {}
-  typedef NoChunk Chunk;
-  __device__ __forceinline__ void prepare(Chunk &, uint32_t) const {}
-  __device__ __forceinline__ bool load(const Chunk &, uint32_t i, double &ox, double &oy, double &oz, double &dx,
-                                       double &dy, double &dz, double &t0) const {
-    return load(i, ox, oy, oz, dx, dy, dz, t0);
-  }
   const mb200_ray *rays;
   const double *tmax;
   unsigned char *occluded;
@@ -118,52 +108,29 @@ struct IOOccluded {
   }
   __device__ __forceinline__ void accept(uint32_t, double, double, double, uint32_t, uint32_t) const {}
   __device__ __forceinline__ void finish(uint32_t i, bool occ) const { occluded[i] = occ ? 1 : 0; }
-  __device__ __forceinline__ double tmax_of(uint32_t i) const { return __ldg(tmax + i); }
 };
 
 // K1 fused into K2: the camera ray of work item i (one jittered sample of one pixel) is generated in
 // the refill step -- Camera::GenerateRay (camera.cc:222-240) after PathTrace's jitter (render.cc:386-393)
-// -- and never stored; hits[i] receives the 32-byte record.
-struct IOCamera {
-  static constexpr bool kTracksCost = true;
+// -- and never stored; hits[i] receives the 32-byte record.  (The wavefront frames: PathTrace.)
+// PINHOLE: the kernel is compiled for Camera::GenerateRay only.  The panorama cameras (sin / cos / fmod / atan2 in
+// double: ~1 400 SASS instructions) get their own instantiation, which keeps the pinhole kernels inside the
+// 32 KB instruction cache level (kernels beyond ~2 048 instructions lose 10-30 %).
+template <bool PINHOLE> struct IOCameraT {
+  static constexpr bool kTracksCost = true, kFused = false;
   __device__ __forceinline__ void mark_hot(uint32_t i) const { mark_hot_tile(m, i); }
-  // (tile, pass) of the chunk the warp is drawing from: one decode (three integer divisions) per 32 rays
-  struct Chunk {
-    uint32_t group; // item >> 5 the fields below belong to (0xFFFFFFFF: none)
-    int x_tile, y_tile, rows_valid;
-    uint32_t pass;
-  };
-  __device__ __forceinline__ void prepare(Chunk &c, uint32_t base) const {
-    int x, y, rl;
-    item_pixel(m, base & ~31u, x, y, rl, c.pass); // lane 0 of the tile
-    c.group = base >> 5;
-    c.x_tile = x, c.y_tile = y;
-    c.rows_valid = m.rows_local - rl; // rows of this tile that exist (>= 1)
-  }
-  __device__ __forceinline__ bool load(const Chunk &c, uint32_t i, double &ox, double &oy, double &oz, double &dx,
-                                       double &dy, double &dz, double &t0) const {
-    if ((i >> 5) != c.group) return load(i, ox, oy, oz, dx, dy, dz, t0);
-    store_miss(hits + i);
-    const int lx = (int)(i & 7u), ly = (int)((i >> 3) & 3u);
-    const int x = c.x_tile + lx * m.step, y = c.y_tile + ly * m.step;
-    if (!(x < m.x1 && ly < c.rows_valid)) return false;
-    Xorshift128 rng;
-    camera_sample(p, x, y, c.pass, rng, ox, oy, oz, dx, dy, dz);
-    t0 = DBL_MAX;
-    return true;
-  }
   mb200_render_params p;
   FrameMap m;
   mb200_hit *hits;
   __device__ __forceinline__ bool load(uint32_t i, double &ox, double &oy, double &oz, double &dx, double &dy,
-                                       double &dz, double &t0) const {
+                                       double &dz, double &tmax) const {
     int x, y, rl;
     uint32_t pass;
     store_miss(hits + i);
     if (!item_pixel(m, i, x, y, rl, pass)) return false;
     Xorshift128 rng;
-    camera_sample(p, x, y, pass, rng, ox, oy, oz, dx, dy, dz);
-    t0 = DBL_MAX;
+    camera_sample<PINHOLE>(p, x, y, pass, rng, ox, oy, oz, dx, dy, dz);
+    tmax = DBL_MAX;
     return true;
   }
   __device__ __forceinline__ void accept(uint32_t i, double t, double u, double v, uint32_t face, uint32_t mat) const {
@@ -174,23 +141,17 @@ struct IOCamera {
 
 // K2 over a queue of path-continuation rays: hits[i] for queue slot i.
 struct IOQueueClosest {
-  static constexpr bool kTracksCost = true;
+  static constexpr bool kTracksCost = true, kFused = false;
   __device__ __forceinline__ void mark_hot(uint32_t i) const { mark_hot_tile(m, __ldg(&q[i].item)); }
-  typedef NoChunk Chunk;
-  __device__ __forceinline__ void prepare(Chunk &, uint32_t) const {}
-  __device__ __forceinline__ bool load(const Chunk &, uint32_t i, double &ox, double &oy, double &oz, double &dx,
-                                       double &dy, double &dz, double &t0) const {
-    return load(i, ox, oy, oz, dx, dy, dz, t0);
-  }
   const QRay *q;
   mb200_hit *hits;
   FrameMap m;
   __device__ __forceinline__ bool load(uint32_t i, double &ox, double &oy, double &oz, double &dx, double &dy,
-                                       double &dz, double &t0) const {
+                                       double &dz, double &tmax) const {
     const double2 *p = reinterpret_cast<const double2 *>(q + i);
     const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
     ox = a.x, oy = a.y, oz = b.x, dx = b.y, dy = c.x, dz = c.y;
-    t0 = DBL_MAX;
+    tmax = DBL_MAX;
     store_miss(hits + i);
     return true;
   }
@@ -201,15 +162,10 @@ struct IOQueueClosest {
 };
 
 // K4 over the queue of shadow rays: an unoccluded ray deposits its `value` into its sample's slot.
+// (The wavefront form of the primary+shadow frame, kept for A/B runs: MB200_FRAME_FUSED=0.)
 struct IOQueueShadow {
-  static constexpr bool kTracksCost = true;
+  static constexpr bool kTracksCost = true, kFused = false;
   __device__ __forceinline__ void mark_hot(uint32_t i) const { mark_hot_tile(m, __ldg(&q[i].item)); }
-  typedef NoChunk Chunk;
-  __device__ __forceinline__ void prepare(Chunk &, uint32_t) const {}
-  __device__ __forceinline__ bool load(const Chunk &, uint32_t i, double &ox, double &oy, double &oz, double &dx,
-                                       double &dy, double &dz, double &t0) const {
-    return load(i, ox, oy, oz, dx, dy, dz, t0);
-  }
   const QRay *q;
   float *contrib; // [items]
   FrameMap m;
@@ -228,84 +184,136 @@ struct IOQueueShadow {
       contrib[w.x] = __uint_as_float(w.y);
     }
   }
-  __device__ __forceinline__ double tmax_of(uint32_t i) const { return __ldg(&q[i].tmax); }
+};
+
+// The lane's 32-byte slot in shared memory (fused frames), two 16-byte units in the column layout of the
+// traversal stack (unit k of thread t at [k * blockDim.x + t]: conflict-free 128-bit accesses):
+//   while the camera ray is traced:  unit 0 = u, v   unit 1 = faceID, materialID   of the closest hit so far
+//   while the shadow ray is traced:  unit 0 = tmax, -  unit 1 = value (float bits)
+struct LaneSlot {
+  uint32_t addr0, addr1; // shared-window addresses of the two units
+  __device__ __forceinline__ void put_uv(double u, double v) const {
+    asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr0), "d"(u), "d"(v) : "memory");
+  }
+  __device__ __forceinline__ void get_uv(double &u, double &v) const {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(u), "=d"(v) : "r"(addr0) : "memory");
+  }
+  __device__ __forceinline__ void put_ids(uint32_t a, uint32_t b) const {
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr1), "r"(a), "r"(b) : "memory");
+  }
+  __device__ __forceinline__ void get_ids(uint32_t &a, uint32_t &b) const {
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr1) : "memory");
+  }
+  __device__ __forceinline__ void put_tmax(double t) const {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr0), "d"(t) : "memory");
+  }
+  __device__ __forceinline__ double get_tmax() const {
+    double t;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(addr0) : "memory");
+    return t;
+  }
+};
+
+// Fused primary+shadow / primary-only frame: camera ray -> shade -> shadow ray in the lane.
+// shade() restates the body of k_shade_primary (kernels.cu) for the two shaders that need no path state.
+template <bool PINHOLE> struct IOFrameFusedT {
+  static constexpr bool kTracksCost = true, kFused = true;
+  __device__ __forceinline__ void mark_hot(uint32_t i) const { mark_hot_tile(m, i & ~kShadowBit); }
+  mb200_render_params p;
+  FrameMap m;
+  float *contrib; // [items]
+  __device__ __forceinline__ bool load(uint32_t i, double &ox, double &oy, double &oz, double &dx, double &dy,
+                                       double &dz, double &tmax) const {
+    int x, y, rl;
+    uint32_t pass;
+    if (!item_pixel(m, i, x, y, rl, pass)) {
+      contrib[i] = 0.f; // padding lane of a ragged tile: the resolve kernel never reads it, keep it defined
+      return false;
+    }
+    Xorshift128 rng;
+    camera_sample<PINHOLE>(p, x, y, pass, rng, ox, oy, oz, dx, dy, dz);
+    tmax = DBL_MAX;
+    return true;
+  }
+  // The sample's camera ray (o, d) is finished with closest hit (t, u, v, face, mat) or face == ~0.
+  // Returns true when a shadow ray has to be traced: (qo, qd, tmax) and the value it deposits if unoccluded;
+  // otherwise `out` is the sample's contribution.
+  __device__ __forceinline__ bool shade(const SceneView &sc, double ox, double oy, double oz, double dx, double dy,
+                                        double dz, double t, double u, double v, uint32_t face, uint32_t mat,
+                                        double &qox, double &qoy, double &qoz, double &qdx, double &qdy, double &qdz,
+                                        double &qtmax, float &value, float &out) const {
+    bool hit = face != 0xFFFFFFFFu;
+    double nx = 0.0, ny = 0.0, nz = 0.0;
+    uint32_t cur_mat = 0; // Intersection::materialID before the first Trace (zero-initialised isect)
+    out = 0.f;
+    if (hit) {
+      IsectD d;
+      build_intersection(sc, ox, oy, oz, dx, dy, dz, t, u, v, face, d);
+      nx = d.nx, ny = d.ny, nz = d.nz;
+      cur_mat = mat;
+    }
+    if (p.use_plane) hit |= plane_intersect(p.plane, ox, oy, oz, dx, dy, dz, t, nx, ny, nz, cur_mat);
+    if (!hit) return false; // a camera ray that escapes contributes nothing (render.cc:409-412)
+    if (p.shader == MB200_SHADER_PRIMARY_ONLY) {
+      out = 1.f;
+      return false;
+    }
+    // the next-event-estimation block the reference leaves empty (render.cc:425-426)
+    const double hx = ox + t * dx, hy = oy + t * dy, hz = oz + t * dz;
+    if ((nx * (-dx) + ny * (-dy) + nz * (-dz)) < 0.0) nx = -nx, ny = -ny, nz = -nz;
+    double lx = p.light[0] - hx, ly = p.light[1] - hy, lz = p.light[2] - hz;
+    const double dist = sqrt(lx * lx + ly * ly + lz * lz);
+    normalize3(lx, ly, lz);
+    qox = hx + lx * kRenderEPS, qoy = hy + ly * kRenderEPS, qoz = hz + lz * kRenderEPS;
+    qdx = lx, qdy = ly, qdz = lz;
+    qtmax = dist - kRenderEPS;
+    const double ndotl = nx * lx + ny * ly + nz * lz;
+    const double kd = (cur_mat != 0xFFFFFFFFu) ? 0.5 : 1.0; // default Material::diffuse (scene.h:58-65)
+    value = (ndotl > 0.0) ? (float)(kd * ndotl) : 0.f;
+    return true;
+  }
 };
 
 // ---- the state machine ------------------------------------------------------------------------------
-// REFILL_MIN: idle lanes that trigger a refill; CHUNK: ray indices taken from the global counter per
-// atomicAdd (32 keeps the end-of-launch imbalance small: a launch of 2 M rays is only ~18 per lane).
-// VAR: bit set of code-generation variants kept for A/B runs (development builds pick them with
-// MB200_TRACE_VAR; production value kVar in kernels.cu):
-//   1  PairNode fetched with four 256-bit loads (LDG.E.256) instead of seven 128-bit + one 32-bit
-//   2  (retired: the direction signs are always one 3-bit mask now, traverse.cuh)
-//   4  leaf prefetch touches only the first 128-byte line of the leaf's records (no per-lane loop)
-//   8  no software prefetch at all
-//  16  branch-free triangle test (one predicate at the end instead of early returns)
-//  32  at most one stack pop per warp iteration (no inner pop loop)
-//  64  camera rays: the (tile, pass) decode of a 32-item chunk is done once per chunk, not per ray
-// 256 / 512  a LEAF step tests up to 2 / 4 triangles of the leaf (in order) instead of one
-// 1024  drain-phase prefetch: once the ray pool is exhausted (the warps that are left run at memory latency, not
-//       at issue rate) the records of a leaf are prefetched when the leaf is entered and a pushed far child when
-//       it is pushed, whatever bit 8 says
-constexpr int kVarWideNode = 1, kVarSignMask = 2, kVarLeafPrefetch1 = 4, kVarNoPrefetch = 8, kVarTriBranchFree = 16,
-              kVarSinglePop = 32, kVarChunkDecode = 64, kVarLeaf2 = 256, kVarLeaf4 = 512, kVarDrainPrefetch = 1024;
-
-template <bool F32, int VAR>
-__device__ __forceinline__ void prefetch_next(const SceneView &sc, uint32_t ref, uint32_t rc, bool draining = false) {
-  if ((VAR & kVarDrainPrefetch) && draining) {
-    if (rc == kBranch) prefetch_l1(sc.nodes + ref);
-    else prefetch_leaf<F32>(sc.tris, ref, rc);
-    return;
-  }
-  if (VAR & kVarNoPrefetch) return;
-  if (rc == kBranch) {
-    prefetch_l1(sc.nodes + ref);
-  } else if (VAR & kVarLeafPrefetch1) {
-    const size_t rec = F32 ? sizeof(TriRecordF32) : sizeof(TriRecordF64);
-    prefetch_l1(reinterpret_cast<const char *>(sc.tris) + (size_t)ref * rec);
-  } else {
-    prefetch_leaf<F32>(sc.tris, ref, rc);
-  }
-}
+// REFILL_MIN: idle (+ parked) lanes that trigger a refill / shade step; CHUNK: ray indices taken from the
+// global counter per atomicAdd (32 keeps the end-of-launch imbalance small).
+// VAR: bit set of code-generation variants for A/B runs (development builds pick them with MB200_TRACE_VAR;
+// production value kVar in kernels.cu).  Round-1 variants that lost (software prefetch, vote policies, 2/4
+// triangles per leaf step, single pop, branch-free triangle test, per-chunk tile decode, K rays per lane) are
+// gone from the source; their logs are profiles/r1_ab*.log and DESIGN.md §5 lists them.
+//   1  inner step: when all lanes in the step share the direction-sign mask, a copy of the two slab tests
+//      specialised for that octant runs (no per-axis selects)
+constexpr int kVarOctant = 1;
 
 struct NodeWords { // one PairNode as loaded
   double b[2][6];
   uint32_t ref0, ref1, cnt0, cnt1, axis;
 };
 
-template <bool WIDE> __device__ __forceinline__ NodeWords load_pair_node(const PairNode *n) {
+// One 128-byte line as four 256-bit loads (LDG.E.256).
+__device__ __forceinline__ NodeWords load_pair_node(const PairNode *n) {
   NodeWords w;
-  if (WIDE) {
-    const char *p = reinterpret_cast<const char *>(n);
-    double a0, a1, a2, a3;
+  const char *p = reinterpret_cast<const char *>(n);
+  double a0, a1, a2, a3;
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3) : "l"(p + 32 * k));
-      (&w.b[0][0])[4 * k + 0] = a0, (&w.b[0][0])[4 * k + 1] = a1, (&w.b[0][0])[4 * k + 2] = a2, (&w.b[0][0])[4 * k + 3] = a3;
-    }
-    uint32_t m0, m1, m2, m3, m4, m5, m6, m7;
-    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3), "=r"(m4), "=r"(m5), "=r"(m6), "=r"(m7)
-                 : "l"(p + 96));
-    w.ref0 = m0, w.ref1 = m1, w.cnt0 = m2, w.cnt1 = m3, w.axis = m4;
-  } else {
-    const double2 *np = reinterpret_cast<const double2 *>(n);
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-      const double2 v = __ldg(np + k);
-      (&w.b[0][0])[2 * k] = v.x, (&w.b[0][0])[2 * k + 1] = v.y;
-    }
-    const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(np + 6));
-    w.ref0 = meta.x, w.ref1 = meta.y, w.cnt0 = meta.z, w.cnt1 = meta.w;
-    w.axis = __ldg(reinterpret_cast<const uint32_t *>(np + 7));
+  for (int k = 0; k < 3; k++) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3) : "l"(p + 32 * k));
+    (&w.b[0][0])[4 * k + 0] = a0, (&w.b[0][0])[4 * k + 1] = a1, (&w.b[0][0])[4 * k + 2] = a2, (&w.b[0][0])[4 * k + 3] = a3;
   }
+  uint32_t m0, m1, m2, m3, m4, m5, m6, m7;
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3), "=r"(m4), "=r"(m5), "=r"(m6), "=r"(m7)
+               : "l"(p + 96));
+  w.ref0 = m0, w.ref1 = m1, w.cnt0 = m2, w.cnt1 = m3, w.axis = m4;
   return w;
 }
 
-template <class IO, bool F32, int S, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int POLICY, unsigned CHUNK, int VAR>
+// counters of a launch: [0..3] nodes, tris, rays, max stack of closest-hit (camera) rays; fused frames add
+// [4..6] nodes, tris, rays of the shadow rays
+template <class IO, int TRI, int S, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int SHADE_MIN, unsigned CHUNK, int VAR>
 __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const IO &io, unsigned long long n,
                                                     unsigned long long *work, TravStack<S, CAP> &st,
-                                                    unsigned long long *gcounters) {
+                                                    const LaneSlot slot, unsigned long long *gcounters) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -316,101 +324,139 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
   uint32_t pool_next = 0, pool_end = 0;
   bool exhausted = false;
   uint32_t iter = 0, born = 0; // warp iterations so far / at the time this lane's ray was loaded
-  typename IO::Chunk chunk;
-  TravCounters cnt = {0u, 0u, 0u};
-  unsigned int nrays = 0;
+  TravCounters cnt = {0u, 0u, 0u}, cnt_s = {0u, 0u, 0u};
+  unsigned int nrays = 0, nrays_s = 0;
   r.ox = r.oy = r.oz = r.dx = r.dy = r.dz = r.ix = r.iy = r.iz = 0.0;
   r.sgn = 0u;
 
+  // enters the tree at the root with the ray in r (hit_t set): INNER / LEAF state, or false when the root is missed
+  auto enter_root = [&](bool shadow) -> bool {
+    bool enter = false;
+    if (!sc.empty) {
+      double tm;
+      if (COUNT) (shadow ? cnt_s.nodes : cnt.nodes)++;
+      enter = slab_test(sc.root_box[0], sc.root_box[1], sc.root_box[2], sc.root_box[3], sc.root_box[4], sc.root_box[5], r,
+                        hit_t, tm);
+    }
+    if (enter && sc.root_cnt != 0u) {
+      ref = sc.root_ref, rc = sc.root_cnt;
+      if (COUNT && rc != kBranch) (shadow ? cnt_s.tris : cnt.tris) += rc;
+      return true;
+    }
+    return false;
+  };
+
   for (;; iter++) {
-    // ---- A. refill idle lanes from the warp's pool of ray indices ----------------------------------
+    // ---- A. shade parked lanes, refill idle lanes ------------------------------------------------------
+    // A step is worth its divergence once enough lanes take part; with nothing else left to do it runs anyway.
     const unsigned idle = __ballot_sync(kFullMask, rc == kIdle);
-    if (idle) {
-      if (!exhausted && (__popc(idle) >= REFILL_MIN || idle == kFullMask)) {
-        if (pool_next == pool_end) {
-          unsigned long long base = 0;
-          if (lane == 0) base = atomicAdd(work, (unsigned long long)CHUNK);
-          base = __shfl_sync(kFullMask, base, 0);
-          if (base >= n) {
-            exhausted = true;
-          } else {
-            pool_next = (uint32_t)base;
-            pool_end = (uint32_t)((base + CHUNK < n) ? base + CHUNK : n);
-            if (VAR & kVarChunkDecode) io.prepare(chunk, pool_next);
-          }
-        }
-        if (!exhausted) {
-          const unsigned avail = pool_end - pool_next, want = __popc(idle);
-          const unsigned rank = __popc(idle & lt_mask);
-          if (rc == kIdle && rank < avail) {
-            item = pool_next + rank;
-            double ox, oy, oz, dx, dy, dz, t0;
-            if ((VAR & kVarChunkDecode) ? io.load(chunk, item, ox, oy, oz, dx, dy, dz, t0)
-                                        : io.load(item, ox, oy, oz, dx, dy, dz, t0)) {
-              ray_setup(r, ox, oy, oz, dx, dy, dz);
-              hit_t = t0;
-              if (ANYHIT) tmax_any = t0;
+    unsigned parked = 0u;
+    if (IO::kFused) parked = __ballot_sync(kFullMask, rc == kShade);
+    if (idle | parked) {
+      unsigned idle_now = idle;
+      if constexpr (IO::kFused) {
+        if (parked && (__popc(parked) >= SHADE_MIN || exhausted || (idle | parked) == kFullMask)) {
+          if (rc == kShade) {
+            double u, v, qox, qoy, qoz, qdx, qdy, qdz, qtmax;
+            uint32_t face, mat;
+            float value, out;
+            slot.get_uv(u, v);
+            slot.get_ids(face, mat);
+            if (io.shade(sc, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, hit_t, u, v, face, mat, qox, qoy, qoz, qdx, qdy, qdz,
+                         qtmax, value, out)) {
+              ray_setup(r, qox, qoy, qoz, qdx, qdy, qdz);
+              hit_t = DBL_MAX; // exact any hit: the closest-hit walk, stopped at the first t < tmax
+              slot.put_tmax(qtmax);
+              slot.put_ids(__float_as_uint(value), 0u);
+              item |= kShadowBit;
               sp = 0;
-              if (IO::kTracksCost) born = iter;
-              if (COUNT) nrays++;
-              bool enter = false;
-              if (!sc.empty) {
-                double tm;
-                if (COUNT) cnt.nodes++;
-                enter = slab_test(sc.root_box[0], sc.root_box[1], sc.root_box[2], sc.root_box[3], sc.root_box[4],
-                                  sc.root_box[5], r, hit_t, tm);
+              born = iter;
+              if (COUNT) nrays_s++;
+              if (!enter_root(true)) { // nothing in the way
+                io.contrib[item & ~kShadowBit] = value;
+                rc = kIdle;
               }
-              if (enter && sc.root_cnt != 0u) {
-                ref = sc.root_ref, rc = sc.root_cnt;
-                if (COUNT && rc != kBranch) cnt.tris += rc;
-              } else {
-                io.finish(item, false);
-              }
+            } else {
+              io.contrib[item] = out;
+              rc = kIdle;
             }
           }
-          pool_next += (want < avail) ? want : avail;
+          idle_now = __ballot_sync(kFullMask, rc == kIdle);
+          parked = 0u;
         }
-      } else if (exhausted && idle == kFullMask) {
-        break;
+      }
+      if (idle_now) {
+        if (!exhausted && (__popc(idle_now) >= REFILL_MIN || (idle_now | parked) == kFullMask)) {
+          if (pool_next == pool_end) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(work, (unsigned long long)CHUNK);
+            base = __shfl_sync(kFullMask, base, 0);
+            if (base >= n) {
+              exhausted = true;
+            } else {
+              pool_next = (uint32_t)base;
+              pool_end = (uint32_t)((base + CHUNK < n) ? base + CHUNK : n);
+            }
+          }
+          if (!exhausted) {
+            const unsigned avail = pool_end - pool_next, want = __popc(idle_now);
+            const unsigned rank = __popc(idle_now & lt_mask);
+            if (rc == kIdle && rank < avail) {
+              item = pool_next + rank;
+              double ox, oy, oz, dx, dy, dz, t0;
+              if (io.load(item, ox, oy, oz, dx, dy, dz, t0)) {
+                ray_setup(r, ox, oy, oz, dx, dy, dz);
+                hit_t = DBL_MAX; // bvh_accel.cc:774 (any hit included: see the header)
+                if (ANYHIT) tmax_any = t0;
+                sp = 0;
+                if (IO::kTracksCost) born = iter;
+                if (COUNT) nrays++;
+                if (IO::kFused) slot.put_ids(0xFFFFFFFFu, 0xFFFFFFFFu); // no hit yet
+                if (!enter_root(false)) {
+                  if constexpr (IO::kFused) rc = kShade; // the plane may still be hit
+                  else io.finish(item, false);
+                }
+              }
+            }
+            pool_next += (want < avail) ? want : avail;
+          }
+        }
+        if (exhausted && idle_now == kFullMask) break;
       }
     }
 
-    // ---- B. which step bodies run this iteration ------------------------------------------------------
+    // ---- B. INNER: one 128-byte PairNode, both children tested (equivalence: traverse.cuh) -----------------
     const bool at_inner = (rc == kBranch);
-    const bool at_leaf = (rc - 1u) < (kIdle - 1u); // 1 <= rc < kIdle
-    bool run_inner = true, run_leaf = true;
-    if (POLICY == 0) {
-      const unsigned m_inner = __ballot_sync(kFullMask, at_inner);
-      const unsigned m_leaf = __ballot_sync(kFullMask, at_leaf);
-      if (!(m_inner | m_leaf)) continue;
-      run_inner = __popc(m_inner) > __popc(m_leaf);
-      run_leaf = !run_inner;
-    } else if (POLICY >= 3) {
-      // threshold vote (A/B): a body runs only when at least POLICY * 2 lanes wait for it, unless the
-      // other body does not qualify either (then the fuller one runs); the skipped lanes wait one iteration
-      const int n_inner = __popc(__ballot_sync(kFullMask, at_inner));
-      const int n_leaf = __popc(__ballot_sync(kFullMask, at_leaf));
-      constexpr int T = POLICY * 2;
-      run_inner = n_inner >= T;
-      run_leaf = n_leaf >= T;
-      if (!run_inner && !run_leaf) {
-        run_inner = n_inner >= n_leaf;
-        run_leaf = !run_inner;
-      }
-    }
-
-    if (run_inner && at_inner) {
-      // ---- INNER: one 128-byte PairNode, both children tested (equivalence: traverse.cuh) -------------
-      const NodeWords nw = load_pair_node<(VAR & kVarWideNode) != 0>(sc.nodes + ref);
+    const bool at_leaf = (rc - 1u) < (kShade - 1u); // 1 <= rc < kShade
+    if (at_inner) {
+      const NodeWords nw = load_pair_node(sc.nodes + ref);
       double t0, t1;
-      const bool h0 = slab_test(nw.b[0][0], nw.b[0][1], nw.b[0][2], nw.b[0][3], nw.b[0][4], nw.b[0][5], r, hit_t, t0);
-      const bool h1 = slab_test(nw.b[1][0], nw.b[1][1], nw.b[1][2], nw.b[1][3], nw.b[1][4], nw.b[1][5], r, hit_t, t1);
-      if (COUNT) cnt.nodes += 2;
+      bool h0, h1;
+      bool done = false;
+      if (VAR & kVarOctant) {
+        int uniform;
+        __match_all_sync(__activemask(), r.sgn, &uniform);
+        if (uniform) {
+          done = true;
+          h0 = h1 = false, t0 = t1 = 0.0;
+#define MB200_OCT(K)                                   \
+  case K:                                              \
+    h0 = slab_test_oct<K>(nw.b[0], r, hit_t, t0);      \
+    h1 = slab_test_oct<K>(nw.b[1], r, hit_t, t1);      \
+    break;
+          switch (r.sgn) { MB200_OCT(0) MB200_OCT(1) MB200_OCT(2) MB200_OCT(3) MB200_OCT(4) MB200_OCT(5) MB200_OCT(6) MB200_OCT(7) }
+#undef MB200_OCT
+        }
+      }
+      if (!done) {
+        h0 = slab_test(nw.b[0][0], nw.b[0][1], nw.b[0][2], nw.b[0][3], nw.b[0][4], nw.b[0][5], r, hit_t, t0);
+        h1 = slab_test(nw.b[1][0], nw.b[1][1], nw.b[1][2], nw.b[1][3], nw.b[1][4], nw.b[1][5], r, hit_t, t1);
+      }
+      const bool shadow = IO::kFused && (item & kShadowBit);
+      if (COUNT) (shadow ? cnt_s.nodes : cnt.nodes) += 2;
       const bool sgn = ((r.sgn >> nw.axis) & 1u) != 0u; // dirSign[axis]
       if (h0 && h1) { // near = data[dirSign[axis]] first, far pushed with its tmin (bvh_accel.cc:818-823)
         st.put(sp++, sgn ? t0 : t1, sgn ? nw.ref0 : nw.ref1, sgn ? nw.cnt0 : nw.cnt1);
-        if ((VAR & kVarDrainPrefetch) && exhausted && (sgn ? nw.cnt0 : nw.cnt1) != 0u)
-          prefetch_next<F32, VAR>(sc, sgn ? nw.ref0 : nw.ref1, sgn ? nw.cnt0 : nw.cnt1, true);
         if (COUNT) cnt.max_stack = max(cnt.max_stack, (unsigned int)sp + 1u);
         ref = sgn ? nw.ref1 : nw.ref0, rc = sgn ? nw.cnt1 : nw.cnt0;
       } else if (h0) {
@@ -420,83 +466,94 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
       } else {
         rc = 0u;
       }
-      if (rc != 0u) {
-        if (COUNT && rc != kBranch) cnt.tris += rc;
-        prefetch_next<F32, VAR>(sc, ref, rc, exhausted);
-      }
-    } else if (run_leaf && at_leaf) {
+      if (COUNT && rc != 0u && rc != kBranch) (shadow ? cnt_s.tris : cnt.tris) += rc;
+    } else if (at_leaf) {
       // ---- LEAF: one triangle of TestLeafNode (bvh_accel.cc:640-697), in indices_ order -----------------
-      constexpr int kPerStep = (VAR & kVarLeaf4) ? 4 : ((VAR & kVarLeaf2) ? 2 : 1);
-#pragma unroll
-      for (int k = 0; k < kPerStep; k++) {
-        const TriEdges tv = load_tri_edges<F32>(sc.tris, ref);
-        double u, v;
-        if (tri_test_edges<(VAR & kVarTriBranchFree) != 0>(hit_t, u, v, tv, r)) {
+      const TriEdges tv = load_tri_edges<TRI>(sc.trav_tris, ref);
+      double u, v;
+      if (tri_test_edges(hit_t, u, v, tv, r)) {
+        bool stop = false;
+        if constexpr (IO::kFused) {
+          if (item & kShadowBit) {
+            stop = hit_t < slot.get_tmax(); // occluded: the sample keeps contribution 0
+            if (stop) io.contrib[item & ~kShadowBit] = 0.f;
+          } else {
+            slot.put_uv(u, v);
+            slot.put_ids(tv.face, tv.mat);
+          }
+        } else {
           io.accept(item, hit_t, u, v, tv.face, tv.mat);
           if (ANYHIT && hit_t < tmax_any) { // occluded: closest-hit Traverse would return t < tmax
             io.finish(item, true);
-            if (IO::kTracksCost && iter - born > io.m.hot_steps) io.mark_hot(item);
-            rc = kIdle;
+            stop = true;
           }
         }
-        if (rc == kIdle) break;
+        if (stop) {
+          if (IO::kTracksCost && iter - born > io.m.hot_steps) io.mark_hot(item);
+          rc = kIdle;
+        }
+      }
+      if (rc != kIdle) {
         ref++;
         rc--;
-        if (rc == 0u) break;
       }
     }
 
     // ---- C. pop: the reference's pop-time (tmin <= hitT) decision; empty stack = ray finished ----------
     if (rc == 0u) {
-      if (VAR & kVarSinglePop) {
+      for (;;) {
         if (sp == 0) {
-          io.finish(item, false);
-          rc = kIdle;
-        } else {
-          double tm;
-          st.get(--sp, tm, ref, rc);
-          if (tm <= hit_t && rc != 0u) {
-            if (COUNT && rc != kBranch) cnt.tris += rc;
-            prefetch_next<F32, VAR>(sc, ref, rc);
+          if (IO::kTracksCost && iter - born > io.m.hot_steps) io.mark_hot(item);
+          if constexpr (IO::kFused) {
+            if (item & kShadowBit) { // unoccluded: the sample receives its value
+              uint32_t vb, unused;
+              slot.get_ids(vb, unused);
+              io.contrib[item & ~kShadowBit] = __uint_as_float(vb);
+              rc = kIdle;
+            } else {
+              rc = kShade;
+            }
           } else {
-            rc = 0u; // culled at pop time: pops again next iteration
-          }
-        }
-      } else {
-        for (;;) {
-          if (sp == 0) {
             io.finish(item, false);
-            if (IO::kTracksCost && iter - born > io.m.hot_steps) io.mark_hot(item);
             rc = kIdle;
-            break;
           }
-          double tm;
-          st.get(--sp, tm, ref, rc);
-          if (tm <= hit_t && rc != 0u) {
-            if (COUNT && rc != kBranch) cnt.tris += rc;
-            prefetch_next<F32, VAR>(sc, ref, rc);
-            break;
-          }
-          rc = 0u;
+          break;
         }
+        double tm;
+        st.get(--sp, tm, ref, rc);
+        if (tm <= hit_t && rc != 0u) {
+          if (COUNT && rc != kBranch) ((IO::kFused && (item & kShadowBit)) ? cnt_s.tris : cnt.tris) += rc;
+          break;
+        }
+        rc = 0u;
       }
     }
   }
 
   if (COUNT) {
-    unsigned long long a = cnt.nodes, b = cnt.tris, c = nrays;
+    unsigned long long a = cnt.nodes, b = cnt.tris, c = nrays, d = cnt_s.nodes, e = cnt_s.tris, f = nrays_s;
     unsigned int m = cnt.max_stack;
     for (int o = 16; o > 0; o >>= 1) {
       a += __shfl_down_sync(kFullMask, a, o);
       b += __shfl_down_sync(kFullMask, b, o);
       c += __shfl_down_sync(kFullMask, c, o);
       m = max(m, __shfl_down_sync(kFullMask, m, o));
+      if (IO::kFused) {
+        d += __shfl_down_sync(kFullMask, d, o);
+        e += __shfl_down_sync(kFullMask, e, o);
+        f += __shfl_down_sync(kFullMask, f, o);
+      }
     }
     if (lane == 0) {
       atomicAdd(&gcounters[0], a);
       atomicAdd(&gcounters[1], b);
       atomicAdd(&gcounters[2], c);
       atomicMax(&gcounters[3], (unsigned long long)m);
+      if (IO::kFused) {
+        atomicAdd(&gcounters[4], d);
+        atomicAdd(&gcounters[5], e);
+        atomicAdd(&gcounters[6], f);
+      }
     }
   }
 }

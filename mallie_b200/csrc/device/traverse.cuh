@@ -78,26 +78,41 @@ __device__ __forceinline__ bool slab_test(const double b0, const double b1, cons
   return (tmax > 0.0) && (tmin <= tmax) && (tmin <= max_t);
 }
 
-struct HitD {
-  double t, u, v;
-  uint32_t face, mat;
-};
+// The same test with the ray's direction signs known at compile time (SGN bit a = dir[a] < 0): the six
+// per-axis selects of slab_test disappear.  Used by the inner step when all of its lanes share an octant
+// (trace_sm.cuh, kVarOctant); the arithmetic and the comparisons are slab_test's, value for value.
+template <int SGN>
+__device__ __forceinline__ bool slab_test_oct(const double (&b)[6], const RayD &r, const double max_t, double &tmin_out) {
+  const double min_x = (SGN & 1) ? b[3] : b[0], max_x = (SGN & 1) ? b[0] : b[3];
+  const double min_y = (SGN & 2) ? b[4] : b[1], max_y = (SGN & 2) ? b[1] : b[4];
+  const double min_z = (SGN & 4) ? b[5] : b[2], max_z = (SGN & 4) ? b[2] : b[5];
+  const double tmin_x = (min_x - r.ox) * r.ix;
+  const double tmax_x = (max_x - r.ox) * r.ix;
+  const double tmin_y = (min_y - r.oy) * r.iy;
+  const double tmax_y = (max_y - r.oy) * r.iy;
+  double tmin = (tmin_x > tmin_y) ? tmin_x : tmin_y;
+  double tmax = (tmax_x < tmax_y) ? tmax_x : tmax_y;
+  const double tmin_z = (min_z - r.oz) * r.iz;
+  const double tmax_z = (max_z - r.oz) * r.iz;
+  tmin = (tmin > tmin_z) ? tmin : tmin_z;
+  tmax = (tmax < tmax_z) ? tmax : tmax_z;
+  tmin_out = tmin;
+  return (tmax > 0.0) && (tmin <= tmax) && (tmin <= max_t);
+}
 
 // ---- triangle records (layout.h) ----------------------------------------------------------------
-// Both record kinds are presented to the triangle test as p0 plus the two edges e1 = p1 - p0,
-// e2 = p2 - p0.  The f64 record stores the edges, rounded once on the host exactly as TriangleIsect
-// rounds them (one IEEE double subtraction each, bvh_accel.cc:600-603); the f32 record stores the
-// float-exact vertices and the edges are formed here after widening to double (same result).
+// Every record kind is presented to the triangle test as p0 plus the two edges e1 = p1 - p0,
+// e2 = p2 - p0.  The f64 records store the edges, rounded once on the host / by the layout kernel exactly as
+// TriangleIsect rounds them (one IEEE double subtraction each, bvh_accel.cc:600-603); the f32 records store
+// the float-exact vertices and the edges are formed here after widening to double (same result).
 struct TriEdges {
   double p0x, p0y, p0z, e1x, e1y, e1z, e2x, e2y, e2z;
   uint32_t face, mat;
 };
 
-template <bool F32> __device__ __forceinline__ TriEdges load_tri_edges(const void *tris, uint32_t i);
+template <int KIND> __device__ __forceinline__ TriEdges load_tri_edges(const void *tris, uint32_t i);
 
-template <> __device__ __forceinline__ TriEdges load_tri_edges<true>(const void *tris, uint32_t i) {
-  const float4 *p = reinterpret_cast<const float4 *>(reinterpret_cast<const TriRecordF32 *>(tris) + i);
-  const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+__device__ __forceinline__ TriEdges tri_edges_from_f32(const float4 a, const float4 b, const float4 c) {
   TriEdges t;
   t.p0x = (double)a.x, t.p0y = (double)a.y, t.p0z = (double)a.z;
   t.e1x = (double)b.x - t.p0x, t.e1y = (double)b.y - t.p0y, t.e1z = (double)b.z - t.p0z;
@@ -107,7 +122,12 @@ template <> __device__ __forceinline__ TriEdges load_tri_edges<true>(const void 
   return t;
 }
 
-template <> __device__ __forceinline__ TriEdges load_tri_edges<false>(const void *tris, uint32_t i) {
+template <> __device__ __forceinline__ TriEdges load_tri_edges<kTriF32>(const void *tris, uint32_t i) {
+  const float4 *p = reinterpret_cast<const float4 *>(reinterpret_cast<const TriRecordF32 *>(tris) + i);
+  return tri_edges_from_f32(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+}
+
+template <> __device__ __forceinline__ TriEdges load_tri_edges<kTriF64>(const void *tris, uint32_t i) {
   const double2 *p = reinterpret_cast<const double2 *>(reinterpret_cast<const TriRecordF64 *>(tris) + i);
   const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4);
   TriEdges t;
@@ -120,12 +140,39 @@ template <> __device__ __forceinline__ TriEdges load_tri_edges<false>(const void
   return t;
 }
 
+// 64-byte f32 record: two 256-bit loads (two L1 wavefronts per lane instead of three)
+template <> __device__ __forceinline__ TriEdges load_tri_edges<kTriF32x64>(const void *tris, uint32_t i) {
+  const char *p = reinterpret_cast<const char *>(tris) + (size_t)i * 64u;
+  float a0, a1, a2, a3, b0, b1, b2, b3, c0, c1, c2, c3, c4, c5, c6, c7;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3), "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
+               : "l"(p));
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(c0), "=f"(c1), "=f"(c2), "=f"(c3), "=f"(c4), "=f"(c5), "=f"(c6), "=f"(c7)
+               : "l"(p + 32));
+  return tri_edges_from_f32(make_float4(a0, a1, a2, a3), make_float4(b0, b1, b2, b3), make_float4(c0, c1, c2, c3));
+}
+
+// 96-byte f64 record: three 256-bit loads, no conversions and no edge subtractions
+template <> __device__ __forceinline__ TriEdges load_tri_edges<kTriF64x96>(const void *tris, uint32_t i) {
+  const char *p = reinterpret_cast<const char *>(tris) + (size_t)i * 96u;
+  double v[12];
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[4 * k]), "=d"(v[4 * k + 1]), "=d"(v[4 * k + 2]), "=d"(v[4 * k + 3])
+                 : "l"(p + 32 * k));
+  TriEdges t;
+  t.p0x = v[0], t.p0y = v[1], t.p0z = v[2];
+  t.e1x = v[3], t.e1y = v[4], t.e1z = v[5];
+  t.e2x = v[6], t.e2y = v[7], t.e2z = v[8];
+  const unsigned long long w = (unsigned long long)__double_as_longlong(v[9]);
+  t.face = (uint32_t)(w & 0xFFFFFFFFull);
+  t.mat = (uint32_t)(w >> 32);
+  return t;
+}
+
 // TriangleIsect (bvh_accel.cc:595-638): Moeller-Trumbore, no culling.
-// BRANCH_FREE: the same arithmetic with every rejection test folded into one predicate.  Each test is
-// written as the negation of the reference's rejecting comparison, so NaNs fall through exactly as they
-// do there (a NaN u, v or t is NOT rejected by `u < 0.0 || u > 1.0` and friends); a near-zero det still
-// rejects first, whatever 1.0 / det produced.
-template <bool BRANCH_FREE>
 __device__ __forceinline__ bool tri_test_edges(double &t_io, double &u_out, double &v_out, const TriEdges &k,
                                                const RayD &r) {
   // p = dir x e2
@@ -133,7 +180,7 @@ __device__ __forceinline__ bool tri_test_edges(double &t_io, double &u_out, doub
   const double py = r.dz * k.e2x - r.dx * k.e2z;
   const double pz = r.dx * k.e2y - r.dy * k.e2x;
   const double det = k.e1x * px + k.e1y * py + k.e1z * pz;
-  if (!BRANCH_FREE && fabs(det) < MB200_TRI_EPS) return false;
+  if (fabs(det) < MB200_TRI_EPS) return false;
   const double inv_det = 1.0 / det;
   const double sx = r.ox - k.p0x, sy = r.oy - k.p0y, sz = r.oz - k.p0z;
   // q = s x e1
@@ -143,15 +190,9 @@ __device__ __forceinline__ bool tri_test_edges(double &t_io, double &u_out, doub
   const double u = (sx * px + sy * py + sz * pz) * inv_det;
   const double v = (qx * r.dx + qy * r.dy + qz * r.dz) * inv_det;
   const double t = (k.e2x * qx + k.e2y * qy + k.e2z * qz) * inv_det;
-  if (BRANCH_FREE) {
-    const bool ok = !(fabs(det) < MB200_TRI_EPS) & !(u < 0.0) & !(u > 1.0) & !(v < 0.0) & !(u + v > 1.0) & !(t < 0.0) &
-                    !(t > t_io);
-    if (!ok) return false;
-  } else {
-    if (u < 0.0 || u > 1.0) return false;
-    if (v < 0.0 || u + v > 1.0) return false;
-    if (t < 0.0 || t > t_io) return false;
-  }
+  if (u < 0.0 || u > 1.0) return false;
+  if (v < 0.0 || u + v > 1.0) return false;
+  if (t < 0.0 || t > t_io) return false;
   t_io = t;
   u_out = u;
   v_out = v;

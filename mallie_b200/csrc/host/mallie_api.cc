@@ -69,15 +69,23 @@ bool BVHAccel::Build(const Mesh *mesh, const BVHBuildOptions &options) {
   const char *force_host = getenv("MB200_HOST_BUILD");
   const bool on_device = !(force_host && atoi(force_host) != 0) && o.min_leaf_primitives >= 2 && mesh->numFaces > 0 &&
                          mb200_device_count() > device_;
+  bool built = false;
   if (on_device) {
-    if (mb200_scene_build(&dev_, device_, mesh->vertices, mesh->numVertices, mesh->faces, mesh->numFaces, mesh->materialIDs,
-                          mesh->facevarying_normals, mesh->facevarying_uvs, &o, &b) != MB200_OK) {
-      printf("Mallie:err\tmsg:BVH build failed: %s\n", mb200_last_error());
+    const int rc = mb200_scene_build(&dev_, device_, mesh->vertices, mesh->numVertices, mesh->faces, mesh->numFaces,
+                                     mesh->materialIDs, mesh->facevarying_normals, mesh->facevarying_uvs, &o, &b);
+    if (rc == MB200_OK) {
+      devMesh_ = mesh;
+      built = true;
+    } else {
       dev_ = nullptr;
-      return false;
+      // a visible GPU that is not sm_100 class cannot build (or trace); the tree itself does not need one
+      if (rc != MB200_ERR_NO_DEVICE) {
+        printf("Mallie:err\tmsg:BVH build failed: %s\n", mb200_last_error());
+        return false;
+      }
     }
-    devMesh_ = mesh;
-  } else if (mb200_bvh_build(&b, mesh->vertices, mesh->numVertices, mesh->faces, mesh->numFaces, &o) != MB200_OK) {
+  }
+  if (!built && mb200_bvh_build(&b, mesh->vertices, mesh->numVertices, mesh->faces, mesh->numFaces, &o) != MB200_OK) {
     printf("Mallie:err\tmsg:BVH build failed: %s\n", mb200_last_error());
     return false;
   }

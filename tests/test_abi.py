@@ -47,7 +47,7 @@ def test_library_does_not_link_the_oracle():
 
 def test_struct_layouts_match_the_header():
     assert C.sizeof(capi.CameraFrame) == 96
-    assert C.sizeof(capi.Counters) == 32 and C.sizeof(capi.RenderStats) == 32
+    assert C.sizeof(capi.Counters) == 32 and C.sizeof(capi.RenderStats) == 64
     assert C.sizeof(capi.BuildOptions) == 24 and C.sizeof(capi.BuildStats) == 12
     # mb200_render_params: 6 ints, frame (96, 8-aligned), int, float[4], int, u32, int, int, double[3], 5 ints
     assert C.sizeof(capi.RenderParams) == 208
@@ -307,3 +307,26 @@ def test_device_layout_f64_records_empty_and_malformed_trees():
         with pytest.raises(M.MallieB200Error):
             capi.device_layout(v, f, bad, bidx)
     hb.close()
+
+
+def test_comm_and_probe_entries_reject_bad_arguments_without_a_gpu():
+    """The NCCL gather entries (include/mallie_b200.h: mb200_comm_*, mb200_gather_framebuffer,
+    mb200_render_frame_gathered) and mb200_probe_peaks validate their arguments before touching CUDA / NCCL."""
+    L = capi.lib()
+    h = C.c_void_p()
+    ident = (C.c_ubyte * 128)()
+    assert L.mb200_comm_init(C.byref(h), None, 2, 0, ident) == -1 and not h.value
+    assert L.mb200_comm_init(None, None, 2, 0, ident) == -1
+    assert L.mb200_comm_adopt(C.byref(h), None, None) == -1
+    assert L.mb200_comm_unique_id(None) == -1
+    assert L.mb200_comm_size(None) == 0 and L.mb200_comm_rank(None) == -1
+    L.mb200_comm_destroy(None)
+    assert L.mb200_gather_framebuffer(None, 8, 8, 3, 4, None, None) == -1
+    p = capi.RenderParams()
+    L.mb200_render_params_default(C.byref(p), 16, 16)
+    assert L.mb200_render_frame_gathered(None, C.byref(p), 1, 4, None, None, None) == -1
+    assert b"null" in L.mb200_last_error()
+    pk = capi.Peaks()
+    assert L.mb200_probe_peaks(0, None) == -1
+    if capi.device_count() == 0:
+        assert L.mb200_probe_peaks(0, C.byref(pk)) == -3          # MB200_ERR_NO_DEVICE: there is no CPU path

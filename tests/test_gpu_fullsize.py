@@ -1,0 +1,195 @@
+"""GPU parity at the BASELINE.json sizes, one -m gpu test per config, and the any-hit query on large-coordinate scenes.
+
+* configs 2 and 4 (teapot / 1 M-triangle sphere, 1920x1080, primary + shadow): the image of a pass must be
+  BIT-IDENTICAL to the oracle's (only + - * / sqrt on both sides); config 4 additionally as the whole 16-spp frame
+  bench.py times, through both forms of the frame (wavefront = production, fused lane state machine = MB200_FRAME_FUSED=1).
+* config 3 (cornell box 1920x1080, 5-segment paths): acos / sin / cos differ in the last ulp between CUDA and glibc, so
+  >= 99.9 % bit-identical pixels and an image sum within 1e-4 (tests/test_gpu_render.py states the same bar).
+* occlusion is DEFINED as "closest-hit Traverse returns t < tmax" (oracle: ora_occluded_batch): checked with tmax within
+  +-4 ulp of the closest t on triangle soups whose coordinates are ~1e6 (slab-test rounding ~1e-10, far above the
+  boxes' 2.3e-13 padding), ~1e-12, and on the tie-heavy doubled grid.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import mallie_b200 as M
+from oracle import orabind as O
+from tests import common as T
+
+pytestmark = pytest.mark.gpu
+
+W, H = 1920, 1080
+CORES = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def gpu_scene(name):
+    m = T.load_mesh(name)
+    return M.Scene.build(m["vertices"], m["faces"], m["material_ids"], m["normals"], m["uvs"], want_bvh=False)
+
+
+@pytest.mark.parametrize("mesh,eye,lookat,light", [
+    ("teapot", (5, 40, 150), (5, 40, 0), (80.0, 120.0, 100.0)),          # BASELINE config 2
+    ("sphere500", (0, 0, 3), (0, 0, 0), (2.0, 4.0, 3.0)),                # BASELINE config 4 (bench.py's scene)
+])
+def test_primary_shadow_1080p_pass_bit_identical(mesh, eye, lookat, light):
+    sc = gpu_scene(mesh)
+    om, ob = T.oracle_scene(mesh)
+    fg = M.camera_frame(eye, lookat, width=W, height=H)
+    fo = O.camera_frame(eye, lookat, width=W, height=H)
+    for pass_index in (0, 11):
+        p = sc.render_params(fg, W, H, shader=M.SHADER_PRIMARY_SHADOW, light=light, pass_index=pass_index)
+        img, cnt, st = sc.render_pass(p)
+        oimg, ocnt, oc = ob.render_pass(fo, W, H, rng_mode=1, pass_index=pass_index, shader=1, light=light, nthreads=CORES)
+        assert img.tobytes() == oimg.tobytes(), f"{mesh} pass {pass_index}: image differs from the oracle's"
+        assert np.array_equal(cnt, ocnt)
+        assert st["primary_rays"] == W * H == oc["trace_calls"] and st["shadow_rays"] == oc["shadow_rays"] > 0
+        # the work the traversal kernels did: camera rays exactly the reference's walk, shadow rays at most the closest-hit walk
+        assert st["camera_nodes_tested"] == oc["n_node"] - oc["shadow_n_node"]
+        assert st["camera_tris_tested"] == oc["n_tri"] - oc["shadow_n_tri"]
+        assert 0 < st["shadow_nodes_tested"] <= oc["shadow_n_node"] and 0 < st["shadow_tris_tested"] <= oc["shadow_n_tri"]
+    sc.close()
+
+
+def test_config4_full_16spp_frame_equals_oracle_both_frame_forms():
+    """The frame bench.py times: 1 M triangles, 1920x1080, 16 spp, primary + shadow."""
+    om, ob = T.oracle_scene("sphere500")
+    fo = O.camera_frame((0, 0, 3), (0, 0, 0), width=W, height=H)
+    want = np.zeros((H, W, 3), np.float32)
+    rays = 0
+    for k in range(16):
+        oimg, _, oc = ob.render_pass(fo, W, H, rng_mode=1, pass_index=k, shader=1, light=(2.0, 4.0, 3.0), nthreads=CORES)
+        want += oimg                                      # AccumImage: float += float in pass order
+        rays += oc["trace_calls"] + oc["shadow_rays"]
+    want_fnv = T.fnv(want)
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+import mallie_b200 as M
+from tests import common as T
+m = T.load_mesh("sphere500")
+sc = M.Scene.build(m["vertices"], m["faces"], want_bvh=False)
+fg = M.camera_frame((0, 0, 3), (0, 0, 0), width=1920, height=1080)
+p = sc.render_params(fg, 1920, 1080, shader=M.SHADER_PRIMARY_SHADOW, light=(2.0, 4.0, 3.0), pass_index=0)
+for rep in range(2):                                      # second frame runs with the longest-rays-first order
+    img, cnt, st = sc.render_frame(p, 16)
+    print("FRAME", T.fnv(img), int(cnt.min()), int(cnt.max()), st["primary_rays"] + st["shadow_rays"])
+sc.close()
+""" % T.HERE.rsplit("/", 1)[0]
+    for fused in ("1", "0"):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900,
+                           env=dict(os.environ, MB200_FRAME_FUSED=fused))
+        lines = [ln.split() for ln in r.stdout.splitlines() if ln.startswith("FRAME")]
+        assert r.returncode == 0 and len(lines) == 2, r.stdout[-2000:] + r.stderr[-3000:]
+        for ln in lines:
+            assert ln[1] == want_fnv, f"MB200_FRAME_FUSED={fused}: 16-spp frame differs from the oracle's"
+            assert ln[2] == ln[3] == "16" and int(ln[4]) == rays
+
+
+def test_config3_cornell_1080p_five_segment_paths():
+    sc = gpu_scene("cornellbox")
+    om, ob = T.oracle_scene("cornellbox")
+    fg = M.camera_frame((0, 0, 20), (0, 0, 0), width=W, height=H)
+    fo = O.camera_frame((0, 0, 20), (0, 0, 0), width=W, height=H)
+    p = sc.render_params(fg, W, H, shader=M.SHADER_PATHTRACE, max_path_length=5, pass_index=7)
+    img, cnt, st = sc.render_pass(p)
+    oimg, _, oc = ob.render_pass(fo, W, H, rng_mode=1, pass_index=7, skip_zombies=1, shader=0, max_path_length=5,
+                                 nthreads=CORES)
+    same = (img.view(np.uint32) == oimg.view(np.uint32)).all(axis=2)
+    assert same.mean() >= 0.999, f"only {same.mean():.5f} of the pixels are bit-identical"
+    tot = float(oimg.sum(dtype=np.float64))
+    assert abs(float(img.sum(dtype=np.float64)) - tot) <= 1e-4 * tot
+    assert st["primary_rays"] == W * H and (cnt == 1).all()
+    assert abs(st["primary_rays"] + st["bounce_rays"] - oc["trace_calls"]) <= 1e-3 * oc["trace_calls"]
+    sc.close()
+
+
+def ulp_steps(x, k):
+    out = x.copy()
+    for _ in range(abs(k)):
+        out = np.nextafter(out, np.inf if k > 0 else -np.inf)
+    return out
+
+
+@pytest.mark.parametrize("case", ["soup_large_negative", "soup_tiny_extent", "doubled_grid", "soup_huge_triangles"])
+def test_occlusion_is_closest_hit_below_tmax_at_any_scale(case):
+    v, f = T.build_cases()[case]
+    sc = M.Scene.build(v, f, want_bvh=False)
+    ob = O.BVH.build(O.Mesh(v, f))
+    bmin, bmax = sc.bounds()
+    rng = np.random.default_rng(11)
+    rays = T.random_rays(rng, 60_000, bmin, bmax)
+    o = ob.trace(rays)
+    hits = sc.trace_closest(rays)
+    T.assert_hits_equal(hits, o["hits"], case)
+    t = o["hits"]["t"].copy()
+    hit = o["mask"]
+    if case == "soup_tiny_extent":
+        assert hit.sum() == 0       # |det| < 2.27e-13 (bvh_accel.cc:598,609) rejects every triangle at this scale
+    else:
+        assert hit.sum() > 1000
+    scale = float(np.linalg.norm(np.asarray(bmax) - np.asarray(bmin)))
+    t[~hit] = scale
+    for k in (-4, -1, 0, 1, 4):
+        tmax = ulp_steps(t, k)
+        got = sc.trace_occluded(rays, tmax)
+        want = ob.occluded(rays, tmax)
+        assert np.array_equal(got, want), f"{case}: tmax = t {k:+d} ulp: {int((got != want).sum())} rays differ"
+        assert np.array_equal(want[hit], np.full(int(hit.sum()), k > 0))     # strict: t < tmax
+    # tmax far inside / far beyond, and shadow-style rays that start on the surface
+    for s in (0.25, 0.999999, 1.000001, 1e6):
+        tmax = t * s
+        assert np.array_equal(sc.trace_occluded(rays, tmax), ob.occluded(rays, tmax))
+    org = rays[hit, :3] + o["hits"]["t"][hit, None] * rays[hit, 3:]
+    d = rng.normal(size=org.shape)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    srays = np.concatenate([org + d * (1e-3 * scale), d], axis=1)
+    tm = np.full(len(srays), 0.5 * scale)
+    if len(srays):
+        got, want = sc.trace_occluded(srays, tm), ob.occluded(srays, tm)
+        assert np.array_equal(got, want) and (case == "doubled_grid" or (want.any() and (~want).any()))
+    sc.close()
+
+
+def test_fused_frame_form_matches_oracle():
+    """MB200_FRAME_FUSED=1 (camera ray -> shade -> shadow ray in one lane of one launch) on a small ragged frame."""
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+import mallie_b200 as M
+from oracle import orabind as O
+from tests import common as T
+m = T.load_mesh("sphere40")
+sc = M.Scene(m["vertices"], m["faces"])
+om, ob = T.oracle_scene("sphere40")
+Wd, Ht = 301, 203
+fg = M.camera_frame((0.3, 0.2, 3), (0, 0, 0), width=Wd, height=Ht)
+fo = O.camera_frame((0.3, 0.2, 3), (0, 0, 0), width=Wd, height=Ht)
+for shader, osh in ((M.SHADER_PRIMARY_SHADOW, 1),):
+    p = sc.render_params(fg, Wd, Ht, shader=shader, light=(2.0, 4.0, 3.0), pass_index=3)
+    img, cnt, st = sc.render_pass(p)
+    oimg, ocnt, oc = ob.render_pass(fo, Wd, Ht, rng_mode=1, pass_index=3, shader=osh, light=(2.0, 4.0, 3.0))
+    assert img.tobytes() == oimg.tobytes() and st["shadow_rays"] == oc["shadow_rays"] and st["primary_rays"] == Wd * Ht
+p = sc.render_params(fg, Wd, Ht, shader=M.SHADER_PRIMARY_ONLY, jitter=False)
+img, _, st = sc.render_pass(p)
+o = ob.trace(O.generate_grid(fo, Wd, Ht), row=Wd)
+assert np.array_equal(img[..., 0].reshape(-1) > 0, o["mask"]) and st["shadow_rays"] == 0
+sc.close()
+for plane in (False, True):          # the plane can be hit where the mesh is missed (camera rays that miss the root box too)
+    pl = M.plane_from_bounds(*sc.bounds()) if plane else None
+    nodes, _ = ob.arrays()
+    opl = O.plane_from_bbox(nodes[0]["bmin"], nodes[0]["bmax"]) if plane else None
+    p = sc.render_params(fg, Wd, Ht, plane=pl, shader=M.SHADER_PRIMARY_SHADOW, light=(2.0, 4.0, 3.0), pass_index=1)
+    img, cnt, st = sc.render_frame(p, 3)
+    want = np.zeros_like(img)
+    for k in (1, 2, 3):
+        want += ob.render_pass(fo, Wd, Ht, plane=opl, rng_mode=1, pass_index=k, shader=1, light=(2.0, 4.0, 3.0))[0]
+    assert img.tobytes() == want.tobytes() and (cnt == 3).all()
+print("FUSED-OK")
+""" % T.HERE.rsplit("/", 1)[0]
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, MB200_FRAME_FUSED="1"))
+    assert r.returncode == 0 and "FUSED-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

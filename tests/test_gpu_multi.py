@@ -79,3 +79,87 @@ def test_cloned_replicas_render_the_same_frame():
     assert img.tobytes() == want.tobytes() and np.array_equal(cnt, wcnt)
     for s in scenes:
         s.close()
+
+
+GATHER_RANK = r"""
+import os, sys, time, numpy as np
+sys.path.insert(0, %(root)r)
+import mallie_b200 as M
+from tests import common as T
+rank, world, idfile = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+W, H = 333, 150
+m = T.load_mesh("sphere40")
+sc = M.Scene(m["vertices"], m["faces"], device=rank)
+if rank == 0:
+    uid = M.Comm.unique_id()
+    with open(idfile + ".tmp", "wb") as fp:
+        fp.write(uid)
+    os.rename(idfile + ".tmp", idfile)
+else:
+    t0 = time.time()
+    while not os.path.exists(idfile):
+        assert time.time() - t0 < 120
+        time.sleep(0.05)
+    uid = open(idfile, "rb").read()
+comm = M.Comm(sc, world, rank, uid)
+fg = M.camera_frame((0.2, 0.1, 3.0), (0, 0, 0), width=W, height=H)
+out = []
+for shader in (M.SHADER_PRIMARY_SHADOW, M.SHADER_PATHTRACE):
+    p = sc.render_params(fg, W, H, shader=shader, light=(2, 4, 3), pass_index=2, max_path_length=4)
+    for band_rows in (4, 12):
+        img = np.full((H, W, 3), -1.0, np.float32)          # pageable host destination on every rank
+        cnt = np.zeros((H, W), np.int32)
+        st = comm.render_frame(p, 3, band_rows, img, cnt, stats=True)
+        out.append((T.fnv(img), int(cnt.min()), int(cnt.max()), st["primary_rays"]))
+    # device destination (enqueue-only) and a rank that does not want the frame
+    import torch
+    torch.cuda.set_device(rank)
+    d_img = torch.full((H, W, 3), -1.0, dtype=torch.float32, device="cuda")
+    comm.render_frame(p, 3, 8, d_img.data_ptr() if rank == 0 else None, None)
+    sc.synchronize()
+    if rank == 0:
+        out.append((T.fnv(d_img.cpu().numpy()), 3, 3, 0))
+    del d_img
+print("GATHER", rank, out)
+comm.close()
+sc.close()
+"""
+
+
+def test_nccl_gathered_frame_is_the_single_gpu_frame(tmp_path):
+    """One process per GPU through the C ABI (mb200_comm_* + mb200_render_frame_gathered): the frame every rank
+    receives from the NCCL all-gather + row placement is bit-identical to the 1-GPU frame."""
+    need_gpus(2)
+    import ast
+    import sys
+    world = 2
+    W, H = 333, 150
+    m = T.load_mesh("sphere40")
+    sc = M.Scene(m["vertices"], m["faces"], device=0)
+    fg = M.camera_frame((0.2, 0.1, 3.0), (0, 0, 0), width=W, height=H)
+    want = {}
+    for shader in (M.SHADER_PRIMARY_SHADOW, M.SHADER_PATHTRACE):
+        p = sc.render_params(fg, W, H, shader=shader, light=(2, 4, 3), pass_index=2, max_path_length=4)
+        want[shader] = T.fnv(sc.render_frame(p, 3)[0])
+    sc.close()
+    idfile = str(tmp_path / "nccl_id")
+    code = GATHER_RANK % dict(root=os.path.dirname(T.HERE))
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(r), str(world), idfile], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(world)]
+    outs = [pr.communicate(timeout=600) for pr in procs]
+    total_primary = {}
+    for r, (pr, (so, se)) in enumerate(zip(procs, outs)):
+        assert pr.returncode == 0, se[-3000:]
+        line = [ln for ln in so.splitlines() if ln.startswith("GATHER")][0]
+        res = ast.literal_eval(line.split(" ", 2)[2])
+        k = 0
+        for shader in (M.SHADER_PRIMARY_SHADOW, M.SHADER_PATHTRACE):
+            n = 3 if r == 0 else 2
+            for j in range(n):
+                fnv, cmin, cmax, prim = res[k]
+                assert fnv == want[shader], (r, shader, j)
+                assert cmin == cmax == 3
+                if j < 2:
+                    total_primary[(shader, j)] = total_primary.get((shader, j), 0) + prim
+                k += 1
+    assert all(v == 3 * W * H for v in total_primary.values()), total_primary

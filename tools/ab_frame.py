@@ -14,7 +14,7 @@ from mallie_b200.procedural import bumpy_sphere  # noqa: E402
 N = int(os.environ.get("SPHERE_N", "500"))
 W, H, SPP = 1920, 1080, 16
 v, f = bumpy_sphere(N)
-sc = M.Scene(v, f)
+sc = M.Scene.build(v, f, want_bvh=False)
 frame = M.camera_frame((0, 0, 3), (0, 0, 0), width=W, height=H)
 stream = torch.cuda.ExternalStream(sc.stream())
 n = W * H
@@ -59,6 +59,8 @@ for name, fn, reps in (("closest", closest, 12), ("frame", frame_, 6)):
 hits = d_hits.cpu().numpy().view(M.capi.HIT_DTYPE)
 chk = int(hits["faceID"].astype(np.uint64).sum())
 img_sum = float(d_img.double().sum())
+import hashlib  # noqa: E402
+img_fnv = hashlib.sha1(d_img.cpu().numpy().tobytes()).hexdigest()[:12]
 tag = " ".join(f"{k[6:]}={os.environ[k]}" for k in sorted(os.environ) if k.startswith("MB200_")) or "production"
 print(f"[{tag}] closest {out['closest'][0]:.3f} ms ({n/out['closest'][0]/1e3:.0f} Mray/s) | frame {out['frame'][0]:.3f} ms "
-      f"med {out['frame'][1]:.3f} {out['frame'][2]} | chk {chk} img {img_sum:.3f}")
+      f"med {out['frame'][1]:.3f} {out['frame'][2]} | chk {chk} img {img_sum:.3f} {img_fnv}")
