@@ -373,6 +373,22 @@ int mb200_render_frame(mb200_scene *scene, const mb200_render_params *params, in
  * image / count: as mb200_render_frame (device pointers must belong to scenes[0]'s GPU).  stats: sums. */
 int mb200_render_frame_multi(mb200_scene *const *scenes, int num_scenes, const mb200_render_params *params,
                              int num_passes, int band_rows, float *image, int *count, mb200_render_stats *stats);
+/* Output resolve on the device: the accumulated frame (float[3*W*H]) and its per-pixel sample counts (int[W*H]) ->
+ * 8-bit pixels, as the reference's front ends produce them on the host.  With the frame still on the device (what
+ * mb200_render_frame / _accumulate leave there) a host receives W*H*3 or W*H*4 bytes instead of W*H*16.
+ * image / count / out: host or device pointers; a device `out` makes the call enqueue-only. */
+typedef enum {
+  MB200_LDR_RGB8_LINEAR = 0,   /* HDRToLDR, main_console.cc:25-43: out[3p+c] = clamp((int)(in / count * 255.5))            */
+  MB200_LDR_BGRA8_GAMMA22 = 1  /* Display, main_sdl.cc:156-165,420-477: BGRA, powf(in / count, 1 / 2.2f) * 255.5, A = 255 */
+} mb200_ldr_mode;
+int mb200_resolve_ldr(mb200_scene *scene, const float *image, const int *count, int width, int height, int mode,
+                      unsigned char *out);
+
+/* mb200_render_frame + mb200_resolve_ldr without the float frame ever leaving the GPU: what DoMainConsole does with
+ * Render + HDRToLDR (main_console.cc:57-75), for num_passes samples per pixel.  params must describe the whole image. */
+int mb200_render_frame_ldr(mb200_scene *scene, const mb200_render_params *params, int num_passes, int mode,
+                           unsigned char *out, mb200_render_stats *stats);
+
 /* Rows of the image a banded call owns (== y1-y0 when bands are disabled). */
 int mb200_band_local_rows(const mb200_render_params *params);
 

@@ -25,6 +25,7 @@ assert RAY_DTYPE.itemsize == 48 and HIT_DTYPE.itemsize == 32
 assert ISECT_DTYPE.itemsize == 184 and NODE_DTYPE.itemsize == 64
 
 SHADER_PATHTRACE, SHADER_PRIMARY_SHADOW, SHADER_PRIMARY_ONLY, SHADER_PATHTRACE_ENV = 0, 1, 2, 3
+LDR_RGB8_LINEAR, LDR_BGRA8_GAMMA22 = 0, 1
 CAMERA_PINHOLE, CAMERA_ENV, CAMERA_ENV_STEREO = 0, 1, 2
 
 # Every symbol include/mallie_b200.h declares (tests/test_abi.py checks the header against this list).
@@ -40,7 +41,7 @@ EXPORTS = [
     "mb200_trace_closest", "mb200_trace_closest_full", "mb200_trace_occluded", "mb200_trace_closest_async",
     "mb200_camera_frame_build", "mb200_generate_rays", "mb200_generate_rays_env", "mb200_generate_rays_grid",
     "mb200_render_params_default", "mb200_plane_from_bounds", "mb200_render_pass", "mb200_render_accumulate",
-    "mb200_render_frame", "mb200_render_frame_multi", "mb200_band_local_rows",
+    "mb200_render_frame", "mb200_render_frame_multi", "mb200_band_local_rows", "mb200_resolve_ldr", "mb200_render_frame_ldr",
     "mb200_comm_unique_id", "mb200_comm_init", "mb200_comm_adopt", "mb200_comm_size", "mb200_comm_rank",
     "mb200_comm_destroy", "mb200_gather_framebuffer", "mb200_render_frame_gathered",
     "mb200_mesh_load_obj", "mb200_mesh_load_eson", "mb200_mesh_transform", "mb200_mesh_num_vertices",
@@ -196,6 +197,8 @@ def lib():
         L.mb200_band_local_rows.argtypes = [C.POINTER(RenderParams)]
         L.mb200_render_frame_multi.argtypes = [C.POINTER(vp), i32, C.POINTER(RenderParams), i32, i32, vp, vp,
                                                C.POINTER(RenderStats)]
+        L.mb200_resolve_ldr.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+        L.mb200_render_frame_ldr.argtypes = [vp, C.POINTER(RenderParams), i32, i32, vp, C.POINTER(RenderStats)]
         L.mb200_comm_unique_id.argtypes = [vp]
         L.mb200_comm_init.argtypes = [C.POINTER(vp), vp, i32, i32, vp]
         L.mb200_comm_adopt.argtypes = [C.POINTER(vp), vp, vp]
@@ -653,6 +656,22 @@ class Scene:
         st = RenderStats()
         check(lib().mb200_render_pass(self.h, C.byref(params), _p(image), _p(count), C.byref(st) if stats else None))
         return image, count, (st.as_dict() if stats else None)
+
+    def resolve_ldr(self, image, count, width, height, mode=0, out=None):
+        """mb200_resolve_ldr: mode 0 = HDRToLDR (RGB8), 1 = Display (BGRA8, gamma 2.2).  image / count / out: numpy arrays
+        or device addresses (ints)."""
+        if out is None:
+            out = np.zeros((height, width, 3 if mode == 0 else 4), np.uint8)
+        check(lib().mb200_resolve_ldr(self.h, _p(image), _p(count), width, height, mode, _p(out)))
+        return out
+
+    def render_frame_ldr(self, params, num_passes, mode=0, out=None, stats=True):
+        """mb200_render_frame_ldr: the frame as 8-bit pixels; the float frame stays on the GPU."""
+        if out is None:
+            out = np.zeros((params.height, params.width, 3 if mode == 0 else 4), np.uint8)
+        st = RenderStats()
+        check(lib().mb200_render_frame_ldr(self.h, C.byref(params), num_passes, mode, _p(out), C.byref(st) if stats else None))
+        return out, (st.as_dict() if stats else None)
 
     def render_accumulate(self, params, num_passes, image=None, count=None, stats=True):
         if image is None:

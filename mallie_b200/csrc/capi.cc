@@ -798,6 +798,56 @@ int mb200_render_frame_multi(mb200_scene *const *scenes, int n, const mb200_rend
   return MB200_OK;
 }
 
+int mb200_resolve_ldr(mb200_scene *s, const float *image, const int *count, int width, int height, int mode,
+                      unsigned char *out) {
+  if (!s || !image || !count || !out || width <= 0 || height <= 0) return set_err(MB200_ERR_INVALID_ARG, "bad argument");
+  if (mode != MB200_LDR_RGB8_LINEAR && mode != MB200_LDR_BGRA8_GAMMA22) return set_err(MB200_ERR_INVALID_ARG, "unknown LDR mode");
+  CU(cudaSetDevice(s->device));
+  const size_t npix = (size_t)width * height;
+  const size_t out_bytes = npix * (mode == MB200_LDR_RGB8_LINEAR ? 3 : 4);
+  const void *d_img, *d_cnt;
+  void *d_out;
+  bool staged;
+  int rc;
+  // the staging slots a render call with host buffers used for its outputs are free again: out0 / out1 hold device
+  // copies of a host frame, in0 the 8-bit result
+  if ((rc = stage_in(s, s->out0, image, npix * 3 * sizeof(float), &d_img)) != MB200_OK) return rc;
+  if ((rc = stage_in(s, s->out1, count, npix * sizeof(int), &d_cnt)) != MB200_OK) return rc;
+  if ((rc = stage_out_begin(s->in0, out, out_bytes, &d_out, &staged)) != MB200_OK) return rc;
+  CU(mb200::launch_resolve_ldr((const float *)d_img, (const int *)d_cnt, npix, mode, (unsigned char *)d_out, s->stream));
+  if (!staged) return MB200_OK; // device destination: enqueue-only
+  if ((rc = stage_out_enqueue(s, s->in0, out_bytes)) != MB200_OK) return rc;
+  CU(cudaStreamSynchronize(s->stream));
+  memcpy(out, s->in0.pinned, out_bytes);
+  return MB200_OK;
+}
+
+int mb200_render_frame_ldr(mb200_scene *s, const mb200_render_params *p, int num_passes, int mode, unsigned char *out,
+                           mb200_render_stats *stats) {
+  if (!s || !p || !out) return set_err(MB200_ERR_INVALID_ARG, "null argument");
+  if (mode != MB200_LDR_RGB8_LINEAR && mode != MB200_LDR_BGRA8_GAMMA22) return set_err(MB200_ERR_INVALID_ARG, "unknown LDR mode");
+  if (p->width <= 0 || p->height <= 0 || p->x0 != 0 || p->y0 != 0 || p->x1 != p->width || p->y1 != p->height || p->band_rows != 0)
+    return set_err(MB200_ERR_INVALID_ARG, "mb200_render_frame_ldr renders whole images");
+  CU(cudaSetDevice(s->device));
+  const size_t npix = (size_t)p->width * p->height;
+  int rc;
+  // the float frame and the counts live in the scene's device staging and never leave the GPU
+  if ((rc = ensure(s->out0, npix * 3 * sizeof(float), false)) != MB200_OK) return rc;
+  if ((rc = ensure(s->out1, npix * sizeof(int), false)) != MB200_OK) return rc;
+  if ((rc = render_common(s, p, num_passes, 2, (float *)s->out0.dev, (int *)s->out1.dev, stats)) != MB200_OK) return rc;
+  const size_t out_bytes = npix * (mode == MB200_LDR_RGB8_LINEAR ? 3 : 4);
+  void *d_out;
+  bool staged;
+  if ((rc = stage_out_begin(s->in0, out, out_bytes, &d_out, &staged)) != MB200_OK) return rc;
+  CU(mb200::launch_resolve_ldr((const float *)s->out0.dev, (const int *)s->out1.dev, npix, mode, (unsigned char *)d_out, s->stream));
+  if (!staged) return MB200_OK;
+  const bool pinned = classify(out) == kPinned;
+  CU(cudaMemcpyAsync(pinned ? (void *)out : s->in0.pinned, d_out, out_bytes, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  if (!pinned) memcpy(out, s->in0.pinned, out_bytes);
+  return MB200_OK;
+}
+
 int mb200_band_local_rows(const mb200_render_params *p) {
   if (!p) return 0;
   if (p->band_rows <= 0) return p->y1 - p->y0;

@@ -392,6 +392,44 @@ __global__ void __launch_bounds__(256)
   else count[pix] += (int)m.passes;
 }
 
+// ---------------------------------------------------------------------------
+// Output resolve: accumulated float frame + per-pixel sample counts -> 8-bit pixels, as the reference's two
+// front ends do it on the host.
+//   mode 0  HDRToLDR (main_console.cc:25-43): RGB8, fclamp(in / count) with int i = x * 255.5 (float * double)
+//   mode 1  Display  (main_sdl.cc:156-165, 420-477): BGRA8 (B at byte 0, A = 255), scale = 1.0f / (float)count,
+//           fclamp(scale * in) with int i = powf(x, 1.0f / 2.2f) * 255.5
+// `(int)double` is x86-64's cvttsd2si in the reference build: NaN and out-of-range values give INT_MIN, which the
+// clamp turns into 0 (CUDA's own conversion would saturate to 255 / 0).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int quantise_x86(double v) {
+  const int i = (v > -2147483649.0 && v < 2147483648.0) ? (int)v : (int)0x80000000;
+  return i < 0 ? 0u : (i > 255 ? 255u : (unsigned int)i);
+}
+
+// powf(x, 1.0f / 2.2f) evaluated as pow in double, rounded to float once: equals glibc's powf (itself computed in
+// double) except where the two double results straddle a float rounding boundary.
+__device__ __forceinline__ float gamma22(float x) { return (float)pow((double)x, (double)(1.0f / 2.2f)); }
+
+__global__ void __launch_bounds__(256) k_resolve_ldr(const float *__restrict__ image, const int *__restrict__ count,
+                                                     size_t npix, int mode, unsigned char *__restrict__ out) {
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (size_t)gridDim.x * blockDim.x) {
+    const float r = image[3 * p + 0], g = image[3 * p + 1], b = image[3 * p + 2];
+    const int n = count[p];
+    if (mode == 0) {
+      const float fn = (float)n; // in[i] / in_count[i / 3]: float / int
+      out[3 * p + 0] = (unsigned char)quantise_x86((double)(r / fn) * 255.5);
+      out[3 * p + 1] = (unsigned char)quantise_x86((double)(g / fn) * 255.5);
+      out[3 * p + 2] = (unsigned char)quantise_x86((double)(b / fn) * 255.5);
+    } else {
+      const float scale = 1.0f / (float)n;
+      const unsigned int qr = quantise_x86((double)gamma22(scale * r) * 255.5);
+      const unsigned int qg = quantise_x86((double)gamma22(scale * g) * 255.5);
+      const unsigned int qb = quantise_x86((double)gamma22(scale * b) * 255.5);
+      reinterpret_cast<unsigned int *>(out)[p] = qb | (qg << 8) | (qr << 16) | 0xFF000000u;
+    }
+  }
+}
+
 // order = stable partition of 0 .. tiles-1: the tiles flagged in `hot` first, then the others; clears `hot`.
 // One CTA of 1024 threads (a 1080p frame has 64 800 tiles: 64 rounds).
 __global__ void __launch_bounds__(1024) k_build_order(unsigned char *__restrict__ hot, uint32_t tiles,
@@ -1028,6 +1066,13 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
     if ((e = cudaStreamWaitEvent(s, pipe->join, 0)) != cudaSuccess) return e;
   }
   return cudaSuccess;
+}
+
+cudaError_t launch_resolve_ldr(const float *image, const int *count, size_t npix, int mode, unsigned char *out, cudaStream_t s) {
+  if (npix == 0) return cudaSuccess;
+  k_resolve_ldr<<<flat_grid(npix, 256), 256, 0, s>>>(image, count, npix, mode, out);
+  g_launches++;
+  return cudaGetLastError();
 }
 
 cudaError_t launch_pad_tris(const void *src, int src_f32, size_t n, int kind, void *dst, cudaStream_t s) {

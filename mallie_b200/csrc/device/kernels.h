@@ -93,6 +93,9 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
                          float *image, int *count, FrameScratch &scratch, unsigned long long *stats, cudaStream_t s,
                          KernelTimer *timer = nullptr, FramePipe *pipe = nullptr);
 
+// Accumulated frame + counts -> 8-bit pixels (mode 0: HDRToLDR RGB8, mode 1: Display BGRA8 with gamma 2.2).
+cudaError_t launch_resolve_ldr(const float *image, const int *count, size_t npix, int mode, unsigned char *out, cudaStream_t s);
+
 // Traversal copy of the triangle records in a padded layout (layout.h: TriKind kTriF32x64 / kTriF64x96).
 cudaError_t launch_pad_tris(const void *src, int src_f32, size_t n, int kind, void *dst, cudaStream_t s);
 

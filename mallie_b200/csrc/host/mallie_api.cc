@@ -458,6 +458,36 @@ void RenderPanoramic(Scene &scene, const RenderConfig &config, std::vector<float
   fflush(stdout);
 }
 
+// DoMainConsole's Render + HDRToLDR (main_console.cc:57-75) in one device-side step: num_passes samples per pixel,
+// quantised on the GPU; only the 8-bit image crosses PCIe.  Returns Mrays/s (0 on failure).
+double RenderLDR(Scene &scene, const RenderConfig &config, std::vector<unsigned char> &out, const double eye[3],
+                 const double lookat[3], const double up[3], const double quat[4], int num_passes, int ldr_mode,
+                 mb200_render_stats *stats) {
+  const int width = config.width, height = config.height;
+  if (num_passes < 1 || width <= 0 || height <= 0) return 0.0;
+  mb200_scene *s = scene.DeviceScene();
+  if (!s) {
+    printf("Mallie:err\tmsg:RenderLDR: no device scene (%s)\n", mb200_last_error());
+    return 0.0;
+  }
+  out.resize((size_t)width * height * (ldr_mode == MB200_LDR_RGB8_LINEAR ? 3 : 4));
+  mb200_render_params p;
+  fill_params(p, scene, config, eye, lookat, up, quat);
+  p.pass = g_render.pass;
+  g_render.pass += (unsigned int)num_passes;
+  mb200_render_stats local;
+  const auto t0 = std::chrono::steady_clock::now();
+  if (mb200_render_frame_ldr(s, &p, num_passes, ldr_mode, out.data(), &local) != MB200_OK) {
+    printf("Mallie:err\tmsg:RenderLDR failed: %s\n", mb200_last_error());
+    return 0.0;
+  }
+  const auto t1 = std::chrono::steady_clock::now();
+  if (stats) *stats = local;
+  const double sec = std::chrono::duration<double>(t1 - t0).count();
+  const double rays = (double)(local.primary_rays + local.bounce_rays + local.shadow_rays);
+  return sec > 0.0 ? rays / sec / 1.0e6 : 0.0;
+}
+
 double RenderAccumulate(Scene &scene, const RenderConfig &config, std::vector<float> &image, std::vector<int> &count,
                         const double eye[3], const double lookat[3], const double up[3], const double quat[4],
                         int num_passes, mb200_render_stats *stats) {

@@ -330,6 +330,11 @@ void RenderPanoramic(Scene &scene, const RenderConfig &config, std::vector<float
 double RenderAccumulate(Scene &scene, const RenderConfig &config, std::vector<float> &image, std::vector<int> &count,
                         const double eye[3], const double lookat[3], const double up[3], const double quat[4],
                         int num_passes, mb200_render_stats *stats = 0);
+// Render + HDRToLDR of DoMainConsole (main_console.cc:57-75) in one device-side step (mb200_render_frame_ldr): only
+// the 8-bit image is copied to the host.  ldr_mode: MB200_LDR_RGB8_LINEAR (HDRToLDR) or MB200_LDR_BGRA8_GAMMA22 (Display).
+double RenderLDR(Scene &scene, const RenderConfig &config, std::vector<unsigned char> &out, const double eye[3],
+                 const double lookat[3], const double up[3], const double quat[4], int num_passes, int ldr_mode,
+                 mb200_render_stats *stats = 0);
 
 // config.json -> RenderConfig (main.cc:98-205): same keys, unknown keys ignored.
 bool LoadJSONConfig(RenderConfig &config, const std::string &filename);

@@ -1144,6 +1144,39 @@ void ora_render_panoramic(const ora_bvh *b, const ora_mesh *mesh, const ora_rend
 /* ======================================================================
  * FNV-1a-64 (SURVEY App. B hashing convention)
  * ==================================================================== */
+/* ======================================================================
+ * Output resolve -- main_console.cc:25-43, main_sdl.cc:156-165,420-477
+ * ==================================================================== */
+/* fclamp, main_console.cc:25-32: `int i = x * 255.5;` is float * double -> double -> int (cvttsd2si) */
+static unsigned char fclamp_console(float x) {
+  int i = x * 255.5;
+  if (i < 0) return 0;
+  if (i > 255) return 255;
+  return (unsigned char)i;
+}
+void ora_hdr_to_ldr(const float *in, const int *in_count, int width, int height, unsigned char *out) {
+  for (long i = 0; i < (long)width * height * 3; i++) out[i] = fclamp_console(in[i] / in_count[i / 3]);
+}
+/* fclamp, main_sdl.cc:156-165 */
+static unsigned char fclamp_display(float x) {
+  float gamma = 2.2f;
+  int i = powf(x, 1.0f / gamma) * 255.5;
+  if (i < 0) return 0;
+  if (i > 255) return 255;
+  return (unsigned char)i;
+}
+void ora_display_bgra(const float *in, const int *counts, int width, int height, unsigned char *out) {
+  for (int y = 0; y < height; y++)
+    for (int x = 0; x < width; x++) {
+      const long p = (long)y * width + x;
+      float scale = 1.0f / (float)counts[p];
+      out[4 * p + 2] = fclamp_display(scale * in[3 * p + 0]);
+      out[4 * p + 1] = fclamp_display(scale * in[3 * p + 1]);
+      out[4 * p + 0] = fclamp_display(scale * in[3 * p + 2]);
+      out[4 * p + 3] = 255;
+    }
+}
+
 uint64_t ora_fnv1a64(const void *data, size_t nbytes, uint64_t seed) {
   const unsigned char *p = (const unsigned char *)data;
   uint64_t h = seed ? seed : 14695981039346656037ULL;

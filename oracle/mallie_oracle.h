@@ -145,6 +145,15 @@ void ora_render_pass_ex(const ora_bvh *b, const ora_mesh *mesh, const ora_render
 void ora_render_panoramic(const ora_bvh *b, const ora_mesh *mesh, const ora_render_params *p, float *image,
                           int *count, int nthreads);
 
+/* --- output resolve --------------------------------------------------------
+ * HDRToLDR + fclamp, main_console.cc:25-43: out[i] = clamp((int)(in[i] / in_count[i / 3] * 255.5)), RGB8.
+ * (pinned: the reference function itself is compiled into oracle/_ref through ref_console.cc.) */
+void ora_hdr_to_ldr(const float *in, const int *in_count, int width, int height, unsigned char *out);
+/* Display + fclamp of the SDL viewer, main_sdl.cc:156-165,420-477: BGRA8, scale = 1.0f / (float)count,
+ * clamp((int)(powf(scale * in, 1.0f / 2.2f) * 255.5)), alpha 255.  (restated only: main_sdl.cc needs SDL headers,
+ * which this image does not have; powf is glibc's, as in the reference build.) */
+void ora_display_bgra(const float *in, const int *counts, int width, int height, unsigned char *out);
+
 /* --- misc ---------------------------------------------------------------- */
 uint64_t ora_fnv1a64(const void *data, size_t nbytes, uint64_t seed /* 0 = standard offset basis */);
 

@@ -301,6 +301,28 @@ def plane_intersect(abcd, rays, t_in):
     return t_out, pos, nrm, hit
 
 
+def hdr_to_ldr(image, count):
+    """HDRToLDR (main_console.cc:34-43): float[H,W,3] + int[H,W] -> uint8[H,W,3]."""
+    img, cnt = np.ascontiguousarray(image, np.float32), np.ascontiguousarray(count, np.int32)
+    h, w = cnt.shape
+    out = np.zeros((h, w, 3), np.uint8)
+    fn = lib().ora_hdr_to_ldr
+    fn.argtypes, fn.restype = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p], None
+    fn(_p(img), _p(cnt), w, h, _p(out))
+    return out
+
+
+def display_bgra(image, count):
+    """Display (main_sdl.cc:420-477): float[H,W,3] + int[H,W] -> uint8[H,W,4] BGRA, gamma 2.2."""
+    img, cnt = np.ascontiguousarray(image, np.float32), np.ascontiguousarray(count, np.int32)
+    h, w = cnt.shape
+    out = np.zeros((h, w, 4), np.uint8)
+    fn = lib().ora_display_bgra
+    fn.argtypes, fn.restype = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p], None
+    fn(_p(img), _p(cnt), w, h, _p(out))
+    return out
+
+
 def rng_stream(pixel, pass_index, n, reference_tid=None):
     st = np.zeros(4, np.uint32)
     if reference_tid is None:

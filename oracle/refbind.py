@@ -223,6 +223,19 @@ def plane_intersect(abcd, rays, t_in):
     return t_out, pos, nrm, hit.astype(bool)
 
 
+def hdr_to_ldr(image, count):
+    """The reference's HDRToLDR (main_console.cc:34-43) itself: float[H,W,3] + int[H,W] -> uint8[H,W,3]."""
+    img = np.ascontiguousarray(image, np.float32)
+    cnt = np.ascontiguousarray(count, np.int32)
+    h, w = cnt.shape
+    out = np.zeros((h, w, 3), np.uint8)
+    fn = lib().ref_hdr_to_ldr
+    fn.argtypes = [C.c_void_p] * 2 + [C.c_int] * 2 + [C.c_void_p]
+    fn.restype = None
+    fn(_p(img), _p(cnt), w, h, _p(out))
+    return out
+
+
 def fnv1a64(data: bytes) -> int:
     """FNV-1a-64 as used for SURVEY App. B goldens (vectorised per byte is slow; use C-ish loop in numpy)."""
     h = 14695981039346656037

@@ -177,7 +177,6 @@ p = sc.render_params(fg, Wd, Ht, shader=M.SHADER_PRIMARY_ONLY, jitter=False)
 img, _, st = sc.render_pass(p)
 o = ob.trace(O.generate_grid(fo, Wd, Ht), row=Wd)
 assert np.array_equal(img[..., 0].reshape(-1) > 0, o["mask"]) and st["shadow_rays"] == 0
-sc.close()
 for plane in (False, True):          # the plane can be hit where the mesh is missed (camera rays that miss the root box too)
     pl = M.plane_from_bounds(*sc.bounds()) if plane else None
     nodes, _ = ob.arrays()
@@ -188,6 +187,7 @@ for plane in (False, True):          # the plane can be hit where the mesh is mi
     for k in (1, 2, 3):
         want += ob.render_pass(fo, Wd, Ht, plane=opl, rng_mode=1, pass_index=k, shader=1, light=(2.0, 4.0, 3.0))[0]
     assert img.tobytes() == want.tobytes() and (cnt == 3).all()
+sc.close()
 print("FUSED-OK")
 """ % T.HERE.rsplit("/", 1)[0]
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
