@@ -268,7 +268,17 @@ def render_frame_multi(scenes, params, num_passes, band_rows=8, image=None, coun
 class Comm:
     """mb200_comm: the NCCL communicator of a frame split over one process per GPU (one Scene replica each)."""
 
+    @staticmethod
+    def _load_order():
+        # the library binds NCCL with dlopen("libnccl.so.2"); if this process is going to use PyTorch as well, torch's
+        # bundled copy has to be the one in the process, so it is loaded first (see csrc/device/gather.cu)
+        try:
+            import torch  # noqa: F401
+        except ImportError:
+            pass
+
     def __init__(self, scene, nranks, rank, unique_id):
+        self._load_order()
         self.h = None
         self.scene = scene
         h = C.c_void_p()
@@ -278,6 +288,7 @@ class Comm:
 
     @staticmethod
     def unique_id():
+        Comm._load_order()
         buf = (C.c_ubyte * 128)()
         check(lib().mb200_comm_unique_id(buf))
         return bytes(buf)

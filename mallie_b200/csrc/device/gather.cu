@@ -11,7 +11,9 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -42,8 +44,13 @@ NcclApi *nccl() {
   static NcclApi api;
   static std::once_flag once;
   std::call_once(once, [] {
-    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
-      api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    // MB200_NCCL_LIB names the library explicitly.  Otherwise the soname: a copy the process has already loaded
+    // (PyTorch's bundled one after `import torch`) is reused by the dynamic loader.  A process that loads PyTorch
+    // AFTER its first mb200_comm_* call would hand torch this (possibly older) copy: import torch first there.
+    const char *forced = getenv("MB200_NCCL_LIB");
+    for (const char *name : {forced, "libnccl.so.2", "libnccl.so"}) {
+      if (!name || !*name) continue;
+      api.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
       if (api.lib) break;
     }
     if (!api.lib) {
@@ -320,16 +327,16 @@ int mb200_render_frame_gathered(mb200_comm *c, const mb200_render_params *p, int
   } else if (stats) {
     memset(stats, 0, sizeof(*stats));
   }
-  if ((rc = mb200_gather_framebuffer(c, p->width, p->height, 3, band_rows, c->send, image)) != MB200_OK) return rc;
   if (count) { // every pixel of a fresh frame has num_passes samples: nothing to gather
     if (device_pointer(count)) {
       k_fill_int<<<148 * 4, 256, 0, s->stream>>>(count, W * H, num_passes);
       mb200::note_launch();
       if (cudaGetLastError() != cudaSuccess) return mb200::capi_set_error(MB200_ERR_CUDA, "count fill failed");
     } else {
-      for (size_t i = 0; i < W * H; i++) count[i] = num_passes;
+      std::fill_n(count, W * H, num_passes); // on the host, while the GPU renders
     }
   }
+  if ((rc = mb200_gather_framebuffer(c, p->width, p->height, 3, band_rows, c->send, image)) != MB200_OK) return rc;
   return MB200_OK;
 }
 
