@@ -5,6 +5,7 @@
 // is NO CPU fallback: without a GPU every compute entry returns MB200_ERR_NO_DEVICE.
 #include <cuda_runtime_api.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -650,16 +651,20 @@ static int render_common(mb200_scene *s, const mb200_render_params *p, int num_p
   if (img_kind != kDevice)
     CU(cudaMemcpyAsync(img_kind == kPinned ? (void *)image : s->out0.pinned, d_img, img_bytes, cudaMemcpyDeviceToHost,
                        s->stream));
-  if (cnt_kind != kDevice)
+  // A fresh frame that covers the buffer has count == num_passes everywhere (every step-th pixel aside): the host
+  // writes it itself while the GPU renders instead of waiting for 4 more bytes per pixel over PCIe.
+  const bool count_is_constant = mode == 2 && covers_all && p->pixel_step <= 1 && cnt_kind != kDevice;
+  if (cnt_kind != kDevice && !count_is_constant)
     CU(cudaMemcpyAsync(cnt_kind == kPinned ? (void *)count : s->out1.pinned, d_cnt, cnt_bytes, cudaMemcpyDeviceToHost,
                        s->stream));
+  if (count_is_constant) std::fill_n(count, npix, num_passes);
   unsigned long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (stats || img_kind != kDevice || cnt_kind != kDevice) {
     if (stats) CU(cudaMemcpyAsync(c, s->d_counters, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
   }
   if (img_kind == kPageable) memcpy(image, s->out0.pinned, img_bytes);
-  if (cnt_kind == kPageable) memcpy(count, s->out1.pinned, cnt_bytes);
+  if (cnt_kind == kPageable && !count_is_constant) memcpy(count, s->out1.pinned, cnt_bytes);
   if (stats) {
     stats->primary_rays = c[0], stats->bounce_rays = c[1], stats->shadow_rays = c[2], stats->zombie_segments = c[3];
     stats->camera_nodes_tested = c[4], stats->camera_tris_tested = c[5];

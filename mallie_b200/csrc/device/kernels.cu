@@ -98,8 +98,15 @@ __global__ void __launch_bounds__(kBlock, MINB)
   LaneSlot slot;
   slot.addr0 = st.sm_addr + (uint32_t)S * st.stride_bytes;
   slot.addr1 = slot.addr0 + st.stride_bytes;
+  uint32_t top_table = 0;
+  if (VAR & kVarTopSmem) { // [stack][lane slots][16 B barrier][top-of-tree table]
+    const uint32_t mbar = st.sm_addr - threadIdx.x * 16u + (uint32_t)(S + (IO::kFused ? 2 : 0)) * st.stride_bytes;
+    top_table = mbar + 16u;
+    if (sc.top_count) stage_top_nodes(sc, mbar, top_table);
+  }
   if (n_dev) n = __ldg(n_dev);
-  trace_state_machine<IO, TRI, S, CAP, ANYHIT, COUNT, REFILL_MIN, SHADE_MIN, CHUNK, VAR>(sc, io, n, work, st, slot, gcounters);
+  trace_state_machine<IO, TRI, S, CAP, ANYHIT, COUNT, REFILL_MIN, SHADE_MIN, CHUNK, VAR>(sc, io, n, work, st, slot, gcounters,
+                                                                                       top_table);
 }
 
 // ---------------------------------------------------------------------------
@@ -524,9 +531,24 @@ __global__ void __launch_bounds__(256) k_pad_tris(const void *__restrict__ src, 
     for (int c = 0; c < 3; c++) v[c] = t.p0[c], v[3 + c] = t.e1[c], v[6 + c] = t.e2[c];
     face = t.face, mat = t.mat;
   }
+  double *o = reinterpret_cast<double *>(reinterpret_cast<char *>(dst) + (size_t)i * 96u);
+  if (kind == kTriWoop) { // traverse.cuh: rows r1, r2, r3 = n of the map into the unit triangle, offsets b = -r . p0
+    const double *p0 = v, *e1 = v + 3, *e2 = v + 6;
+    const double n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+    const double a[3] = {e2[1] * n[2] - e2[2] * n[1], e2[2] * n[0] - e2[0] * n[2], e2[0] * n[1] - e2[1] * n[0]}; // e2 x n
+    const double b[3] = {n[1] * e1[2] - n[2] * e1[1], n[2] * e1[0] - n[0] * e1[2], n[0] * e1[1] - n[1] * e1[0]}; // n x e1
+    const double sa = 1.0 / ((e1[0] * a[0] + e1[1] * a[1]) + e1[2] * a[2]);
+    const double sb = 1.0 / ((e2[0] * b[0] + e2[1] * b[1]) + e2[2] * b[2]);
+    double w[12];
+    for (int c = 0; c < 3; c++) w[c] = a[c] * sa, w[4 + c] = b[c] * sb, w[8 + c] = n[c];
+    w[3] = -((w[0] * p0[0] + w[1] * p0[1]) + w[2] * p0[2]);
+    w[7] = -((w[4] * p0[0] + w[5] * p0[1]) + w[6] * p0[2]);
+    w[11] = -((w[8] * p0[0] + w[9] * p0[1]) + w[10] * p0[2]);
+    for (int c = 0; c < 12; c++) o[c] = w[c];
+    return;
+  }
   v[9] = __longlong_as_double((long long)(((unsigned long long)mat << 32) | face));
   v[10] = v[11] = 0.0;
-  double *o = reinterpret_cast<double *>(reinterpret_cast<char *>(dst) + (size_t)i * 96u);
   for (int c = 0; c < 12; c++) o[c] = v[c];
 }
 
@@ -588,7 +610,8 @@ template <class IO, int TRI, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, i
 cudaError_t launch_sm(const SceneView &sc, const IO &io, size_t n, const unsigned int *n_dev,
                       unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
   auto k = k_trace_sm<IO, TRI, CAP, ANYHIT, COUNT, REFILL_MIN, SHADE_MIN, S, MINB, CHUNK, VAR>;
-  const size_t smem = (size_t)(S + (IO::kFused ? 2 : 0)) * kBlock * sizeof(uint4);
+  size_t smem = (size_t)(S + (IO::kFused ? 2 : 0)) * kBlock * sizeof(uint4);
+  if (VAR & kVarTopSmem) smem += 16 + (size_t)sc.top_count * kTopSlotBytes;
   static int grids[64]; // per instantiation, per device
   int grid = 0;
   const cudaError_t ge = persistent_grid(k, smem, MINB, grids, &grid);
@@ -612,6 +635,8 @@ cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const
     if (var == 104) return MB200_SM(kRefillMin, 4, S, kMinBlocks, kChunk, 0);      // shade step at 4 parked lanes
     if (var == 116) return MB200_SM(kRefillMin, 16, S, kMinBlocks, kChunk, 0);     // ... at 16
     if (var == 212) return MB200_SM(12, 12, S, kMinBlocks, kChunk, 0);             // refill and shade at 12
+    if (var == 2) return MB200_SM(kRefillMin, kShadeMin, 0, kMinBlocks, kChunk, kVarTopSmem);  // top of the tree in shared memory
+    if (var == 300) return MB200_SM(kRefillMin, kShadeMin, 0, kMinBlocks, kChunk, 0);   // control for it: stack in local memory
     if (var == 308) return MB200_SM(kRefillMin, kShadeMin, 8, kMinBlocks, kChunk, 0);  // 8 stack entries in shared memory
     if (var == 306) return MB200_SM(kRefillMin, kShadeMin, 6, kMinBlocks, kChunk, 0);  // 6 (more L1)
   }
@@ -635,6 +660,7 @@ cudaError_t launch_trace_kind(const SceneView &sc, int stack_cap, const IO &io, 
 #ifdef MB200_DEV_VARIANTS // A/B: padded traversal records (MB200_TRI_LAYOUT, scene.cc)
     MB200_KIND(kTriF32x64)
     MB200_KIND(kTriF64x96)
+    MB200_KIND(kTriWoop)
 #endif
   }
 #undef MB200_KIND

@@ -36,6 +36,7 @@
 namespace mb200 {
 
 static const uint32_t kBranch = 0xFFFFFFFFu;
+static const uint32_t kTopBit = 0x80000000u; // ref of a branch child that lives in the staged top-of-tree table
 
 struct alignas(128) PairNode {
   double box[2][6];
@@ -71,7 +72,12 @@ static_assert(sizeof(TriRecordF64) == 80, "TriRecordF64");
 //   kTriF64x96  96 B : p0, e1, e2 as doubles | faceID, materialID | padding  -> 3 x LDG.256, no conversions and no
 //                      edge subtractions in the kernel (e = (double)p1 - (double)p0 is formed once, by the layout
 //                      kernel, with the same single IEEE subtraction TriangleIsect performs, bvh_accel.cc:600-603)
-enum TriKind : int { kTriF32 = 0, kTriF64 = 1, kTriF32x64 = 2, kTriF64x96 = 3 };
+//   kTriWoop    96 B : Woop's affine map into the unit triangle (rows r1, r2, r3 = n and offsets b = -r . p0, doubles);
+//                      faceID / materialID are read from the canonical record when a hit is accepted.  NOT exact: its
+//                      roundings differ from TriangleIsect's, so hit records are not bit-identical to the reference.
+//                      Development builds only, to measure what north_star's "Woop-packed triangles" would buy and
+//                      cost (tools/woop_report.py).
+enum TriKind : int { kTriF32 = 0, kTriF64 = 1, kTriF32x64 = 2, kTriF64x96 = 3, kTriWoop = 4 };
 #ifdef __CUDACC__
 __host__ __device__
 #endif
@@ -117,6 +123,11 @@ struct SceneView {
   int tri_f32;               // 1 = TriRecordF32
   const void *trav_tris;     // what the traversal kernels read: `tris`, or a padded copy of it (TriKind)
   int tri_kind;              // TriKind of trav_tris
+  // Development variant (MB200_TOP_NODES=K, kVarTopSmem): the first K pair nodes in breadth-first order, child refs
+  // that stay inside the table re-numbered and tagged with kTopBit; every CTA stages the table into shared memory
+  // with cp.async.bulk at kernel start (trace_sm.cuh).
+  const PairNode *top_nodes;
+  uint32_t top_count;
   // verbatim mesh (mesh.h:7-18) for BuildIntersection
   const double *vertices;    // [3*nv]
   const uint32_t *faces;     // [3*nf]

@@ -234,6 +234,7 @@ static int wanted_tri_kind(const SceneView &v) {
   const char *e = getenv("MB200_TRI_LAYOUT");
   const int want = e ? atoi(e) : 0;
   if (want == 96) return kTriF64x96;
+  if (e && !strcmp(e, "woop")) return kTriWoop; // not bit-exact: measurement only (layout.h)
   if (want == 64 && v.tri_f32) return kTriF32x64;
   return v.tri_f32 ? kTriF32 : kTriF64;
 }
@@ -267,6 +268,45 @@ int scene_finish(mb200_scene *s, std::string *err) {
       return e == cudaErrorMemoryAllocation ? MB200_ERR_OUT_OF_MEMORY : MB200_ERR_CUDA;
     }
     v.trav_tris = pad, v.tri_kind = kind;
+  }
+  // top-of-tree table for the shared-memory staging variant (development builds; layout.h)
+  v.top_nodes = nullptr, v.top_count = 0;
+  const char *tn = getenv("MB200_TOP_NODES");
+  const int want_top = tn ? atoi(tn) : 0;
+  if (want_top > 0 && !v.empty && v.root_cnt == kBranch && v.num_pair_nodes > 0) {
+    std::vector<PairNode> all(v.num_pair_nodes);
+    if ((e = cudaMemcpyAsync(all.data(), v.nodes, all.size() * sizeof(PairNode), cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(s->stream)) != cudaSuccess) {
+      if (err) *err = std::string("top-of-tree table: ") + cudaGetErrorString(e);
+      return MB200_ERR_CUDA;
+    }
+    std::vector<uint32_t> order; // breadth-first from the root pair
+    std::vector<uint32_t> slot(v.num_pair_nodes, 0xFFFFFFFFu);
+    order.push_back(v.root_ref);
+    slot[v.root_ref] = 0;
+    for (size_t head = 0; head < order.size() && order.size() < (size_t)want_top; head++)
+      for (int c = 0; c < 2 && order.size() < (size_t)want_top; c++) {
+        const PairNode &n = all[order[head]];
+        if (n.cnt[c] == kBranch && slot[n.ref[c]] == 0xFFFFFFFFu) {
+          slot[n.ref[c]] = (uint32_t)order.size();
+          order.push_back(n.ref[c]);
+        }
+      }
+    std::vector<PairNode> top(order.size());
+    for (size_t i = 0; i < order.size(); i++) {
+      top[i] = all[order[i]];
+      for (int c = 0; c < 2; c++)
+        if (top[i].cnt[c] == kBranch && slot[top[i].ref[c]] != 0xFFFFFFFFu) top[i].ref[c] = slot[top[i].ref[c]] | kTopBit;
+    }
+    void *d_top = nullptr;
+    if ((e = cudaMalloc(&d_top, top.size() * sizeof(PairNode))) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_top, top.data(), top.size() * sizeof(PairNode), cudaMemcpyHostToDevice, s->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(s->stream)) != cudaSuccess) {
+      if (err) *err = std::string("top-of-tree table: ") + cudaGetErrorString(e);
+      return MB200_ERR_CUDA;
+    }
+    s->allocs.push_back(d_top);
+    v.top_nodes = (const PairNode *)d_top, v.top_count = (uint32_t)top.size();
   }
   if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) {
     if (err) *err = std::string("upload: ") + cudaGetErrorString(e);

@@ -283,7 +283,40 @@ template <bool PINHOLE> struct IOFrameFusedT {
 // gone from the source; their logs are profiles/r1_ab*.log and DESIGN.md §5 lists them.
 //   1  inner step: when all lanes in the step share the direction-sign mask, a copy of the two slab tests
 //      specialised for that octant runs (no per-axis selects)
-constexpr int kVarOctant = 1;
+//   2  the top of the tree (SceneView::top_nodes, breadth-first, MB200_TOP_NODES=K) is staged into shared memory by
+//      every CTA with cp.async.bulk (one 128-byte bulk copy per node into a 144-byte slot: lanes that read different
+//      nodes then hit different banks) and inner steps whose ref carries kTopBit read it with LDS.128; the traversal
+//      stack moves to local memory to make room
+constexpr int kVarOctant = 1, kVarTopSmem = 2;
+constexpr uint32_t kTopSlotBytes = 144;
+
+// Stages sc.top_nodes into shared memory at `table` (shared-window address; 16-byte aligned) and waits for it.
+// mbar: 8 bytes of shared memory for the transaction barrier.
+__device__ __forceinline__ void stage_top_nodes(const SceneView &sc, uint32_t mbar, uint32_t table) {
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(sc.top_count * 128u) : "memory");
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < sc.top_count; i += blockDim.x)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     table + i * kTopSlotBytes),
+                 "l"(sc.top_nodes + i), "r"(128), "r"(mbar)
+                 : "memory");
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done)
+                 : "r"(mbar), "r"(0)
+                 : "memory");
+}
+
+__device__ __forceinline__ void lds128(uint32_t addr, double &a, double &b) {
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
 
 struct NodeWords { // one PairNode as loaded
   double b[2][6];
@@ -308,13 +341,26 @@ __device__ __forceinline__ NodeWords load_pair_node(const PairNode *n) {
   return w;
 }
 
+// the same node from the staged table (eight LDS.128)
+__device__ __forceinline__ NodeWords load_pair_node_smem(uint32_t addr) {
+  NodeWords w;
+#pragma unroll
+  for (int k = 0; k < 6; k++) lds128(addr + 16 * k, (&w.b[0][0])[2 * k], (&w.b[0][0])[2 * k + 1]);
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.ref0), "=r"(w.ref1), "=r"(w.cnt0), "=r"(w.cnt1) : "r"(addr + 96));
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w.axis) : "r"(addr + 112));
+  return w;
+}
+
 // counters of a launch: [0..3] nodes, tris, rays, max stack of closest-hit (camera) rays; fused frames add
 // [4..6] nodes, tris, rays of the shadow rays
 template <class IO, int TRI, int S, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int SHADE_MIN, unsigned CHUNK, int VAR>
 __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const IO &io, unsigned long long n,
                                                     unsigned long long *work, TravStack<S, CAP> &st,
-                                                    const LaneSlot slot, unsigned long long *gcounters) {
+                                                    const LaneSlot slot, unsigned long long *gcounters,
+                                                    uint32_t top_table = 0) {
   const unsigned lane = threadIdx.x & 31u;
+  // top-of-tree staging variant: the root pair is entry 0 of the table
+  const uint32_t root_ref = ((VAR & kVarTopSmem) && sc.top_count && sc.root_cnt == kBranch) ? kTopBit : sc.root_ref;
   const unsigned lt_mask = (1u << lane) - 1u;
 
   RayD r;
@@ -339,7 +385,7 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
                         hit_t, tm);
     }
     if (enter && sc.root_cnt != 0u) {
-      ref = sc.root_ref, rc = sc.root_cnt;
+      ref = root_ref, rc = sc.root_cnt;
       if (COUNT && rc != kBranch) (shadow ? cnt_s.tris : cnt.tris) += rc;
       return true;
     }
@@ -429,7 +475,9 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
     const bool at_inner = (rc == kBranch);
     const bool at_leaf = (rc - 1u) < (kShade - 1u); // 1 <= rc < kShade
     if (at_inner) {
-      const NodeWords nw = load_pair_node(sc.nodes + ref);
+      NodeWords nw;
+      if ((VAR & kVarTopSmem) && (ref & kTopBit)) nw = load_pair_node_smem(top_table + (ref & ~kTopBit) * kTopSlotBytes);
+      else nw = load_pair_node(sc.nodes + ref);
       double t0, t1;
       bool h0, h1;
       bool done = false;
@@ -469,9 +517,19 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
       if (COUNT && rc != 0u && rc != kBranch) (shadow ? cnt_s.tris : cnt.tris) += rc;
     } else if (at_leaf) {
       // ---- LEAF: one triangle of TestLeafNode (bvh_accel.cc:640-697), in indices_ order -----------------
-      const TriEdges tv = load_tri_edges<TRI>(sc.trav_tris, ref);
       double u, v;
-      if (tri_test_edges(hit_t, u, v, tv, r)) {
+      bool accepted;
+      uint32_t tface = 0, tmat = 0;
+      if constexpr (TRI == kTriWoop) { // development variant, not bit-exact (traverse.cuh)
+        const WoopRec wr = load_woop(sc.trav_tris, ref);
+        accepted = tri_test_woop(hit_t, u, v, wr, r);
+        if (accepted) tri_ids(sc.tris, sc.tri_f32, ref, tface, tmat);
+      } else {
+        const TriEdges tv = load_tri_edges<TRI>(sc.trav_tris, ref);
+        accepted = tri_test_edges(hit_t, u, v, tv, r);
+        tface = tv.face, tmat = tv.mat;
+      }
+      if (accepted) {
         bool stop = false;
         if constexpr (IO::kFused) {
           if (item & kShadowBit) {
@@ -479,10 +537,10 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
             if (stop) io.contrib[item & ~kShadowBit] = 0.f;
           } else {
             slot.put_uv(u, v);
-            slot.put_ids(tv.face, tv.mat);
+            slot.put_ids(tface, tmat);
           }
         } else {
-          io.accept(item, hit_t, u, v, tv.face, tv.mat);
+          io.accept(item, hit_t, u, v, tface, tmat);
           if (ANYHIT && hit_t < tmax_any) { // occluded: closest-hit Traverse would return t < tmax
             io.finish(item, true);
             stop = true;

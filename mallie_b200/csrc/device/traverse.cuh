@@ -172,6 +172,55 @@ template <> __device__ __forceinline__ TriEdges load_tri_edges<kTriF64x96>(const
   return t;
 }
 
+// ---- Woop's test (development variant, NOT bit-exact with TriangleIsect) -------------------------------------
+// The record maps world space onto the triangle's own frame, in which it is (0,0,0) (1,0,0) (0,1,0):
+//   r3 = n = e1 x e2 (so r3 . d = -det of TriangleIsect and the same |det| < eps rejection applies),
+//   r1 = (e2 x n) / (e1 . (e2 x n)),  r2 = (n x e1) / (e2 . (n x e1)),  b_k = -r_k . p0.
+//   t = -(r3 . o + b3) / (r3 . d),  u = (r1 . o + b1) + t (r1 . d),  v = (r2 . o + b2) + t (r2 . d)
+// 20 multiplies, 17 additions and one division against Moeller-Trumbore's 27 + 17 (edges precomputed) + one.
+struct WoopRec {
+  double r1x, r1y, r1z, b1, r2x, r2y, r2z, b2, r3x, r3y, r3z, b3;
+};
+__device__ __forceinline__ WoopRec load_woop(const void *tris, uint32_t i) {
+  const char *p = reinterpret_cast<const char *>(tris) + (size_t)i * 96u;
+  double v[12];
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[4 * k]), "=d"(v[4 * k + 1]), "=d"(v[4 * k + 2]), "=d"(v[4 * k + 3])
+                 : "l"(p + 32 * k));
+  return WoopRec{v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]};
+}
+__device__ __forceinline__ bool tri_test_woop(double &t_io, double &u_out, double &v_out, const WoopRec &w, const RayD &r) {
+  const double dz = (w.r3x * r.dx + w.r3y * r.dy) + w.r3z * r.dz;
+  if (fabs(dz) < MB200_TRI_EPS) return false;
+  const double oz = ((w.r3x * r.ox + w.r3y * r.oy) + w.r3z * r.oz) + w.b3;
+  const double t = -oz / dz;
+  const double ox = ((w.r1x * r.ox + w.r1y * r.oy) + w.r1z * r.oz) + w.b1;
+  const double dx = (w.r1x * r.dx + w.r1y * r.dy) + w.r1z * r.dz;
+  const double u = ox + t * dx;
+  const double oy = ((w.r2x * r.ox + w.r2y * r.oy) + w.r2z * r.oz) + w.b2;
+  const double dy = (w.r2x * r.dx + w.r2y * r.dy) + w.r2z * r.dz;
+  const double v = oy + t * dy;
+  if (u < 0.0 || u > 1.0) return false;
+  if (v < 0.0 || u + v > 1.0) return false;
+  if (t < 0.0 || t > t_io) return false;
+  t_io = t;
+  u_out = u;
+  v_out = v;
+  return true;
+}
+// faceID / materialID of canonical record i (read on accept only)
+__device__ __forceinline__ void tri_ids(const void *tris, int tri_f32, uint32_t i, uint32_t &face, uint32_t &mat) {
+  if (tri_f32) {
+    const TriRecordF32 *t = reinterpret_cast<const TriRecordF32 *>(tris) + i;
+    face = __ldg(&t->face), mat = __ldg(&t->mat);
+  } else {
+    const TriRecordF64 *t = reinterpret_cast<const TriRecordF64 *>(tris) + i;
+    face = __ldg(&t->face), mat = __ldg(&t->mat);
+  }
+}
+
 // TriangleIsect (bvh_accel.cc:595-638): Moeller-Trumbore, no culling.
 __device__ __forceinline__ bool tri_test_edges(double &t_io, double &u_out, double &v_out, const TriEdges &k,
                                                const RayD &r) {

@@ -11,3 +11,5 @@ run MB200_TRACE_VAR=104 MB200_TRI_LAYOUT=96
 run MB200_FRAME_FUSED=0 MB200_TRI_LAYOUT=96
 run MB200_FRAME_FUSED=0 MB200_TRACE_VAR=1
 run MB200_FRAME_FUSED=0 MB200_TRACE_VAR=1 MB200_TRI_LAYOUT=96
+# Woop record (not bit-exact): frame time only, the image differs by construction
+run MB200_TRI_LAYOUT=woop

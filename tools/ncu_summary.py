@@ -13,6 +13,9 @@ rep = sys.argv[1]
 skip = sys.argv[2] if len(sys.argv) > 2 else "0"   # which launch of the report
 SEL = ["--launch-skip", skip, "--launch-count", "1"]
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+        "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum", "l1tex__data_pipe_lsu_wavefronts.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
         "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "l1tex__t_bytes.sum",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
         "launch__occupancy_limit_shared_mem", "launch__shared_mem_per_block_dynamic",

@@ -15,6 +15,6 @@ sc = M.Scene.build(v, f, want_bvh=False)
 frame = M.camera_frame((0, 0, 3), (0, 0, 0), width=W, height=H)
 p = sc.render_params(frame, W, H, shader=M.SHADER_PRIMARY_SHADOW, light=(2.0, 4.0, 3.0))
 for _ in range(int(os.environ.get("PROF_FRAMES", "1"))):
-    img, cnt, st = sc.render_frame(p, SPP)
-print(st, float(img.sum()))
+    img, cnt, st = sc.render_frame(p, SPP, stats=False)     # stats=True would launch the counting instantiations
+print(float(img.sum()))
 sc.close()
