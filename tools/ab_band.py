@@ -13,12 +13,12 @@ from mallie_b200.procedural import bumpy_sphere  # noqa: E402
 
 W, H, SPP = 1920, 1080, 16
 v, f = bumpy_sphere(500)
-sc = M.Scene(v, f)
+sc = M.Scene.build(v, f, want_bvh=False)
 frame = M.camera_frame((0, 0, 3), (0, 0, 0), width=W, height=H)
 stream = torch.cuda.ExternalStream(sc.stream())
 L, C = M.capi.lib(), M.capi.C
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-for N in (1, 2, 4, 8):
+for N in tuple(int(x) for x in os.environ.get("AB_N", "1,2,4,8").split(",")):
     bands = (4, N, 0) if N > 1 else None
     p = sc.render_params(frame, W, H, shader=M.SHADER_PRIMARY_SHADOW, light=(2.0, 4.0, 3.0), bands=bands, compact=N > 1)
     rows = sc.band_local_rows(p) if N > 1 else H
