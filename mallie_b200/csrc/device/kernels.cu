@@ -19,6 +19,7 @@
 
 #include "shade.cuh"
 #include "trace_sm.cuh"
+#include "trace_tr.cuh"
 #include "traverse.cuh"
 
 namespace mb200 {
@@ -107,6 +108,18 @@ __global__ void __launch_bounds__(kBlock, MINB)
   if (n_dev) n = __ldg(n_dev);
   trace_state_machine<IO, TRI, S, CAP, ANYHIT, COUNT, REFILL_MIN, SHADE_MIN, CHUNK, VAR>(sc, io, n, work, st, slot, gcounters,
                                                                                        top_table);
+}
+
+// The two-rays-per-lane machine (trace_tr.cuh): the rays' read-only halves in dynamic shared memory.
+template <class IO, int TRI, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int HYST, int MINB, unsigned CHUNK>
+__global__ void __launch_bounds__(kBlock, MINB)
+    k_trace_tr(const __grid_constant__ SceneView sc, const __grid_constant__ IO io, unsigned long long n,
+               const unsigned int *__restrict__ n_dev, unsigned long long *__restrict__ work,
+               unsigned long long *__restrict__ gcounters) {
+  extern __shared__ uint4 smem_fat[]; // [2 rays x kFatUnits][kBlock], column layout
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_fat + threadIdx.x);
+  if (n_dev) n = __ldg(n_dev);
+  trace_two_ray_machine<IO, TRI, CAP, ANYHIT, COUNT, REFILL_MIN, HYST, CHUNK>(sc, io, n, work, base, kBlock * 16u, gcounters);
 }
 
 // ---------------------------------------------------------------------------
@@ -505,6 +518,32 @@ __global__ void k_add_stats_fused(const unsigned long long *__restrict__ batch, 
   if (t < 8 && map[t] >= 0 && batch[map[t]]) atomicAdd(&total[t], batch[map[t]]);
 }
 
+// 64-byte copies of the pair nodes (layout.h: PairNode64).  *bad is set when a box coordinate is not (float -/+ kEPS)
+// exactly or a leaf holds more than 65 534 triangles: the scene then keeps its 128-byte nodes.
+__global__ void __launch_bounds__(256) k_pack_nodes64(const PairNode *__restrict__ src, uint32_t n, PairNode64 *__restrict__ dst,
+                                                      int *__restrict__ bad) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const PairNode s = src[i];
+  PairNode64 o;
+  bool ok = true;
+  for (int c = 0; c < 2; c++) {
+    for (int k = 0; k < 6; k++) {
+      const double v = s.box[c][k];
+      const float f = (float)(k < 3 ? v + MB200_TRI_EPS : v - MB200_TRI_EPS);
+      const double back = k < 3 ? (double)f - MB200_TRI_EPS : (double)f + MB200_TRI_EPS;
+      ok &= __double_as_longlong(back) == __double_as_longlong(v);
+      o.box[c][k] = f;
+    }
+    o.ref[c] = s.ref[c];
+    ok &= s.cnt[c] == kBranch || s.cnt[c] < 0xFFFFu;
+    o.cnt[c] = s.cnt[c] == kBranch ? (uint16_t)0xFFFFu : (uint16_t)s.cnt[c];
+  }
+  o.axis = s.axis;
+  dst[i] = o;
+  if (!ok) atomicOr(bad, 1);
+}
+
 // Traversal copies of the triangle records (layout.h: TriKind).  One thread per record.
 __global__ void __launch_bounds__(256) k_pad_tris(const void *__restrict__ src, int src_f32, uint32_t n, int kind,
                                                   void *__restrict__ dst) {
@@ -621,6 +660,20 @@ cudaError_t launch_sm(const SceneView &sc, const IO &io, size_t n, const unsigne
   return cudaGetLastError();
 }
 
+template <class IO, int TRI, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int HYST, int MINB, unsigned CHUNK>
+cudaError_t launch_tr(const SceneView &sc, const IO &io, size_t n, const unsigned int *n_dev, unsigned long long *work,
+                      unsigned long long *counters, cudaStream_t s) {
+  auto k = k_trace_tr<IO, TRI, CAP, ANYHIT, COUNT, REFILL_MIN, HYST, MINB, CHUNK>;
+  const size_t smem = (size_t)2 * kFatUnits * kBlock * sizeof(uint4);
+  static int grids[64]; // per instantiation, per device
+  int grid = 0;
+  const cudaError_t ge = persistent_grid(k, smem, MINB, grids, &grid);
+  if (ge != cudaSuccess) return ge;
+  k<<<grid, kBlock, smem, s>>>(sc, io, (unsigned long long)n, n_dev, work, counters);
+  g_launches++;
+  return cudaGetLastError();
+}
+
 // Picks the kernel instantiation: production parameters, or (development builds, -DMB200_DEV_VARIANTS)
 // the A/B variants selected with MB200_TRACE_VAR.
 template <class IO, int TRI, int CAP, bool ANYHIT, bool COUNT>
@@ -629,12 +682,24 @@ cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const
   constexpr int S = IO::kFused ? kSmemStackFused : kSmemStack;
 #define MB200_SM(R, H, SS, B, C, V) launch_sm<IO, TRI, CAP, ANYHIT, COUNT, R, H, SS, B, C, V>(sc, io, n, n_dev, work, counters, s)
 #ifdef MB200_DEV_VARIANTS
+  if constexpr (!IO::kFused && CAP <= 64 && (TRI == kTriF32 || TRI == kTriF64)) {
+    // two rays per lane, one body per iteration (trace_tr.cuh): MB200_TRACE_TR = hysteresis of the vote (0, 4, 8) + 1
+    static const int tr = env_int("MB200_TRACE_TR", 0);
+#define MB200_TR(R, H, B) launch_tr<IO, TRI, CAP, ANYHIT, COUNT, R, H, B, kChunk>(sc, io, n, n_dev, work, counters, s)
+    if (tr == 1) return MB200_TR(kRefillMin, 0, kMinBlocks);
+    if (tr == 5) return MB200_TR(kRefillMin, 4, kMinBlocks);
+    if (tr == 9) return MB200_TR(kRefillMin, 8, kMinBlocks);
+    if (tr == 105) return MB200_TR(4, 4, kMinBlocks);
+    if (tr == 205) return MB200_TR(16, 4, kMinBlocks);
+#undef MB200_TR
+  }
   if constexpr (!COUNT && CAP <= 64) {
     static const int var = env_int("MB200_TRACE_VAR", -1); // -1 = not set: the production instantiation
     if (var == 1) return MB200_SM(kRefillMin, kShadeMin, S, kMinBlocks, kChunk, kVarOctant);
     if (var == 104) return MB200_SM(kRefillMin, 4, S, kMinBlocks, kChunk, 0);      // shade step at 4 parked lanes
     if (var == 116) return MB200_SM(kRefillMin, 16, S, kMinBlocks, kChunk, 0);     // ... at 16
     if (var == 212) return MB200_SM(12, 12, S, kMinBlocks, kChunk, 0);             // refill and shade at 12
+    if (var == 4 && sc.nodes64) return MB200_SM(kRefillMin, kShadeMin, S, kMinBlocks, kChunk, kVarNode64);  // 64-byte pair nodes
     if (var == 2) return MB200_SM(kRefillMin, kShadeMin, 0, kMinBlocks, kChunk, kVarTopSmem);  // top of the tree in shared memory
     if (var == 300) return MB200_SM(kRefillMin, kShadeMin, 0, kMinBlocks, kChunk, 0);   // control for it: stack in local memory
     if (var == 308) return MB200_SM(kRefillMin, kShadeMin, 8, kMinBlocks, kChunk, 0);  // 8 stack entries in shared memory
@@ -1097,6 +1162,13 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
 cudaError_t launch_resolve_ldr(const float *image, const int *count, size_t npix, int mode, unsigned char *out, cudaStream_t s) {
   if (npix == 0) return cudaSuccess;
   k_resolve_ldr<<<flat_grid(npix, 256), 256, 0, s>>>(image, count, npix, mode, out);
+  g_launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_nodes64(const PairNode *src, size_t n, PairNode64 *dst, int *bad, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  k_pack_nodes64<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, (uint32_t)n, dst, bad);
   g_launches++;
   return cudaGetLastError();
 }

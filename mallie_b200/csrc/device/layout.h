@@ -47,6 +47,18 @@ struct alignas(128) PairNode {
 };
 static_assert(sizeof(PairNode) == 128, "PairNode must be one 128-byte line");
 
+// Development variant (MB200_NODE_LAYOUT=64, kVarNode64): the same pair node in 64 bytes.  Every box coordinate the
+// reference builder produces is (vertex coordinate -/+ kEPS) rounded once to double (bvh_accel.cc:285-315); when the
+// vertices are float-exact the coordinate is therefore determined by that float, and the kernel rebuilds the exact
+// double with one conversion and one addition.  Two 256-bit loads (two L1 wavefronts per lane) instead of four.
+struct alignas(64) PairNode64 {
+  float box[2][6];  // the float f with (double)f -/+ kEPS == the exact box coordinate (checked when the copy is made)
+  uint32_t ref[2];
+  uint16_t cnt[2];  // 0xFFFF = branch
+  uint32_t axis;
+};
+static_assert(sizeof(PairNode64) == 64, "PairNode64");
+
 struct alignas(16) TriRecordF32 {
   float p0[3];
   uint32_t face;
@@ -128,6 +140,7 @@ struct SceneView {
   // with cp.async.bulk at kernel start (trace_sm.cuh).
   const PairNode *top_nodes;
   uint32_t top_count;
+  const PairNode64 *nodes64; // development variant kVarNode64 (null: not available for this scene)
   // verbatim mesh (mesh.h:7-18) for BuildIntersection
   const double *vertices;    // [3*nv]
   const uint32_t *faces;     // [3*nf]

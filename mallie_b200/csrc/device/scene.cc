@@ -269,6 +269,26 @@ int scene_finish(mb200_scene *s, std::string *err) {
     }
     v.trav_tris = pad, v.tri_kind = kind;
   }
+  // 64-byte pair nodes (development builds; layout.h: PairNode64)
+  v.nodes64 = nullptr;
+  const char *nl = getenv("MB200_NODE_LAYOUT");
+  if (nl && atoi(nl) == 64 && !v.empty && v.num_pair_nodes > 0 && v.tri_f32) {
+    void *d64 = nullptr;
+    int *d_bad = nullptr, bad = 1;
+    if ((e = cudaMalloc(&d64, (size_t)v.num_pair_nodes * sizeof(PairNode64))) == cudaSuccess &&
+        (e = cudaMalloc((void **)&d_bad, sizeof(int))) == cudaSuccess &&
+        (e = cudaMemsetAsync(d_bad, 0, sizeof(int), s->stream)) == cudaSuccess &&
+        (e = launch_pack_nodes64(v.nodes, v.num_pair_nodes, (PairNode64 *)d64, d_bad, s->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s->stream)) == cudaSuccess)
+      e = cudaStreamSynchronize(s->stream);
+    if (d_bad) cudaFree(d_bad);
+    if (e != cudaSuccess) {
+      if (err) *err = std::string("64-byte pair nodes: ") + cudaGetErrorString(e);
+      return MB200_ERR_CUDA;
+    }
+    if (bad) cudaFree(d64); // some coordinate is not float -/+ kEPS: keep the 128-byte nodes
+    else s->allocs.push_back(d64), s->device_bytes += (size_t)v.num_pair_nodes * sizeof(PairNode64), v.nodes64 = (const PairNode64 *)d64;
+  }
   // top-of-tree table for the shared-memory staging variant (development builds; layout.h)
   v.top_nodes = nullptr, v.top_count = 0;
   const char *tn = getenv("MB200_TOP_NODES");

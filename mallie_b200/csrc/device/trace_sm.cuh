@@ -287,7 +287,9 @@ template <bool PINHOLE> struct IOFrameFusedT {
 //      every CTA with cp.async.bulk (one 128-byte bulk copy per node into a 144-byte slot: lanes that read different
 //      nodes then hit different banks) and inner steps whose ref carries kTopBit read it with LDS.128; the traversal
 //      stack moves to local memory to make room
-constexpr int kVarOctant = 1, kVarTopSmem = 2;
+//   4  64-byte pair nodes (layout.h: PairNode64): two 256-bit loads per visit, the exact doubles rebuilt with twelve
+//      conversions and twelve additions
+constexpr int kVarOctant = 1, kVarTopSmem = 2, kVarNode64 = 4;
 constexpr uint32_t kTopSlotBytes = 144;
 
 // Stages sc.top_nodes into shared memory at `table` (shared-window address; 16-byte aligned) and waits for it.
@@ -338,6 +340,34 @@ __device__ __forceinline__ NodeWords load_pair_node(const PairNode *n) {
                : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3), "=r"(m4), "=r"(m5), "=r"(m6), "=r"(m7)
                : "l"(p + 96));
   w.ref0 = m0, w.ref1 = m1, w.cnt0 = m2, w.cnt1 = m3, w.axis = m4;
+  return w;
+}
+
+// the 64-byte form: float f per coordinate, exact double = (double)f -/+ kEPS (layout.h)
+__device__ __forceinline__ NodeWords load_pair_node64(const PairNode64 *n) {
+  NodeWords w;
+  const char *p = reinterpret_cast<const char *>(n);
+  float f[12];
+  uint32_t m0, m1, m2, m3;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7])
+               : "l"(p));
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(*reinterpret_cast<uint32_t *>(&f[8])), "=r"(*reinterpret_cast<uint32_t *>(&f[9])),
+                 "=r"(*reinterpret_cast<uint32_t *>(&f[10])), "=r"(*reinterpret_cast<uint32_t *>(&f[11])), "=r"(m0), "=r"(m1),
+                 "=r"(m2), "=r"(m3)
+               : "l"(p + 32));
+#pragma unroll
+  for (int c = 0; c < 2; c++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      w.b[c][k] = (double)f[6 * c + k] - MB200_TRI_EPS;         // bmin: vertex - kEPS (bvh_accel.cc:293-306)
+      w.b[c][3 + k] = (double)f[6 * c + 3 + k] + MB200_TRI_EPS; // bmax: vertex + kEPS
+    }
+  w.ref0 = m0, w.ref1 = m1;
+  const uint32_t c0 = m2 & 0xFFFFu, c1 = m2 >> 16;
+  w.cnt0 = c0 == 0xFFFFu ? kBranch : c0, w.cnt1 = c1 == 0xFFFFu ? kBranch : c1;
+  w.axis = m3;
   return w;
 }
 
@@ -477,6 +507,7 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
     if (at_inner) {
       NodeWords nw;
       if ((VAR & kVarTopSmem) && (ref & kTopBit)) nw = load_pair_node_smem(top_table + (ref & ~kTopBit) * kTopSlotBytes);
+      else if (VAR & kVarNode64) nw = load_pair_node64(sc.nodes64 + ref);
       else nw = load_pair_node(sc.nodes + ref);
       double t0, t1;
       bool h0, h1;
