@@ -35,7 +35,7 @@ constexpr int kSmemStack = 12;  // stack entries per thread kept in shared memor
 constexpr int kSmemStackFused = 10; // fused frames: two more 16-byte units per thread hold the lane slot
 constexpr int kMinBlocks = 8;   // resident CTAs per SM the register allocation targets (64 registers)
 constexpr unsigned kChunk = 32; // ray indices per atomicAdd
-constexpr int kVar = 0;         // code-generation variants (trace_sm.cuh)
+constexpr int kVar = kVarOctNodes; // octant copies of the pair nodes: no sign selects in the inner step (trace_sm.cuh)
 
 __device__ __forceinline__ unsigned int lane_id() { return threadIdx.x & 31u; }
 
@@ -518,6 +518,30 @@ __global__ void k_add_stats_fused(const unsigned long long *__restrict__ batch, 
   if (t < 8 && map[t] >= 0 && batch[map[t]]) atomicAdd(&total[t], batch[map[t]]);
 }
 
+// Octant copies of the pair nodes (layout.h: nodes_oct): one thread per (node, octant).
+__global__ void __launch_bounds__(256) k_octant_nodes(const PairNode *__restrict__ src, uint32_t n, PairNode *__restrict__ dst) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * 8) return;
+  const uint32_t oct = (uint32_t)(i / n), k = (uint32_t)(i - (size_t)oct * n);
+  const PairNode s = src[k];
+  const bool swap = ((oct >> s.axis) & 1u) != 0u; // dirSign[axis] = 1: data[1] is the near child (bvh_accel.cc:818-823)
+  PairNode o;
+  for (int c = 0; c < 2; c++) {
+    const int from = swap ? 1 - c : c;
+    for (int a = 0; a < 3; a++) {
+      const bool neg = ((oct >> a) & 1u) != 0u; // IntersectRayAABB: min plane = dirSign ? bmax : bmin (bvh_accel.cc:556-561)
+      o.box[c][a] = neg ? s.box[from][3 + a] : s.box[from][a];
+      o.box[c][3 + a] = neg ? s.box[from][a] : s.box[from][3 + a];
+    }
+    // a branch child is addressed inside the same copy: absolute index, so the walk needs no per-ray offset
+    o.ref[c] = s.cnt[from] == kBranch ? oct * n + s.ref[from] : s.ref[from];
+    o.cnt[c] = s.cnt[from];
+  }
+  o.axis = s.axis;
+  o.pad_[0] = o.pad_[1] = o.pad_[2] = 0u;
+  dst[i] = o;
+}
+
 // 64-byte copies of the pair nodes (layout.h: PairNode64).  *bad is set when a box coordinate is not (float -/+ kEPS)
 // exactly or a leaf holds more than 65 534 triangles: the scene then keeps its 128-byte nodes.
 __global__ void __launch_bounds__(256) k_pack_nodes64(const PairNode *__restrict__ src, uint32_t n, PairNode64 *__restrict__ dst,
@@ -696,16 +720,20 @@ cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const
   if constexpr (!COUNT && CAP <= 64) {
     static const int var = env_int("MB200_TRACE_VAR", -1); // -1 = not set: the production instantiation
     if (var == 1) return MB200_SM(kRefillMin, kShadeMin, S, kMinBlocks, kChunk, kVarOctant);
-    if (var == 104) return MB200_SM(kRefillMin, 4, S, kMinBlocks, kChunk, 0);      // shade step at 4 parked lanes
-    if (var == 116) return MB200_SM(kRefillMin, 16, S, kMinBlocks, kChunk, 0);     // ... at 16
-    if (var == 212) return MB200_SM(12, 12, S, kMinBlocks, kChunk, 0);             // refill and shade at 12
+    if (var == 104 && sc.nodes_oct) return MB200_SM(kRefillMin, 4, S, kMinBlocks, kChunk, kVar);      // shade step at 4 parked lanes
+    if (var == 116 && sc.nodes_oct) return MB200_SM(kRefillMin, 16, S, kMinBlocks, kChunk, kVar);     // ... at 16
+    if (var == 212 && sc.nodes_oct) return MB200_SM(12, 12, S, kMinBlocks, kChunk, kVar);             // refill and shade at 12
+    if (var == 0) return MB200_SM(kRefillMin, kShadeMin, S, kMinBlocks, kChunk, 0);   // canonical nodes (round-1 production)
     if (var == 4 && sc.nodes64) return MB200_SM(kRefillMin, kShadeMin, S, kMinBlocks, kChunk, kVarNode64);  // 64-byte pair nodes
     if (var == 2) return MB200_SM(kRefillMin, kShadeMin, 0, kMinBlocks, kChunk, kVarTopSmem);  // top of the tree in shared memory
-    if (var == 300) return MB200_SM(kRefillMin, kShadeMin, 0, kMinBlocks, kChunk, 0);   // control for it: stack in local memory
-    if (var == 308) return MB200_SM(kRefillMin, kShadeMin, 8, kMinBlocks, kChunk, 0);  // 8 stack entries in shared memory
-    if (var == 306) return MB200_SM(kRefillMin, kShadeMin, 6, kMinBlocks, kChunk, 0);  // 6 (more L1)
+    if (var == 1300) return MB200_SM(kRefillMin, kShadeMin, 0, kMinBlocks, kChunk, 0);   // control for it: canonical nodes, stack in local memory
+    if (var == 308 && sc.nodes_oct) return MB200_SM(kRefillMin, kShadeMin, 8, kMinBlocks, kChunk, kVar);  // 8 stack entries in shared memory
+    if (var == 316 && sc.nodes_oct) return MB200_SM(kRefillMin, kShadeMin, 16, kMinBlocks, kChunk, kVar); // 16
+    if (var == 300 && sc.nodes_oct) return MB200_SM(kRefillMin, kShadeMin, 0, kMinBlocks, kChunk, kVar);  // none: stack in local memory
   }
 #endif
+  // scenes without octant copies (MB200_NODE_OCT=0, or not enough memory for them) walk the canonical nodes
+  if (!sc.nodes_oct) return MB200_SM(kRefillMin, kShadeMin, S, kMinBlocks, kChunk, kVar & ~kVarOctNodes);
   return MB200_SM(kRefillMin, kShadeMin, S, kMinBlocks, kChunk, kVar);
 #undef MB200_SM
 }
@@ -1162,6 +1190,13 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
 cudaError_t launch_resolve_ldr(const float *image, const int *count, size_t npix, int mode, unsigned char *out, cudaStream_t s) {
   if (npix == 0) return cudaSuccess;
   k_resolve_ldr<<<flat_grid(npix, 256), 256, 0, s>>>(image, count, npix, mode, out);
+  g_launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_octant_nodes(const PairNode *src, size_t n, PairNode *dst, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  k_octant_nodes<<<(unsigned)((n * 8 + 255) / 256), 256, 0, s>>>(src, (uint32_t)n, dst);
   g_launches++;
   return cudaGetLastError();
 }

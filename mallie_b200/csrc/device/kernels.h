@@ -96,6 +96,8 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
 // Accumulated frame + counts -> 8-bit pixels (mode 0: HDRToLDR RGB8, mode 1: Display BGRA8 with gamma 2.2).
 cudaError_t launch_resolve_ldr(const float *image, const int *count, size_t npix, int mode, unsigned char *out, cudaStream_t s);
 
+// The eight octant copies of the pair nodes (layout.h: nodes_oct); dst holds 8 * n nodes.
+cudaError_t launch_octant_nodes(const PairNode *src, size_t n, PairNode *dst, cudaStream_t s);
 // 64-byte copies of the pair nodes (development variant; *bad != 0 afterwards: not representable, do not use them).
 cudaError_t launch_pack_nodes64(const PairNode *src, size_t n, PairNode64 *dst, int *bad, cudaStream_t s);
 // Traversal copy of the triangle records in a padded layout (layout.h: TriKind kTriF32x64 / kTriF64x96).

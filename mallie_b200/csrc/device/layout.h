@@ -141,6 +141,13 @@ struct SceneView {
   const PairNode *top_nodes;
   uint32_t top_count;
   const PairNode64 *nodes64; // development variant kVarNode64 (null: not available for this scene)
+  // Octant copies of the pair nodes (kVarOctNodes; null: none): copy s (bit a of s = direction component a is negative)
+  // at nodes_oct + s * num_pair_nodes.  In copy s every box is stored as (near x, near y, near z, far x, far y, far z)
+  // for rays of that octant -- what IntersectRayAABB selects with dirSign (bvh_accel.cc:556-561) -- and the children
+  // are ordered (near, far) as Traverse orders them with dirSign[axis] (bvh_accel.cc:818-823), so the inner step
+  // needs no per-axis selects and no axis: the same values reach the same arithmetic.  Branch refs inside a copy are
+  // absolute (s * num_pair_nodes + index), so a ray enters its copy at the root and never leaves it.
+  const PairNode *nodes_oct;
   // verbatim mesh (mesh.h:7-18) for BuildIntersection
   const double *vertices;    // [3*nv]
   const uint32_t *faces;     // [3*nf]

@@ -269,6 +269,26 @@ int scene_finish(mb200_scene *s, std::string *err) {
     }
     v.trav_tris = pad, v.tri_kind = kind;
   }
+  // octant copies of the pair nodes (layout.h: nodes_oct)
+  v.nodes_oct = nullptr;
+  // (production layout; MB200_NODE_OCT=0 keeps the canonical nodes only.  8 x 128 B per branch node: 99 MB for the
+  // 1 M-triangle scene, 1 GB for 10 M triangles; without the memory for it the scene walks the canonical nodes.)
+  const char *no = getenv("MB200_NODE_OCT");
+  if (!(no && atoi(no) == 0) && !v.empty && v.num_pair_nodes > 0 && (size_t)v.num_pair_nodes * 8 < 0xFFFFFFFFull) {
+    void *d8 = nullptr;
+    const size_t bytes = (size_t)v.num_pair_nodes * 8 * sizeof(PairNode);
+    if ((e = cudaMalloc(&d8, bytes)) == cudaSuccess) {
+      s->allocs.push_back(d8);
+      s->device_bytes += bytes;
+      if ((e = launch_octant_nodes(v.nodes, v.num_pair_nodes, (PairNode *)d8, s->stream)) != cudaSuccess) {
+        if (err) *err = std::string("octant node copies: ") + cudaGetErrorString(e);
+        return MB200_ERR_CUDA;
+      }
+      v.nodes_oct = (const PairNode *)d8;
+    } else {
+      cudaGetLastError(); // out of memory: not an error, the canonical nodes do
+    }
+  }
   // 64-byte pair nodes (development builds; layout.h: PairNode64)
   v.nodes64 = nullptr;
   const char *nl = getenv("MB200_NODE_LAYOUT");

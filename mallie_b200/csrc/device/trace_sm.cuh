@@ -108,6 +108,8 @@ struct IOOccluded {
   }
   __device__ __forceinline__ void accept(uint32_t, double, double, double, uint32_t, uint32_t) const {}
   __device__ __forceinline__ void finish(uint32_t i, bool occ) const { occluded[i] = occ ? 1 : 0; }
+  // re-read on the (rare) accepted triangle instead of occupying two registers for the whole walk
+  __device__ __forceinline__ double tmax_of(uint32_t i) const { return __ldg(tmax + i); }
 };
 
 // K1 fused into K2: the camera ray of work item i (one jittered sample of one pixel) is generated in
@@ -184,6 +186,7 @@ struct IOQueueShadow {
       contrib[w.x] = __uint_as_float(w.y);
     }
   }
+  __device__ __forceinline__ double tmax_of(uint32_t i) const { return __ldg(&q[i].tmax); }
 };
 
 // The lane's 32-byte slot in shared memory (fused frames), two 16-byte units in the column layout of the
@@ -289,7 +292,9 @@ template <bool PINHOLE> struct IOFrameFusedT {
 //      stack moves to local memory to make room
 //   4  64-byte pair nodes (layout.h: PairNode64): two 256-bit loads per visit, the exact doubles rebuilt with twelve
 //      conversions and twelve additions
-constexpr int kVarOctant = 1, kVarTopSmem = 2, kVarNode64 = 4;
+//   8  octant copies of the pair nodes (layout.h: nodes_oct): boxes pre-ordered (near, far) per axis and children
+//      pre-ordered (near, far) for the ray's octant, so the step has no sign selects and no axis lookup
+constexpr int kVarOctant = 1, kVarTopSmem = 2, kVarNode64 = 4, kVarOctNodes = 8;
 constexpr uint32_t kTopSlotBytes = 144;
 
 // Stages sc.top_nodes into shared memory at `table` (shared-window address; 16-byte aligned) and waits for it.
@@ -325,8 +330,9 @@ struct NodeWords { // one PairNode as loaded
   uint32_t ref0, ref1, cnt0, cnt1, axis;
 };
 
-// One 128-byte line as four 256-bit loads (LDG.E.256).
-__device__ __forceinline__ NodeWords load_pair_node(const PairNode *n) {
+// One 128-byte line as four 256-bit loads (LDG.E.256).  AXIS = false (octant copies: the children are pre-ordered): the
+// last load is 128 bits wide, which keeps four destination registers free at the step's register peak.
+template <bool AXIS = true> __device__ __forceinline__ NodeWords load_pair_node(const PairNode *n) {
   NodeWords w;
   const char *p = reinterpret_cast<const char *>(n);
   double a0, a1, a2, a3;
@@ -335,10 +341,15 @@ __device__ __forceinline__ NodeWords load_pair_node(const PairNode *n) {
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3) : "l"(p + 32 * k));
     (&w.b[0][0])[4 * k + 0] = a0, (&w.b[0][0])[4 * k + 1] = a1, (&w.b[0][0])[4 * k + 2] = a2, (&w.b[0][0])[4 * k + 3] = a3;
   }
-  uint32_t m0, m1, m2, m3, m4, m5, m6, m7;
-  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3), "=r"(m4), "=r"(m5), "=r"(m6), "=r"(m7)
-               : "l"(p + 96));
+  uint32_t m0, m1, m2, m3, m4 = 0, m5, m6, m7;
+  if (AXIS) {
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3), "=r"(m4), "=r"(m5), "=r"(m6), "=r"(m7)
+                 : "l"(p + 96));
+    (void)m5, (void)m6, (void)m7;
+  } else {
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3) : "l"(p + 96));
+  }
   w.ref0 = m0, w.ref1 = m1, w.cnt0 = m2, w.cnt1 = m3, w.axis = m4;
   return w;
 }
@@ -394,7 +405,7 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
   const unsigned lt_mask = (1u << lane) - 1u;
 
   RayD r;
-  double hit_t = 0.0, tmax_any = 0.0;
+  double hit_t = 0.0;
   uint32_t ref = 0, rc = kIdle, item = 0;
   int sp = 0;
   uint32_t pool_next = 0, pool_end = 0;
@@ -452,6 +463,7 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
                 io.contrib[item & ~kShadowBit] = value;
                 rc = kIdle;
               }
+              if ((VAR & kVarOctNodes) && rc == kBranch) ref += r.sgn * sc.num_pair_nodes; // into the octant's copy
             } else {
               io.contrib[item] = out;
               rc = kIdle;
@@ -483,7 +495,6 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
               if (io.load(item, ox, oy, oz, dx, dy, dz, t0)) {
                 ray_setup(r, ox, oy, oz, dx, dy, dz);
                 hit_t = DBL_MAX; // bvh_accel.cc:774 (any hit included: see the header)
-                if (ANYHIT) tmax_any = t0;
                 sp = 0;
                 if (IO::kTracksCost) born = iter;
                 if (COUNT) nrays++;
@@ -492,6 +503,7 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
                   if constexpr (IO::kFused) rc = kShade; // the plane may still be hit
                   else io.finish(item, false);
                 }
+                if ((VAR & kVarOctNodes) && rc == kBranch) ref += r.sgn * sc.num_pair_nodes; // into the octant's copy // from here on: the first node of the octant's copy
               }
             }
             pool_next += (want < avail) ? want : avail;
@@ -508,10 +520,16 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
       NodeWords nw;
       if ((VAR & kVarTopSmem) && (ref & kTopBit)) nw = load_pair_node_smem(top_table + (ref & ~kTopBit) * kTopSlotBytes);
       else if (VAR & kVarNode64) nw = load_pair_node64(sc.nodes64 + ref);
+      else if (VAR & kVarOctNodes) nw = load_pair_node<false>(sc.nodes_oct + ref); // branch refs of a copy are absolute
       else nw = load_pair_node(sc.nodes + ref);
       double t0, t1;
       bool h0, h1;
       bool done = false;
+      if (VAR & kVarOctNodes) { // the copy is already ordered for this ray's octant
+        done = true;
+        h0 = slab_test_oct<0>(nw.b[0], r, hit_t, t0);
+        h1 = slab_test_oct<0>(nw.b[1], r, hit_t, t1);
+      }
       if (VAR & kVarOctant) {
         int uniform;
         __match_all_sync(__activemask(), r.sgn, &uniform);
@@ -533,7 +551,8 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
       }
       const bool shadow = IO::kFused && (item & kShadowBit);
       if (COUNT) (shadow ? cnt_s.nodes : cnt.nodes) += 2;
-      const bool sgn = ((r.sgn >> nw.axis) & 1u) != 0u; // dirSign[axis]
+      // dirSign[axis]: child 1 is the near one; the octant copies store the near child first
+      const bool sgn = (VAR & kVarOctNodes) ? false : (((r.sgn >> nw.axis) & 1u) != 0u);
       if (h0 && h1) { // near = data[dirSign[axis]] first, far pushed with its tmin (bvh_accel.cc:818-823)
         st.put(sp++, sgn ? t0 : t1, sgn ? nw.ref0 : nw.ref1, sgn ? nw.cnt0 : nw.cnt1);
         if (COUNT) cnt.max_stack = max(cnt.max_stack, (unsigned int)sp + 1u);
@@ -572,9 +591,11 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
           }
         } else {
           io.accept(item, hit_t, u, v, tface, tmat);
-          if (ANYHIT && hit_t < tmax_any) { // occluded: closest-hit Traverse would return t < tmax
-            io.finish(item, true);
-            stop = true;
+          if constexpr (ANYHIT) {
+            if (hit_t < io.tmax_of(item)) { // occluded: closest-hit Traverse would return t < tmax
+              io.finish(item, true);
+              stop = true;
+            }
           }
         }
         if (stop) {
