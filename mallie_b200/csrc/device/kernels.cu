@@ -32,6 +32,7 @@ constexpr int kBlock = 128; // threads per CTA of the traversal kernels
 constexpr int kRefillMin = 8;   // idle lanes that trigger a refill
 constexpr int kShadeMin = 8;    // parked lanes that trigger a shade step (fused frames)
 constexpr int kSmemStack = 12;  // stack entries per thread kept in shared memory (24 KB per CTA)
+constexpr int kSmemStackQuery = 8;  // plain closest-hit / any-hit queries over a caller's ray buffer
 constexpr int kSmemStackFused = 10; // fused frames: two more 16-byte units per thread hold the lane slot
 constexpr int kMinBlocks = 8;   // resident CTAs per SM the register allocation targets (64 registers)
 constexpr unsigned kChunk = 32; // ray indices per atomicAdd
@@ -703,7 +704,9 @@ cudaError_t launch_tr(const SceneView &sc, const IO &io, size_t n, const unsigne
 template <class IO, int TRI, int CAP, bool ANYHIT, bool COUNT>
 cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const unsigned int *n_dev,
                               unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
-  constexpr int S = IO::kFused ? kSmemStackFused : kSmemStack;
+  // frames keep 12 stack entries per thread in shared memory; a lone query launch (no second stream to hide its tail
+  // behind) measured 7 % faster with 8, i.e. with more of the SM's 256 KB left as L1 (profiles/r2_ab7_*.log)
+  constexpr int S = IO::kFused ? kSmemStackFused : (IO::kTracksCost ? kSmemStack : kSmemStackQuery);
 #define MB200_SM(R, H, SS, B, C, V) launch_sm<IO, TRI, CAP, ANYHIT, COUNT, R, H, SS, B, C, V>(sc, io, n, n_dev, work, counters, s)
 #ifdef MB200_DEV_VARIANTS
   if constexpr (!IO::kFused && CAP <= 64 && (TRI == kTriF32 || TRI == kTriF64)) {
@@ -730,6 +733,12 @@ cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const
     if (var == 308 && sc.nodes_oct) return MB200_SM(kRefillMin, kShadeMin, 8, kMinBlocks, kChunk, kVar);  // 8 stack entries in shared memory
     if (var == 316 && sc.nodes_oct) return MB200_SM(kRefillMin, kShadeMin, 16, kMinBlocks, kChunk, kVar); // 16
     if (var == 300 && sc.nodes_oct) return MB200_SM(kRefillMin, kShadeMin, 0, kMinBlocks, kChunk, kVar);  // none: stack in local memory
+    if (var == 409 && sc.nodes_oct) return MB200_SM(kRefillMin, kShadeMin, 12, 9, kChunk, kVar);   // 9 CTAs per SM (56 registers)
+    if (var == 410 && sc.nodes_oct) return MB200_SM(kRefillMin, kShadeMin, 10, 10, kChunk, kVar);  // 10 CTAs per SM (48 registers)
+    if (var == 407 && sc.nodes_oct) return MB200_SM(kRefillMin, kShadeMin, 12, 7, kChunk, kVar);   // 7 CTAs per SM (72 registers)
+    if (var == 406 && sc.nodes_oct) return MB200_SM(kRefillMin, kShadeMin, 12, 6, kChunk, kVar);   // 6 CTAs per SM (80 registers)
+    if (var == 506 && sc.nodes_oct) return MB200_SM(6, kShadeMin, 12, kMinBlocks, kChunk, kVar);   // refill at 6 idle lanes
+    if (var == 512 && sc.nodes_oct) return MB200_SM(12, kShadeMin, 12, kMinBlocks, kChunk, kVar);  // refill at 12
   }
 #endif
   // scenes without octant copies (MB200_NODE_OCT=0, or not enough memory for them) walk the canonical nodes
