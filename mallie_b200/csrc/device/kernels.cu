@@ -19,6 +19,7 @@
 
 #include "shade.cuh"
 #include "trace_sm.cuh"
+#include "trace_ds.cuh"
 #include "trace_tr.cuh"
 #include "traverse.cuh"
 
@@ -121,6 +122,18 @@ __global__ void __launch_bounds__(kBlock, MINB)
   const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_fat + threadIdx.x);
   if (n_dev) n = __ldg(n_dev);
   trace_two_ray_machine<IO, TRI, CAP, ANYHIT, COUNT, REFILL_MIN, HYST, CHUNK>(sc, io, n, work, base, kBlock * 16u, gcounters);
+}
+
+// The dual-slot machine (trace_ds.cuh): one ray per phase per lane; the rays' read-only halves in dynamic shared memory.
+template <class IO, int TRI, int CAP, bool ANYHIT, bool COUNT, bool OCT, int REFILL_MIN, int MINB, unsigned CHUNK>
+__global__ void __launch_bounds__(kBlock, MINB)
+    k_trace_ds(const __grid_constant__ SceneView sc, const __grid_constant__ IO io, unsigned long long n,
+               const unsigned int *__restrict__ n_dev, unsigned long long *__restrict__ work,
+               unsigned long long *__restrict__ gcounters) {
+  extern __shared__ uint4 smem_fat[]; // [2 rays x kFatUnits][kBlock], column layout
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_fat + threadIdx.x);
+  if (n_dev) n = __ldg(n_dev);
+  trace_dual_slot_machine<IO, TRI, CAP, ANYHIT, COUNT, OCT, REFILL_MIN, CHUNK>(sc, io, n, work, base, kBlock * 16u, gcounters);
 }
 
 // ---------------------------------------------------------------------------
@@ -699,6 +712,20 @@ cudaError_t launch_tr(const SceneView &sc, const IO &io, size_t n, const unsigne
   return cudaGetLastError();
 }
 
+template <class IO, int TRI, int CAP, bool ANYHIT, bool COUNT, bool OCT, int REFILL_MIN, int MINB, unsigned CHUNK>
+cudaError_t launch_ds(const SceneView &sc, const IO &io, size_t n, const unsigned int *n_dev, unsigned long long *work,
+                      unsigned long long *counters, cudaStream_t s) {
+  auto k = k_trace_ds<IO, TRI, CAP, ANYHIT, COUNT, OCT, REFILL_MIN, MINB, CHUNK>;
+  const size_t smem = (size_t)2 * kFatUnits * kBlock * sizeof(uint4);
+  static int grids[64]; // per instantiation, per device
+  int grid = 0;
+  const cudaError_t ge = persistent_grid(k, smem, MINB, grids, &grid);
+  if (ge != cudaSuccess) return ge;
+  k<<<grid, kBlock, smem, s>>>(sc, io, (unsigned long long)n, n_dev, work, counters);
+  g_launches++;
+  return cudaGetLastError();
+}
+
 // Picks the kernel instantiation: production parameters, or (development builds, -DMB200_DEV_VARIANTS)
 // the A/B variants selected with MB200_TRACE_VAR.
 template <class IO, int TRI, int CAP, bool ANYHIT, bool COUNT>
@@ -713,6 +740,18 @@ cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const
     // two rays per lane, one body per iteration (trace_tr.cuh): MB200_TRACE_TR = hysteresis of the vote (0, 4, 8) + 1
     static const int tr = env_int("MB200_TRACE_TR", 0);
 #define MB200_TR(R, H, B) launch_tr<IO, TRI, CAP, ANYHIT, COUNT, R, H, B, kChunk>(sc, io, n, n_dev, work, counters, s)
+    // one slot per phase per lane (trace_ds.cuh): MB200_TRACE_DS = CTAs per SM * 100 + refill threshold
+    static const int ds = env_int("MB200_TRACE_DS", 0);
+    if (ds && sc.nodes_oct) {
+#define MB200_DS(R, B) launch_ds<IO, TRI, CAP, ANYHIT, COUNT, true, R, B, kChunk>(sc, io, n, n_dev, work, counters, s)
+      if (ds == 608) return MB200_DS(8, 6);
+      if (ds == 604) return MB200_DS(4, 6);
+      if (ds == 616) return MB200_DS(16, 6);
+      if (ds == 508) return MB200_DS(8, 5);
+      if (ds == 708) return MB200_DS(8, 7);
+      if (ds == 808) return MB200_DS(8, 8);
+#undef MB200_DS
+    }
     if (tr == 1) return MB200_TR(kRefillMin, 0, kMinBlocks);
     if (tr == 5) return MB200_TR(kRefillMin, 4, kMinBlocks);
     if (tr == 9) return MB200_TR(kRefillMin, 8, kMinBlocks);
