@@ -17,7 +17,8 @@ A "step" is one frame.  Camera eye (0,0,3) -> origin, fov 45, light (2,4,3).
           the library's row-placement kernel assemble the frame on every rank (mb200_render_frame_gathered).
 * e2e   : the same frame through the C-ABI call a Mallie host makes with a pinned HOST framebuffer
           (mb200_render_frame at N = 1, mb200_render_frame_gathered at N > 1 with the host buffer on rank 0); the
-          device->host copy of the framebuffer is inside the timed region.
+          device->host copy of the framebuffer is inside the timed region (at N = 1 the library copies the rows of the
+          frame's first batch while the second one is still traced).
 * parity: outside the timed region, at every N: a 64-bit digest of the final frame on every rank, compared with the oracle's
           frame (all 16 passes for 1m; the first pass for 10m, and says so) -- the run FAILS if they differ.
 * roofline : the traversal kernel k_trace_sm (closest-hit launches over camera rays + any-hit launches over shadow rays).
@@ -443,7 +444,7 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = rays_frame * args.steps / float(e2e_t[0]) / 1e6
-    d2h = H * W * 3 * 4 + H * W * 4
+    d2h = H * W * 3 * 4          # the float frame; count of a fresh whole frame is the constant SPP, written by the host
     h2d = C.sizeof(M.capi.RenderParams)
     host_fnv = frame_hash(h_img.numpy()) if rank == 0 else None
 

@@ -646,22 +646,43 @@ static int render_common(mb200_scene *s, const mb200_render_params *p, int num_p
     }
   }
   if (stats) CU(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), s->stream));
+  // A host framebuffer is copied back in row chunks: the frame is cut into batches by rows, so the first rows are final
+  // while the later ones are still traced, and their device -> host copy runs on the pipe's copy stream meanwhile.
+  mb200::FrameChunks chunks;
+  const bool to_host = img_kind != kDevice || cnt_kind != kDevice;
   CU(mb200::launch_frame(s->view, s->stack_cap, *p, num_passes, mode, d_img, d_cnt, s->frame_scratch,
-                         stats ? s->d_counters : nullptr, s->stream, &s->timer, &s->pipe));
-  if (img_kind != kDevice)
-    CU(cudaMemcpyAsync(img_kind == kPinned ? (void *)image : s->out0.pinned, d_img, img_bytes, cudaMemcpyDeviceToHost,
-                       s->stream));
+                         stats ? s->d_counters : nullptr, s->stream, &s->timer, &s->pipe, to_host ? &chunks : nullptr));
   // A fresh frame that covers the buffer has count == num_passes everywhere (every step-th pixel aside): the host
   // writes it itself while the GPU renders instead of waiting for 4 more bytes per pixel over PCIe.
   const bool count_is_constant = mode == 2 && covers_all && p->pixel_step <= 1 && cnt_kind != kDevice;
-  if (cnt_kind != kDevice && !count_is_constant)
-    CU(cudaMemcpyAsync(cnt_kind == kPinned ? (void *)count : s->out1.pinned, d_cnt, cnt_bytes, cudaMemcpyDeviceToHost,
-                       s->stream));
+  const bool copy_img = img_kind != kDevice, copy_cnt = cnt_kind != kDevice && !count_is_constant;
+  void *img_dst = img_kind == kPinned ? (void *)image : s->out0.pinned;
+  void *cnt_dst = cnt_kind == kPinned ? (void *)count : s->out1.pinned;
+  bool chunked = false;
+  if (to_host && chunks.n > 0 && s->pipe.copy) {
+    chunked = true;
+    const size_t W = (size_t)p->width;
+    for (int c = 0; c < chunks.n; c++) {
+      const size_t r0 = (size_t)chunks.row0[c], nr = (size_t)(chunks.row1[c] - chunks.row0[c]);
+      CU(cudaStreamWaitEvent(s->pipe.copy, chunks.done_a[c], 0));
+      if (chunks.done_b[c]) CU(cudaStreamWaitEvent(s->pipe.copy, chunks.done_b[c], 0));
+      if (copy_img)
+        CU(cudaMemcpyAsync((char *)img_dst + r0 * W * 3 * sizeof(float), (const char *)d_img + r0 * W * 3 * sizeof(float),
+                           nr * W * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->pipe.copy));
+      if (copy_cnt)
+        CU(cudaMemcpyAsync((char *)cnt_dst + r0 * W * sizeof(int), (const char *)d_cnt + r0 * W * sizeof(int),
+                           nr * W * sizeof(int), cudaMemcpyDeviceToHost, s->pipe.copy));
+    }
+  } else {
+    if (copy_img) CU(cudaMemcpyAsync(img_dst, d_img, img_bytes, cudaMemcpyDeviceToHost, s->stream));
+    if (copy_cnt) CU(cudaMemcpyAsync(cnt_dst, d_cnt, cnt_bytes, cudaMemcpyDeviceToHost, s->stream));
+  }
   if (count_is_constant) std::fill_n(count, npix, num_passes);
   unsigned long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (stats || img_kind != kDevice || cnt_kind != kDevice) {
+  if (stats || to_host) {
     if (stats) CU(cudaMemcpyAsync(c, s->d_counters, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
+    if (chunked) CU(cudaStreamSynchronize(s->pipe.copy));
   }
   if (img_kind == kPageable) memcpy(image, s->out0.pinned, img_bytes);
   if (cnt_kind == kPageable && !count_is_constant) memcpy(count, s->out1.pinned, cnt_bytes);

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "shade.cuh"
 #include "trace_sm.cuh"
@@ -464,12 +465,13 @@ __global__ void __launch_bounds__(256) k_resolve_ldr(const float *__restrict__ i
   }
 }
 
-// order = stable partition of 0 .. tiles-1: the tiles flagged in `hot` first, then the others; clears `hot`.
-// One CTA of 1024 threads (a 1080p frame has 64 800 tiles: 64 rounds).
-__global__ void __launch_bounds__(1024) k_build_order(unsigned char *__restrict__ hot, uint32_t tiles,
+// order[tile0 .. tile0 + tiles) = stable partition of the tiles tile0 .. tile0 + tiles - 1: those flagged in `hot` first,
+// then the others; clears their flags.  One CTA of 1024 threads per range (a 1080p frame has 64 800 tiles: 64 rounds).
+__global__ void __launch_bounds__(1024) k_build_order(unsigned char *__restrict__ hot, uint32_t tile0, uint32_t tiles,
                                                       uint32_t *__restrict__ order) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t base_hot, base_cold;
+  hot += tile0, order += tile0;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   // pass 1: how many hot tiles
   uint32_t mine = 0;
@@ -500,7 +502,7 @@ __global__ void __launch_bounds__(1024) k_build_order(unsigned char *__restrict_
     }
     const uint32_t hot_rank = warp_off + before;   // hot tiles of this round before me
     const uint32_t cold_rank = tid - hot_rank;     // cold tiles of this round before me
-    if (in) order[h ? base_hot + hot_rank : base_cold + cold_rank] = i;
+    if (in) order[h ? base_hot + hot_rank : base_cold + cold_rank] = tile0 + i;
     if (in) hot[i] = 0;
     __syncthreads();
     if (tid == 0) {
@@ -512,7 +514,6 @@ __global__ void __launch_bounds__(1024) k_build_order(unsigned char *__restrict_
   }
 }
 
-// stats of a batch -> the caller's accumulated stats (shadow rays traced = fill of the shadow queue)
 // tcount: the traversal launches' counters, camera [0..3] and shadow [4..7] (nodes, tris, rays, max stack)
 __global__ void k_add_stats(const unsigned long long *__restrict__ batch, const unsigned int *__restrict__ shadow_count,
                             const unsigned long long *__restrict__ tcount, unsigned long long *__restrict__ total) {
@@ -912,10 +913,13 @@ cudaError_t FramePipe::init() {
   if (aux) return cudaSuccess;
   cudaError_t e = cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking);
   if (e != cudaSuccess) return e;
+  if ((e = cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking)) != cudaSuccess) return e;
   for (cudaEvent_t *ev : {&fork, &join, &resolved[0], &resolved[1]}) {
     e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     if (e != cudaSuccess) return e;
   }
+  for (cudaEvent_t &ev : chunk_ev)
+    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -936,6 +940,12 @@ cudaError_t FramePipe::reserve_tiles(size_t tiles, cudaStream_t s) {
 void FramePipe::release() {
   for (cudaEvent_t ev : {fork, join, resolved[0], resolved[1]})
     if (ev) cudaEventDestroy(ev);
+  for (cudaEvent_t &ev : chunk_ev) {
+    if (ev) cudaEventDestroy(ev);
+    ev = nullptr;
+  }
+  if (copy) cudaStreamDestroy(copy);
+  copy = nullptr;
   if (aux) cudaStreamDestroy(aux);
   if (hot) cudaFree(hot);
   if (order) cudaFree(order);
@@ -1058,7 +1068,8 @@ static size_t batch_item_budget() {
 
 cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_params &p, int num_passes, int mode,
                          float *image, int *count, FrameScratch &scratch, unsigned long long *stats, cudaStream_t s,
-                         KernelTimer *timer, FramePipe *pipe) {
+                         KernelTimer *timer, FramePipe *pipe, FrameChunks *chunks) {
+  if (chunks) chunks->n = 0;
   const FrameMap m0 = make_frame_map(p, p.pass, 1);
   const size_t tiles = frame_map_tiles(m0);
   if (tiles == 0 || num_passes < 1) return cudaSuccess;
@@ -1074,15 +1085,47 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
   const size_t item_limit = fused ? 0x7FFFFFE0ull : 0xFFFFFFE0ull; // fused: bit 31 of the item marks the shadow ray
   if (tiles * 32 > item_limit) return cudaErrorInvalidValue;
 
-  size_t per_batch = batch_item_budget() / (tiles * 32);
-  if (per_batch < 1) per_batch = 1;
-  if (per_batch > (size_t)num_passes) per_batch = (size_t)num_passes;
-  while (per_batch > 1 && tiles * 32 * per_batch > item_limit) per_batch--;
-  // Two streams need at least two batches to overlap one batch's drain with the other's kernels.
+  // ---- batches.  By tile rows when all passes of one tile row fit a batch (then a batch's pixels are final when it is
+  // resolved and the caller can start copying them: `chunks`); by passes over the whole tile set otherwise.  Two streams
+  // need at least two batches to overlap one batch's drain with the other's kernels.
   static const bool pipeline_off = env_int("MB200_FRAME_PIPELINE", 1) == 0;
-  const bool piped = pipe && !pipeline_off && num_passes >= 2;
-  if (piped && per_batch > (size_t)(num_passes + 1) / 2) per_batch = (size_t)(num_passes + 1) / 2;
-  const size_t max_items = tiles * 32 * per_batch;
+  static const bool rows_off = env_int("MB200_FRAME_ROWSPLIT", 1) == 0;
+  // (a single pass is cut in two only when it is big enough for the second launch to pay: 2^20 samples)
+  const bool piped = pipe && !pipeline_off && (num_passes >= 2 || tiles * 32 >= ((size_t)1 << 20));
+  const size_t tiles_x = (size_t)m0.tiles_x, tiles_y = tiles / tiles_x;
+  const size_t row_items = tiles_x * 32 * (size_t)num_passes; // one tile row, all passes
+  const size_t budget = batch_item_budget() < item_limit ? batch_item_budget() : item_limit;
+  const bool by_rows = !rows_off && row_items <= budget && tiles_y >= 2 && piped;
+  struct Batch {
+    uint32_t tile0, ntiles;
+    int pass0, npasses;
+  };
+  std::vector<Batch> batches;
+  size_t max_items = 0;
+  int rows_per_batch = 0;
+  if (by_rows) {
+    size_t rows_max = budget / row_items; // tile rows per batch
+    size_t nb = (tiles_y + rows_max - 1) / rows_max;
+    const size_t want = (chunks && chunks->want > 2) ? (size_t)chunks->want : 2;
+    if (nb < want) nb = want < tiles_y ? want : tiles_y;
+    rows_per_batch = (int)((tiles_y + nb - 1) / nb);
+    for (size_t r = 0; r < tiles_y; r += (size_t)rows_per_batch) {
+      const size_t rows = (r + rows_per_batch <= tiles_y) ? (size_t)rows_per_batch : tiles_y - r;
+      batches.push_back({(uint32_t)(r * tiles_x), (uint32_t)(rows * tiles_x), 0, num_passes});
+      if (rows * row_items > max_items) max_items = rows * row_items;
+    }
+  } else {
+    size_t per_batch = budget / (tiles * 32);
+    if (per_batch < 1) per_batch = 1;
+    if (per_batch > (size_t)num_passes) per_batch = (size_t)num_passes;
+    if (piped && num_passes >= 2 && per_batch > (size_t)(num_passes + 1) / 2) per_batch = (size_t)(num_passes + 1) / 2;
+    for (int done = 0; done < num_passes; done += (int)per_batch) {
+      const int nb = (int)((size_t)(num_passes - done) < per_batch ? (size_t)(num_passes - done) : per_batch);
+      batches.push_back({0u, (uint32_t)tiles, done, nb});
+    }
+    max_items = tiles * 32 * per_batch;
+  }
+  const bool two_streams = piped && batches.size() >= 2;
 
   // scratch carve-up (one slot per stream)
   const size_t n_traces = path ? (size_t)p.max_path_length : 2;
@@ -1093,24 +1136,33 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
   const size_t state_bytes = path ? align_up(max_items * sizeof(PathState), 256) : 0;
   const size_t slot_bytes = ctl_bytes + hits_bytes + contrib_bytes + queue_bytes * (path ? 2 : 1) + state_bytes;
   cudaError_t e = cudaSuccess;
-  if (piped) {
+  if (two_streams || (pipe && chunks)) {
     if ((e = pipe->init()) != cudaSuccess) return e;
     // the previous frame may still be running on aux when the block has to grow
     if (scratch.bytes < slot_bytes * 2 && (e = cudaStreamSynchronize(pipe->aux)) != cudaSuccess) return e;
   }
-  if ((e = frame_scratch_reserve(scratch, slot_bytes * (piped ? 2 : 1), s)) != cudaSuccess) return e;
-  // longest-rays-first schedule from the previous frame's flags (same tile layout only)
+  if ((e = frame_scratch_reserve(scratch, slot_bytes * (two_streams ? 2 : 1), s)) != cudaSuccess) return e;
+  // longest-rays-first schedule from the previous frame's flags (same tile layout and batch cut only); the order is a
+  // permutation inside every batch's tile range
   const uint32_t *order = nullptr;
   unsigned char *hot = nullptr;
   static const bool lpt_off = env_int("MB200_FRAME_LPT", 1) == 0;
   if (pipe && !lpt_off && tiles >= 1024) {
-    const long long layout[12] = {p.width, p.height, p.x0, p.y0, p.x1, p.y1, p.band_rows, p.band_count,
-                                  p.band_index, p.band_compact, p.pixel_step, (long long)tiles};
+    const long long layout[12] = {p.width, p.height, p.x0, p.y0, p.x1, p.y1, p.band_rows * 1000003LL + p.band_count,
+                                  p.band_index, p.band_compact, p.pixel_step, (long long)tiles,
+                                  by_rows ? rows_per_batch : 0};
     if ((e = pipe->reserve_tiles(tiles, s)) != cudaSuccess) return e;
     const bool same = pipe->have_hot && memcmp(layout, pipe->layout, sizeof(layout)) == 0;
     if (same) {
-      k_build_order<<<1, 1024, 0, s>>>(pipe->hot, (uint32_t)tiles, pipe->order);
-      g_launches++;
+      if (by_rows) {
+        for (const Batch &b : batches) {
+          k_build_order<<<1, 1024, 0, s>>>(pipe->hot, b.tile0, b.ntiles, pipe->order);
+          g_launches++;
+        }
+      } else {
+        k_build_order<<<1, 1024, 0, s>>>(pipe->hot, 0u, (uint32_t)tiles, pipe->order);
+        g_launches++;
+      }
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
       order = pipe->order;
     } else {
@@ -1120,16 +1172,22 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
     hot = pipe->hot;
     pipe->have_hot = true;
   }
-  if (piped) { // aux starts after whatever the caller queued on s (uploads, the previous frame)
+  if (two_streams) { // aux starts after whatever the caller queued on s (uploads, the previous frame)
     if ((e = cudaEventRecord(pipe->fork, s)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(pipe->aux, pipe->fork, 0)) != cudaSuccess) return e;
   }
 
-  int done = 0, batch = 0;
+  // which batches end a chunk the caller is told about (row cut, compact or unbanded buffers only)
+  const bool report = chunks && by_rows && pipe && (p.band_rows == 0 || p.band_compact);
+  const size_t nbatch = batches.size();
+  const size_t nchunks = report ? (nbatch < (size_t)kMaxFrameChunks ? nbatch : (size_t)kMaxFrameChunks) : 0;
+  const size_t per_chunk = nchunks ? (nbatch + nchunks - 1) / nchunks : 0;
+  const int step = m0.step;
+
   bool aux_used = false;
-  while (done < num_passes) {
-    const int nb = (int)((size_t)(num_passes - done) < per_batch ? (size_t)(num_passes - done) : per_batch);
-    const int slot = piped ? (batch & 1) : 0;
+  for (size_t bi = 0; bi < nbatch; bi++) {
+    const Batch &B = batches[bi];
+    const int slot = two_streams ? (int)(bi & 1) : 0;
     const cudaStream_t st = slot ? pipe->aux : s;
     aux_used |= slot != 0;
     char *base = reinterpret_cast<char *>(scratch.base) + (size_t)slot * slot_bytes;
@@ -1143,13 +1201,13 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
     queue[1] = path ? reinterpret_cast<QRay *>(reinterpret_cast<char *>(queue[0]) + queue_bytes) : queue[0];
     PathState *states = path ? reinterpret_cast<PathState *>(reinterpret_cast<char *>(queue[0]) + 2 * queue_bytes) : nullptr;
 
-    FrameMap m = make_frame_map(p, p.pass + (uint32_t)done, (uint32_t)nb);
-    m.order = order, m.hot = hot;
+    FrameMap m = make_frame_map(p, p.pass + (uint32_t)B.pass0, (uint32_t)B.npasses);
+    m.order = order, m.hot = hot, m.tile0 = B.tile0;
     {
       static const int hs = env_int("MB200_HOT_STEPS", (int)kHotSteps);
       m.hot_steps = (uint32_t)hs;
     }
-    const uint32_t items = (uint32_t)(tiles * 32 * (size_t)nb);
+    const uint32_t items = (uint32_t)((size_t)B.ntiles * 32 * (size_t)B.npasses);
     if ((e = cudaMemsetAsync(base, 0, ctl_bytes, st)) != cudaSuccess) return e;
 
     if (fused) {
@@ -1209,26 +1267,48 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
       }
     }
 
-    // the image is accumulated in pass order (float += float): batch k resolves after batch k - 1
-    if (piped && batch > 0 && (e = cudaStreamWaitEvent(st, pipe->resolved[(batch - 1) & 1], 0)) != cudaSuccess) return e;
+    // pass cut: the image is accumulated in pass order (float += float), batch k resolves after batch k - 1.
+    // row cut: every batch holds all passes of its own pixels, nothing to order.
     int bmode = mode;
-    if (mode == 2 && done > 0) bmode = 1;
+    if (!by_rows) {
+      if (two_streams && bi > 0 && (e = cudaStreamWaitEvent(st, pipe->resolved[(bi - 1) & 1], 0)) != cudaSuccess) return e;
+      if (mode == 2 && B.pass0 > 0) bmode = 1;
+    }
     {
       TimedScope ts(timer, kKResolve, st);
-      k_resolve<<<(unsigned)((tiles * 32 + 255) / 256), 256, 0, st>>>(m, (uint32_t)tiles, bmode, contrib, image, count);
+      k_resolve<<<(unsigned)(((size_t)B.ntiles * 32 + 255) / 256), 256, 0, st>>>(m, B.ntiles, bmode, contrib, image, count);
     }
     g_launches++;
-    if (piped && (e = cudaEventRecord(pipe->resolved[batch & 1], st)) != cudaSuccess) return e;
+    if (!by_rows && two_streams && (e = cudaEventRecord(pipe->resolved[bi & 1], st)) != cudaSuccess) return e;
+    if (nchunks) { // the last batch of a chunk on each stream carries one of the chunk's two events
+      const size_t c = bi / per_chunk, last = ((c + 1) * per_chunk < nbatch ? (c + 1) * per_chunk : nbatch) - 1;
+      if (bi == last || (bi + 1 == last && two_streams)) {
+        cudaEvent_t ev = pipe->chunk_ev[2 * c + (bi == last ? 0 : 1)];
+        if ((e = cudaEventRecord(ev, st)) != cudaSuccess) return e;
+        if (bi == last) {
+          const size_t first = c * per_chunk;
+          const int r0 = (int)(batches[first].tile0 / tiles_x) * 4 * step;
+          int r1 = (int)((B.tile0 + B.ntiles) / tiles_x) * 4 * step;
+          const int rows_buf = (p.band_rows > 0) ? m0.rows_local : (p.y1 - p.y0);
+          if (r1 > rows_buf) r1 = rows_buf;
+          const int off = (p.band_rows > 0) ? 0 : p.y0; // unbanded buffers are indexed by image row
+          chunks->row0[c] = off + r0, chunks->row1[c] = off + r1;
+          chunks->done_a[c] = ev;
+          if (!(two_streams && last > first)) chunks->done_b[c] = nullptr;
+          chunks->n = (int)c + 1;
+        } else {
+          chunks->done_b[c] = ev;
+        }
+      }
+    }
     if (stats) {
       if (fused) k_add_stats_fused<<<1, 32, 0, st>>>(tcount, stats);
       else k_add_stats<<<1, 32, 0, st>>>(bstats, shadow ? qcount : nullptr, tcount, stats);
       g_launches++;
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    done += nb;
-    batch++;
   }
-  if (piped && aux_used) { // everything the frame queued on aux is ordered before what follows on s
+  if (two_streams && aux_used) { // everything the frame queued on aux is ordered before what follows on s
     if ((e = cudaEventRecord(pipe->join, pipe->aux)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(s, pipe->join, 0)) != cudaSuccess) return e;
   }

@@ -42,9 +42,25 @@ struct KernelTimer {
 // that held a ray of more than kHotSteps steps (`hot`); the next frame over the same tile layout hands those
 // tiles out first (`order`, a stable partition of the tile indices built by k_build_order), so its long rays
 // start while the GPU is full.  Pure scheduling: which warp traces a ray never changes a result.
+// When do which rows of a frame become final?  launch_frame cuts a frame into batches by tile rows (every batch holds all
+// passes of its rows), so a caller that copies the frame somewhere -- to the host, to the other ranks -- can start with the
+// first rows while the later ones are still traced.  Rows are those of the caller's buffer (local rows of a compact band
+// buffer, image rows otherwise).  A chunk is final once BOTH of its events have completed (the frame's batches alternate
+// between two streams; the second event is null when one stream carried the whole chunk).  n == 0: the frame was not
+// cut by rows (passes did not fit a batch, or non-compact bands): everything is final when the stream is.
+constexpr int kMaxFrameChunks = 8;
+struct FrameChunks {
+  int want = 2;  // in: chunks the caller would like (>= 1)
+  int n = 0;     // out
+  int row0[kMaxFrameChunks], row1[kMaxFrameChunks];
+  cudaEvent_t done_a[kMaxFrameChunks], done_b[kMaxFrameChunks]; // owned by the FramePipe
+};
+
 struct FramePipe {
   cudaStream_t aux = nullptr;
+  cudaStream_t copy = nullptr; // device -> host / collective work that overlaps the frame's later batches
   cudaEvent_t fork = nullptr, join = nullptr, resolved[2] = {nullptr, nullptr};
+  cudaEvent_t chunk_ev[2 * kMaxFrameChunks] = {nullptr};
   unsigned char *hot = nullptr; // [tiles_cap]
   uint32_t *order = nullptr;    // [tiles_cap]
   size_t tiles_cap = 0;
@@ -91,7 +107,7 @@ void frame_scratch_release(FrameScratch &fs);
 // frames) camera nodes, camera triangles, shadow nodes, shadow triangles tested (accumulated).
 cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_params &p, int num_passes, int mode,
                          float *image, int *count, FrameScratch &scratch, unsigned long long *stats, cudaStream_t s,
-                         KernelTimer *timer = nullptr, FramePipe *pipe = nullptr);
+                         KernelTimer *timer = nullptr, FramePipe *pipe = nullptr, FrameChunks *chunks = nullptr);
 
 // Accumulated frame + counts -> 8-bit pixels (mode 0: HDRToLDR RGB8, mode 1: Display BGRA8 with gamma 2.2).
 cudaError_t launch_resolve_ldr(const float *image, const int *count, size_t npix, int mode, unsigned char *out, cudaStream_t s);

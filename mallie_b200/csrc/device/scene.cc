@@ -475,6 +475,7 @@ void scene_destroy(mb200_scene *s) {
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->pipe.aux) cudaStreamSynchronize(s->pipe.aux);
+  if (s->pipe.copy) cudaStreamSynchronize(s->pipe.copy);
   for (void *p : s->allocs) cudaFree(p);
   mb200_scene::Staging *sts[4] = {&s->in0, &s->in1, &s->out0, &s->out1};
   for (auto *st : sts) {

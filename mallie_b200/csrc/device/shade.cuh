@@ -235,6 +235,9 @@ struct FrameMap {
   const uint32_t *order;
   unsigned char *hot;
   uint32_t hot_steps;
+  // First tile of the batch: a frame is cut into batches by tile rows (each batch holds ALL passes of its rows, so its
+  // pixels are final when it is resolved), or -- when one tile row times the passes would not fit a batch -- by passes.
+  uint32_t tile0;
 };
 
 constexpr uint32_t kHotSteps = 160; // mean ray ~35 steps, p99 ~130, silhouette rays up to ~430 (1 M-triangle sphere)
@@ -268,6 +271,7 @@ __host__ inline FrameMap make_frame_map(const mb200_render_params &p, uint32_t p
   m.passes = passes, m.pass0 = pass0;
   m.magic_passes = div_magic(passes), m.magic_tiles_x = div_magic((uint32_t)m.tiles_x);
   m.order = nullptr, m.hot = nullptr, m.hot_steps = kHotSteps;
+  m.tile0 = 0u;
   return m;
 }
 
@@ -280,7 +284,7 @@ __device__ __forceinline__ bool item_pixel(const FrameMap &m, uint32_t item, int
   const uint32_t lane = item & 31u, g = item >> 5;
   const uint32_t slot = m.magic_passes ? (uint32_t)__umul64hi((unsigned long long)g, m.magic_passes) : g;
   pass = m.pass0 + (g - slot * m.passes);
-  const uint32_t tile = m.order ? __ldg(m.order + slot) : slot;
+  const uint32_t tile = m.order ? __ldg(m.order + m.tile0 + slot) : m.tile0 + slot;
   const uint32_t tyu = m.magic_tiles_x ? (uint32_t)__umul64hi((unsigned long long)tile, m.magic_tiles_x) : tile;
   const int ty = (int)tyu, tx = (int)(tile - tyu * (uint32_t)m.tiles_x);
   x = m.x0 + (tx * 8 + (int)(lane & 7u)) * m.step;
@@ -295,7 +299,7 @@ __device__ __forceinline__ void mark_hot_tile(const FrameMap &m, uint32_t item) 
   if (!m.hot) return;
   const uint32_t g = item >> 5;
   const uint32_t slot = m.magic_passes ? (uint32_t)__umul64hi((unsigned long long)g, m.magic_passes) : g;
-  m.hot[m.order ? __ldg(m.order + slot) : slot] = 1;
+  m.hot[m.order ? __ldg(m.order + m.tile0 + slot) : m.tile0 + slot] = 1;
 }
 
 // where a pixel of this call lives in the caller's image / count buffers
