@@ -467,10 +467,14 @@ __global__ void __launch_bounds__(256) k_resolve_ldr(const float *__restrict__ i
 
 // order[tile0 .. tile0 + tiles) = stable partition of the tiles tile0 .. tile0 + tiles - 1: those flagged in `hot` first,
 // then the others; clears their flags.  One CTA of 1024 threads per range (a 1080p frame has 64 800 tiles: 64 rounds).
-__global__ void __launch_bounds__(1024) k_build_order(unsigned char *__restrict__ hot, uint32_t tile0, uint32_t tiles,
+struct OrderRanges { // one CTA per batch of the frame
+  uint32_t tile0[64], tiles[64];
+};
+__global__ void __launch_bounds__(1024) k_build_order(unsigned char *__restrict__ hot, const __grid_constant__ OrderRanges rg,
                                                       uint32_t *__restrict__ order) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t base_hot, base_cold;
+  const uint32_t tile0 = rg.tile0[blockIdx.x], tiles = rg.tiles[blockIdx.x];
   hot += tile0, order += tile0;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   // pass 1: how many hot tiles
@@ -1154,13 +1158,15 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
     if ((e = pipe->reserve_tiles(tiles, s)) != cudaSuccess) return e;
     const bool same = pipe->have_hot && memcmp(layout, pipe->layout, sizeof(layout)) == 0;
     if (same) {
-      if (by_rows) {
-        for (const Batch &b : batches) {
-          k_build_order<<<1, 1024, 0, s>>>(pipe->hot, b.tile0, b.ntiles, pipe->order);
-          g_launches++;
-        }
-      } else {
-        k_build_order<<<1, 1024, 0, s>>>(pipe->hot, 0u, (uint32_t)tiles, pipe->order);
+      // one launch, one CTA per tile range (the batches of a row cut; the whole tile set otherwise)
+      for (size_t b0 = 0; b0 < (by_rows ? batches.size() : 1); b0 += 64) {
+        OrderRanges rg;
+        unsigned nr = 0;
+        if (by_rows)
+          for (size_t b = b0; b < batches.size() && nr < 64; b++, nr++) rg.tile0[nr] = batches[b].tile0, rg.tiles[nr] = batches[b].ntiles;
+        else
+          rg.tile0[0] = 0u, rg.tiles[0] = (uint32_t)tiles, nr = 1;
+        k_build_order<<<nr, 1024, 0, s>>>(pipe->hot, rg, pipe->order);
         g_launches++;
       }
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
