@@ -191,6 +191,29 @@ __device__ __forceinline__ uint32_t queue_slot(unsigned int *qcount, bool want) 
   return base + (unsigned)__popc(m & ((1u << lane_id()) - 1u));
 }
 
+// The same for a whole CTA (every thread must call it), with the CTA's rays grouped by the octant of their
+// direction: slots [base + first[oct] ...) in arrival order.  A warp of the next traversal launch then pulls rays
+// that walk the same octant copy of the pair nodes, at no extra pass over the queue.
+__device__ __forceinline__ uint32_t queue_slot_by_octant(unsigned int *qcount, bool want, double dx, double dy, double dz) {
+  __shared__ unsigned int s_cnt[8], s_first[8];
+  if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0u;
+  __syncthreads();
+  const uint32_t oct = (dx < 0.0 ? 1u : 0u) | (dy < 0.0 ? 2u : 0u) | (dz < 0.0 ? 4u : 0u);
+  unsigned int rank = 0;
+  if (want) rank = atomicAdd(&s_cnt[oct], 1u);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int first[8], total = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) first[k] = total, total += s_cnt[k];
+    const unsigned int base = total ? atomicAdd(qcount, total) : 0u;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s_first[k] = base + first[k];
+  }
+  __syncthreads();
+  return s_first[oct] + rank;
+}
+
 __device__ __forceinline__ void store_qray(QRay *dst, double ox, double oy, double oz, double dx, double dy, double dz,
                                            double tmax, uint32_t item, float value) {
   double2 *o = reinterpret_cast<double2 *>(dst);
@@ -257,7 +280,7 @@ __global__ void __launch_bounds__(256)
     k_shade_primary(const __grid_constant__ SceneView sc, const __grid_constant__ mb200_render_params p,
                     const __grid_constant__ FrameMap m, uint32_t items, const mb200_hit *__restrict__ hits,
                     float *__restrict__ contrib, QRay *__restrict__ queue, unsigned int *__restrict__ qcount,
-                    PathState *__restrict__ states, unsigned long long *__restrict__ stats) {
+                    PathState *__restrict__ states, unsigned long long *__restrict__ stats, int group) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; // grid covers whole warps of items
   int x = 0, y = 0, rl = 0;
   uint32_t pass = 0;
@@ -313,7 +336,7 @@ __global__ void __launch_bounds__(256)
     }
     // a camera ray that escapes contributes nothing (pathLength < kMinPathLength, render.cc:409-412)
   }
-  const uint32_t slot = queue_slot(qcount, push);
+  const uint32_t slot = group ? queue_slot_by_octant(qcount, push, qdx, qdy, qdz) : queue_slot(qcount, push);
   if (push) store_qray(queue + slot, qox, qoy, qoz, qdx, qdy, qdz, qtmax, i, value);
   if (i < items) contrib[i] = out;
   warp_add_stats(stats, valid ? 1u : 0u, zombies);
@@ -325,13 +348,13 @@ __global__ void __launch_bounds__(256)
                    unsigned int len, const QRay *__restrict__ qin, const unsigned int *__restrict__ qin_count,
                    const mb200_hit *__restrict__ hits, QRay *__restrict__ qout, unsigned int *__restrict__ qout_count,
                    PathState *__restrict__ states, float *__restrict__ contrib,
-                   unsigned long long *__restrict__ stats) {
+                   unsigned long long *__restrict__ stats, int group) {
   const unsigned int n = __ldg(qin_count);
   const unsigned int max_len = (unsigned int)p.max_path_length;
   unsigned int zombies = 0, traced = 0;
   const unsigned int stride = gridDim.x * blockDim.x;
-  for (unsigned int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += stride) {
-    const unsigned int j = base + lane_id();
+  for (unsigned int base = blockIdx.x * blockDim.x; base < n; base += stride) { // uniform per CTA
+    const unsigned int j = base + threadIdx.x;
     bool push = false;
     double qox = 0, qoy = 0, qoz = 0, qdx = 0, qdy = 0, qdz = 0;
     uint32_t item = 0;
@@ -376,7 +399,7 @@ __global__ void __launch_bounds__(256)
         push = true;
       }
     }
-    const uint32_t slot = queue_slot(qout_count, push);
+    const uint32_t slot = group ? queue_slot_by_octant(qout_count, push, qdx, qdy, qdz) : queue_slot(qout_count, push);
     if (push) store_qray(qout + slot, qox, qoy, qoz, qdx, qdy, qdz, DBL_MAX, item, 0.f);
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -386,6 +409,93 @@ __global__ void __launch_bounds__(256)
   if (lane_id() == 0) {
     if (traced) atomicAdd(&stats[1], (unsigned long long)traced);
     if (zombies) atomicAdd(&stats[3], (unsigned long long)zombies);
+  }
+}
+
+// ---- bounce-queue re-ordering (SURVEY 7.2 "Divergence"; the reference's bounce loop is render.cc:401-450) --------------
+// Continuation rays leave k_shade_* in sample order: neighbouring slots hold rays with unrelated directions.  A single
+// counting-sort pass regroups the queue by  key = octant of the direction (3 bits: the octant copy of the pair nodes the
+// ray will walk, layout.h) << 12 | Morton code of the origin's cell in a 16^3 grid over the scene box,  so that the 32
+// rays a warp pulls share their node copy and start next to each other.  The sample a ray belongs to travels inside
+// the QRay, so nothing downstream depends on the slot a ray sits in; the order inside a bucket is whatever the atomics
+// give and is not observable (a ray's result does not depend on its neighbours).
+constexpr uint32_t kSortBuckets = 8u << 12;
+struct SortGrid {
+  double lo[3], scale[3]; // cell = (o - lo) * scale, clamped to 0..15
+};
+
+__device__ __forceinline__ uint32_t spread4(uint32_t v) { // abcd -> a00b00c00d
+  return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6);
+}
+
+__device__ __forceinline__ uint32_t sort_key(const SortGrid &g, const QRay *q) {
+  const double2 *p = reinterpret_cast<const double2 *>(q);
+  const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+  const double o[3] = {a.x, a.y, b.x};
+  uint32_t cell[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double f = (o[k] - g.lo[k]) * g.scale[k];
+    cell[k] = f >= 15.0 ? 15u : (f > 0.0 ? (uint32_t)f : 0u); // NaN -> 0
+  }
+  const uint32_t oct = (b.y < 0.0 ? 1u : 0u) | (c.x < 0.0 ? 2u : 0u) | (c.y < 0.0 ? 4u : 0u);
+  return (oct << 12) | spread4(cell[0]) | (spread4(cell[1]) << 1) | (spread4(cell[2]) << 2);
+}
+
+__global__ void __launch_bounds__(256) k_sort_count(const __grid_constant__ SortGrid g, const QRay *__restrict__ q,
+                                                    const unsigned int *__restrict__ n_dev, unsigned int *__restrict__ hist) {
+  const unsigned int n = __ldg(n_dev);
+  for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+    atomicAdd(&hist[sort_key(g, q + j)], 1u);
+}
+
+// exclusive scan of the kSortBuckets counters in place: one CTA, 32 counters per thread
+__global__ void __launch_bounds__(1024) k_sort_scan(unsigned int *__restrict__ hist) {
+  __shared__ unsigned int warp_sums[32];
+  constexpr unsigned int kPer = kSortBuckets / 1024;
+  const unsigned int t = threadIdx.x, lane = t & 31u, w = t >> 5;
+  unsigned int v[kPer], sum = 0;
+#pragma unroll
+  for (unsigned int k = 0; k < kPer; k += 4) {
+    const uint4 x = reinterpret_cast<const uint4 *>(hist + t * kPer)[k / 4];
+    v[k] = x.x, v[k + 1] = x.y, v[k + 2] = x.z, v[k + 3] = x.w;
+    sum += x.x + x.y + x.z + x.w;
+  }
+  unsigned int inc = sum;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int up = __shfl_up_sync(kFullMask, inc, o);
+    if (lane >= (unsigned)o) inc += up;
+  }
+  if (lane == 31) warp_sums[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    unsigned int ws = warp_sums[lane];
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int up = __shfl_up_sync(kFullMask, ws, o);
+      if (lane >= (unsigned)o) ws += up;
+    }
+    warp_sums[lane] = ws;
+  }
+  __syncthreads();
+  unsigned int run = inc - sum + (w ? warp_sums[w - 1] : 0u);
+#pragma unroll
+  for (unsigned int k = 0; k < kPer; k++) {
+    const unsigned int c = v[k];
+    hist[t * kPer + k] = run;
+    run += c;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_sort_scatter(const __grid_constant__ SortGrid g, const QRay *__restrict__ q,
+                                                      const unsigned int *__restrict__ n_dev, unsigned int *__restrict__ offs,
+                                                      QRay *__restrict__ out) {
+  const unsigned int n = __ldg(n_dev);
+  for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const unsigned int pos = atomicAdd(&offs[sort_key(g, q + j)], 1u);
+    const uint4 *src = reinterpret_cast<const uint4 *>(q + j);
+    uint4 *dst = reinterpret_cast<uint4 *>(out + pos);
+    const uint4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
+    dst[0] = a, dst[1] = b, dst[2] = c, dst[3] = d;
   }
 }
 
@@ -770,6 +880,8 @@ cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const
     if (var == 104 && sc.nodes_oct) return MB200_SM(kRefillMin, 4, S, kMinBlocks, kChunk, kVar);      // shade step at 4 parked lanes
     if (var == 116 && sc.nodes_oct) return MB200_SM(kRefillMin, 16, S, kMinBlocks, kChunk, kVar);     // ... at 16
     if (var == 212 && sc.nodes_oct) return MB200_SM(12, 12, S, kMinBlocks, kChunk, kVar);             // refill and shade at 12
+    if (var == 24 && sc.nodes_oct) return MB200_SM(kRefillMin, kShadeMin, S, kMinBlocks, kChunk, kVar | kVarVote);  // phase vote
+    if (var == 56 && sc.nodes_oct) return MB200_SM(kRefillMin, kShadeMin, S, kMinBlocks, kChunk, kVar | kVarVote | kVarVoteBoth);
     if (var == 0) return MB200_SM(kRefillMin, kShadeMin, S, kMinBlocks, kChunk, 0);   // canonical nodes (round-1 production)
     if (var == 4 && sc.nodes64) return MB200_SM(kRefillMin, kShadeMin, S, kMinBlocks, kChunk, kVarNode64);  // 64-byte pair nodes
     if (var == 2) return MB200_SM(kRefillMin, kShadeMin, 0, kMinBlocks, kChunk, kVarTopSmem);  // top of the tree in shared memory
@@ -1138,7 +1250,18 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
   const size_t contrib_bytes = align_up(max_items * sizeof(float), 256);
   const size_t queue_bytes = (path || shadow) ? align_up(max_items * sizeof(QRay), 256) : 0;
   const size_t state_bytes = path ? align_up(max_items * sizeof(PathState), 256) : 0;
-  const size_t slot_bytes = ctl_bytes + hits_bytes + contrib_bytes + queue_bytes * (path ? 2 : 1) + state_bytes;
+  // bounce queues are regrouped by octant and origin cell before they are traced (k_sort_*), MB200_SORT_BOUNCES=0: not
+  // 2 (default): grouped by octant inside every CTA of the shade kernels, no extra pass; 1: full counting sort; 3: both
+  static const int sort_mode = env_int("MB200_SORT_BOUNCES", 2);
+  const bool sort_q = path && (sort_mode & 1), group_q = path && (sort_mode & 2);
+  const size_t sort_bytes = sort_q ? align_up(kSortBuckets * sizeof(unsigned int), 256) : 0;
+  const size_t slot_bytes = ctl_bytes + hits_bytes + contrib_bytes + queue_bytes * (path ? 2 : 1) + state_bytes + sort_bytes;
+  SortGrid sgrid;
+  for (int k = 0; k < 3; k++) {
+    const double ext = sc.root_box[3 + k] - sc.root_box[k];
+    sgrid.lo[k] = sc.root_box[k];
+    sgrid.scale[k] = (ext > 0.0 && ext < DBL_MAX) ? 16.0 / ext : 0.0;
+  }
   cudaError_t e = cudaSuccess;
   if (two_streams || (pipe && chunks)) {
     if ((e = pipe->init()) != cudaSuccess) return e;
@@ -1206,6 +1329,7 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
     QRay *queue[2] = {reinterpret_cast<QRay *>(base + ctl_bytes + hits_bytes + contrib_bytes), nullptr};
     queue[1] = path ? reinterpret_cast<QRay *>(reinterpret_cast<char *>(queue[0]) + queue_bytes) : queue[0];
     PathState *states = path ? reinterpret_cast<PathState *>(reinterpret_cast<char *>(queue[0]) + 2 * queue_bytes) : nullptr;
+    unsigned int *sort_hist = sort_q ? reinterpret_cast<unsigned int *>(reinterpret_cast<char *>(queue[0]) + 2 * queue_bytes + state_bytes) : nullptr;
 
     FrameMap m = make_frame_map(p, p.pass + (uint32_t)B.pass0, (uint32_t)B.npasses);
     m.order = order, m.hot = hot, m.tile0 = B.tile0;
@@ -1246,7 +1370,8 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
       if (e != cudaSuccess) return e;
       {
         TimedScope ts(timer, kKShade, st);
-        k_shade_primary<<<(items + 255) / 256, 256, 0, st>>>(sc, p, m, items, hits, contrib, queue[0], qcount + 0, states, bstats);
+        k_shade_primary<<<(items + 255) / 256, 256, 0, st>>>(sc, p, m, items, hits, contrib, queue[0], qcount + 0, states, bstats,
+                                                             group_q ? 1 : 0);
       }
       g_launches++;
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -1258,7 +1383,17 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
       if ((e = launch_trace<IOQueueShadow, true>(sc, stack_cap, io, 0, qcount + 0, work + 1, stats ? tcount + 4 : nullptr, st)) != cudaSuccess) return e;
     } else if (path) {
       for (int len = 2; len <= p.max_path_length; len++) {
-        const int qi = len & 1; // segment `len` reads queue[qi], writes queue[qi ^ 1]
+        int qi = len & 1; // segment `len` reads queue[qi], writes queue[qi ^ 1]
+        if (sort_q) { // the shade kernels always fill queue[0]; its regrouped copy in queue[1] is what is traced and shaded
+          TimedScope ts(timer, kKShade, st);
+          if ((e = cudaMemsetAsync(sort_hist, 0, kSortBuckets * sizeof(unsigned int), st)) != cudaSuccess) return e;
+          k_sort_count<<<num_sms() * 4, 256, 0, st>>>(sgrid, queue[0], qcount + (len - 2), sort_hist);
+          k_sort_scan<<<1, 1024, 0, st>>>(sort_hist);
+          k_sort_scatter<<<num_sms() * 4, 256, 0, st>>>(sgrid, queue[0], qcount + (len - 2), sort_hist, queue[1]);
+          g_launches += 3;
+          if ((e = cudaGetLastError()) != cudaSuccess) return e;
+          qi = 1;
+        }
         const IOQueueClosest io{queue[qi], hits, m};
         {
           TimedScope ts(timer, kKBounceTrace, st);
@@ -1267,7 +1402,7 @@ cudaError_t launch_frame(const SceneView &sc, int stack_cap, const mb200_render_
         if (e != cudaSuccess) return e;
         TimedScope ts(timer, kKShade, st);
         k_shade_bounce<<<num_sms() * 8, 256, 0, st>>>(sc, p, (unsigned int)len, queue[qi], qcount + (len - 2), hits, queue[qi ^ 1],
-                                                      qcount + (len - 1), states, contrib, bstats);
+                                                      qcount + (len - 1), states, contrib, bstats, group_q ? 1 : 0);
         g_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
       }

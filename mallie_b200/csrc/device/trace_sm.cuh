@@ -294,7 +294,10 @@ template <bool PINHOLE> struct IOFrameFusedT {
 //      conversions and twelve additions
 //   8  octant copies of the pair nodes (layout.h: nodes_oct): boxes pre-ordered (near, far) per axis and children
 //      pre-ordered (near, far) for the ray's octant, so the step has no sign selects and no axis lookup
-constexpr int kVarOctant = 1, kVarTopSmem = 2, kVarNode64 = 4, kVarOctNodes = 8;
+//  16  phase vote: an iteration runs only the step body (INNER or LEAF) that more lanes of the warp wait for; the
+//      other lanes keep their state.  +32: both bodies run when the smaller group has at least kVoteBoth lanes
+constexpr int kVarOctant = 1, kVarTopSmem = 2, kVarNode64 = 4, kVarOctNodes = 8, kVarVote = 16, kVarVoteBoth = 32;
+constexpr int kVoteBoth = 10;
 constexpr uint32_t kTopSlotBytes = 144;
 
 // Stages sc.top_nodes into shared memory at `table` (shared-window address; 16-byte aligned) and waits for it.
@@ -514,8 +517,15 @@ __device__ __forceinline__ void trace_state_machine(const SceneView &sc, const I
     }
 
     // ---- B. INNER: one 128-byte PairNode, both children tested (equivalence: traverse.cuh) -----------------
-    const bool at_inner = (rc == kBranch);
-    const bool at_leaf = (rc - 1u) < (kShade - 1u); // 1 <= rc < kShade
+    bool at_inner = (rc == kBranch);
+    bool at_leaf = (rc - 1u) < (kShade - 1u); // 1 <= rc < kShade
+    if (VAR & kVarVote) {
+      const int ni = __popc(__ballot_sync(kFullMask, at_inner)), nl = __popc(__ballot_sync(kFullMask, at_leaf));
+      if (!(VAR & kVarVoteBoth) || min(ni, nl) < kVoteBoth) {
+        if (ni >= nl) at_leaf = false;
+        else at_inner = false;
+      }
+    }
     if (at_inner) {
       NodeWords nw;
       if ((VAR & kVarTopSmem) && (ref & kTopBit)) nw = load_pair_node_smem(top_table + (ref & ~kTopBit) * kTopSlotBytes);

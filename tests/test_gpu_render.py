@@ -289,3 +289,40 @@ print("LPT-OK")
         env = dict(os.environ, MB200_HOT_STEPS=hot)
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
         assert r.returncode == 0 and "LPT-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+def test_bounce_queue_regrouping_is_invisible():
+    """Continuation rays are regrouped before they are traced (by octant inside the shade kernels' CTAs by default, a
+    full counting sort by octant and origin cell with MB200_SORT_BOUNCES=1/3): a ray's result does not depend on the
+    queue slot it sits in, so path-traced frames and their ray counts must not depend on the mode.  The knob is read
+    once per process, hence the subprocesses."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, hashlib
+sys.path.insert(0, %r)
+import mallie_b200 as M
+from tests import common as T
+out = []
+for name, eye, lookat, plane in (("cornellbox", (0, 0, 20), (0, 0, 0), False), ("teapot", (5, 40, 150), (5, 40, 0), True)):
+    m = T.load_mesh(name)
+    sc = M.Scene(m["vertices"], m["faces"], m["material_ids"], m["normals"], m["uvs"])
+    W, H = 400, 300
+    fg = M.camera_frame(eye, lookat, width=W, height=H)
+    pl = M.plane_from_bounds(*sc.bounds()) if plane else None
+    p = sc.render_params(fg, W, H, shader=M.SHADER_PATHTRACE, max_path_length=6, plane=pl, pass_index=2)
+    img, cnt, st = sc.render_frame(p, 3)
+    assert img.max() > 0 and st["bounce_rays"] > W * H
+    out.append(hashlib.blake2b(img.tobytes() + cnt.tobytes(), digest_size=8).hexdigest() + ":%%d:%%d" %% (st["bounce_rays"], st["zombie_segments"]))
+    sc.close()
+print("DIGEST " + " ".join(out))
+""" % T.HERE.rsplit("/", 1)[0]
+    seen = {}
+    for mode in ("0", "1", "2", "3"):
+        env = dict(os.environ, MB200_SORT_BOUNCES=mode)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+        assert r.returncode == 0 and "DIGEST " in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+        seen[mode] = r.stdout.split("DIGEST ", 1)[1].strip()
+    assert len(set(seen.values())) == 1, seen
