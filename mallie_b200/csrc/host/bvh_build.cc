@@ -45,6 +45,9 @@ struct Builder {
   const TriCache *tc;
   uint32_t *indices;
   mb200_build_options opt;
+  const double *vertices; // for the box of an empty range only
+  const uint32_t *faces;
+  size_t nfaces;
 };
 
 struct SubTree {
@@ -60,6 +63,15 @@ inline double half_area2(const double lo[3], const double hi[3]) {
 
 void range_bounds(const Builder &b, uint32_t l, uint32_t r, double lo[3], double hi[3]) {
   const TriCache &tc = *b.tc;
+  if (l == r) {
+    // An empty range (the left child of the object-median fallback on a single triangle, reachable only with
+    // minLeafPrimitives <= 1): ComputeBoundingBox seeds the box with the first vertex of the triangle at
+    // indices[leftIndex] before its loop (bvh_accel.cc:291-298) and the loop then adds nothing.
+    const uint32_t t = b.indices[l < b.nfaces ? l : b.nfaces - 1];
+    const double *p0 = b.vertices + 3 * (size_t)b.faces[3 * (size_t)t];
+    for (int a = 0; a < 3; a++) lo[a] = p0[a] - kBoundsPad, hi[a] = p0[a] + kBoundsPad;
+    return;
+  }
   for (int a = 0; a < 3; a++) {
     double mn = tc.lo[a][b.indices[l]], mx = tc.hi[a][b.indices[l]];
     for (uint32_t i = l + 1; i < r; i++) {
@@ -240,6 +252,17 @@ bool build_bvh(HostBVH &out, const double *vertices, size_t nverts, const uint32
     if (err) *err = "bin_size must be in (1, 65536]";
     return false;
   }
+  // minLeafPrimitives <= 0 would split empty ranges into two empty ranges down to maxTreeDepth (2^depth nodes; the
+  // reference does exactly that and runs out of memory); minLeafPrimitives == 1 is accepted and reproduces the
+  // reference's depth-maxTreeDepth chains of empty left children under every single-triangle range.
+  if (opt.min_leaf_primitives < 1) {
+    if (err) *err = "min_leaf_primitives must be >= 1";
+    return false;
+  }
+  if (opt.max_tree_depth < 0) {
+    if (err) *err = "max_tree_depth must be >= 0";
+    return false;
+  }
   if (nfaces > 0xFFFFFFF0ull) {
     if (err) *err = "too many triangles (index array is 32-bit, bvh_accel.h:85)";
     return false;
@@ -280,6 +303,7 @@ bool build_bvh(HostBVH &out, const double *vertices, size_t nverts, const uint32
   b.tc = &tc;
   b.indices = out.indices.data();
   b.opt = opt;
+  b.vertices = vertices, b.faces = faces, b.nfaces = nfaces;
   SubTree root;
   root.nodes.reserve(nfaces / 4 + 16);
 #pragma omp parallel

@@ -180,6 +180,20 @@ double ref_scene_build(void *h) {
   return ok ? (t1 - t0) : -1.0;
 }
 
+// The same with explicit BVHBuildOptions (bvh_accel.h:32-42).
+double ref_scene_build_opts(void *h, double cost_taabb, int min_leaf_primitives, int max_tree_depth, int bin_size) {
+  RefScene *s = (RefScene *)h;
+  BVHBuildOptions options;
+  options.costTaabb = cost_taabb;
+  options.minLeafPrimitives = min_leaf_primitives;
+  options.maxTreeDepth = max_tree_depth;
+  options.binSize = bin_size;
+  double t0 = now_sec();
+  bool ok = s->scene->accel().Build(&s->scene->mesh(), options);
+  double t1 = now_sec();
+  return ok ? (t1 - t0) : -1.0;
+}
+
 size_t ref_scene_num_nodes(void *h) { return ((RefScene *)h)->scene->accel().GetNodes().size(); }
 size_t ref_scene_num_indices(void *h) { return ((RefScene *)h)->scene->accel().GetIndices().size(); }
 

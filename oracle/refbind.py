@@ -56,6 +56,8 @@ def lib():
         L.ref_scene_get_mesh.argtypes = [vp] * 6
         L.ref_scene_build.restype = dbl
         L.ref_scene_build.argtypes = [vp]
+        L.ref_scene_build_opts.restype = dbl
+        L.ref_scene_build_opts.argtypes = [vp, dbl, C.c_int, C.c_int, C.c_int]
         L.ref_scene_get_bvh.argtypes = [vp, vp, vp]
         L.ref_scene_get_stats.argtypes = [vp, vp]
         L.ref_scene_dump.restype = i32
@@ -131,8 +133,13 @@ class RefScene:
         L.ref_scene_get_mesh(self.h, _p(v), _p(f), _p(m), _p(n), _p(t))
         return dict(vertices=v, faces=f, material_ids=m, normals=n, uvs=t)
 
-    def build(self):
-        s = lib().ref_scene_build(self.h)
+    def build(self, cost_taabb=None, min_leaf=None, max_depth=None, bin_size=None):
+        """BVHAccel::Build; with any option given, explicit BVHBuildOptions (defaults 0.2 / 16 / 256 / 64)."""
+        if (cost_taabb, min_leaf, max_depth, bin_size) != (None, None, None, None):
+            s = lib().ref_scene_build_opts(self.h, 0.2 if cost_taabb is None else cost_taabb, 16 if min_leaf is None else min_leaf,
+                                           256 if max_depth is None else max_depth, 64 if bin_size is None else bin_size)
+        else:
+            s = lib().ref_scene_build(self.h)
         if s < 0:
             raise RuntimeError("reference BVHAccel::Build failed")
         return s

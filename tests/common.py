@@ -124,6 +124,23 @@ def build_cases():
     return cases
 
 
+def build_option_cases():
+    """(mesh name, BVHBuildOptions as keyword arguments): non-default options the reference's builder was run with for
+    tests/golden/build_golden.json (key "name|k=v,...").  min_leaf=1 makes the reference hang a depth-maxTreeDepth chain
+    of empty left leaves under every single-triangle range; only small meshes carry it."""
+    opts = [dict(min_leaf=2, bin_size=8), dict(min_leaf=4), dict(max_depth=3), dict(max_depth=5), dict(bin_size=2),
+            dict(bin_size=16), dict(bin_size=128, cost_taabb=0.5), dict(bin_size=1024), dict(cost_taabb=0.0),
+            dict(cost_taabb=5.0, min_leaf=8)]
+    out = [(n, o) for n in ("soup_overlapping", "doubled_grid", "soup_large_negative", "identical_100") for o in opts]
+    out += [(n, dict(min_leaf=1)) for n in ("soup_1", "soup_17", "identical_100")]
+    out += [("soup_17", dict(min_leaf=1, max_depth=9)), ("soup_overlapping", dict(min_leaf=1, max_depth=14))]
+    return out
+
+
+def build_option_key(name, opt):
+    return name + "|" + ",".join(f"{k}={opt[k]}" for k in sorted(opt))
+
+
 @functools.lru_cache(maxsize=None)
 def build_golden():
     with open(os.path.join(GOLDEN, "build_golden.json")) as fp:

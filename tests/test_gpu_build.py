@@ -72,6 +72,20 @@ def test_device_builder_edge_cases_match_the_reference_tree(name):
     db.close()
 
 
+DEVICE_OPTION_CASES = [(n, o) for n, o in T.build_option_cases() if o.get("min_leaf", 16) >= 2]
+
+
+@pytest.mark.parametrize("name,opt", DEVICE_OPTION_CASES, ids=[T.build_option_key(n, o) for n, o in DEVICE_OPTION_CASES])
+def test_device_builder_matches_the_reference_tree_under_options(name, opt):
+    """The reference's own trees under non-default BVHBuildOptions (goldens made by ref_scene_build_opts)."""
+    v, f = T.build_cases()[name]
+    g = T.build_golden()[T.build_option_key(name, opt)]
+    db = M.HostBVH.build_device(v, f, **opt)
+    assert T.tree_fingerprint(*db.arrays()) == {k: g[k] for k in ("num_nodes", "nodes_fnv", "indices_fnv")}
+    assert db.stats() == g["stats"]
+    db.close()
+
+
 @pytest.mark.parametrize("case", [
     dict(n=5000, seed=1),                                   # overlapping triangles, many straddle the planes
     dict(n=5000, seed=2, tri=0.8),                          # huge triangles: most bins shared, frequent median fallback

@@ -207,6 +207,36 @@ def test_deep_tree_uses_big_stack():
         M.Scene(v, f, nodes=nodes, indices=idx)
 
 
+def test_tree_with_empty_leaves_min_leaf_primitives_1():
+    """minLeafPrimitives = 1: the reference's tree hangs a 256-deep chain under every triangle, each level an EMPTY left
+    leaf (a point box at the triangle's first vertex) and the triangle again.  The traversal must visit and count those
+    boxes as the reference does (hits and counters against the oracle walking the very same tree; the tree itself is
+    pinned to the reference's in tests/test_build_golden.py)."""
+    rng = np.random.default_rng(5)
+    for name in ("soup_17", "identical_100"):
+        v, f = T.build_cases()[name]
+        hb = M.HostBVH.build(v, f, min_leaf=1)
+        nodes, idx = hb.arrays()
+        assert hb.stats()["maxTreeDepth"] == 256 and ((nodes["flag"] == 1) & (nodes["data"][:, 0] == 0)).sum() > 1000
+        sc = M.Scene(v, f, nodes=nodes, indices=idx)
+        ob = O.BVH.from_arrays(nodes, idx, O.Mesh(v, f))
+        rays = T.random_rays(rng, 20_000, v.min(0) - 0.1, v.max(0) + 0.1)
+        # plus rays aimed at first vertices, i.e. straight through the point boxes of the empty leaves
+        tgt = v[f[rng.integers(0, len(f), 5000), 0]]
+        org = tgt + rng.normal(0, 1.0, tgt.shape)
+        d = tgt - org
+        rays = np.concatenate([rays, np.concatenate([org, d / np.linalg.norm(d, axis=1, keepdims=True)], axis=1)])
+        hits, cnt = sc.trace_closest(rays, counters=True)
+        o = ob.trace(rays)
+        T.assert_hits_equal(hits, o["hits"], name)
+        assert cnt["nodes_tested"] == o["n_node"] and cnt["tris_tested"] == o["n_tri"]
+        assert o["mask"].any()
+        tmax = np.where(o["mask"], o["hits"]["t"] * rng.choice([0.9, 1.0, 1.1], len(rays)), 5.0)
+        assert np.array_equal(sc.trace_occluded(rays, tmax), ob.occluded(rays, tmax))
+        sc.close()
+        hb.close()
+
+
 def test_malformed_bvh_is_rejected():
     m = T.load_mesh("sphere40")
     hb = M.HostBVH.build(m["vertices"], m["faces"])

@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
+python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -2
 for n in 8 4 2 1; do  # the 1m workload at every N, then config 5 (10m) at 8
   if [ $n -eq 1 ]; then python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/r2_scale_n_n1.json 2> gpurun_out/r2_scale_n_n1.err
   else python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2953$n bench.py --gpus $n --steps 20 --warmup 3 --no-cpu > gpurun_out/r2_scale_n_n$n.json 2> gpurun_out/r2_scale_n_n$n.err; fi
