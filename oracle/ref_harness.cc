@@ -136,6 +136,28 @@ void *ref_scene_from_file(const char *path, int kind, double scene_scale) {
   return s;
 }
 
+// The real Scene::Init (scene.cc:66-250): load, scene_fit / scene_scale, BVHAccel::Build with default options.
+// kind 0 = .obj, 1 = .eson.  bounds (nullable): Scene::BoundingBox after Init, bmin[3] then bmax[3].
+void *ref_scene_init(const char *path, int kind, double scene_scale, int scene_fit, double *bounds) {
+  RefScene *s = new RefScene;
+  s->scene = new HarnessScene;
+  zero_mesh(s->scene->mesh());
+  const std::string p(path), none;
+  const bool ok = s->scene->Init(kind == 0 ? p : none, kind == 1 ? p : none, none, none, scene_scale, scene_fit != 0);
+  if (!ok) {
+    zero_mesh(s->scene->mesh());
+    delete s->scene;
+    delete s;
+    return NULL;
+  }
+  if (bounds) {
+    real3 bmin, bmax;
+    s->scene->BoundingBox(bmin, bmax);
+    for (int k = 0; k < 3; k++) bounds[k] = bmin[k], bounds[3 + k] = bmax[k];
+  }
+  return s;
+}
+
 void ref_scene_destroy(void *h) {
   RefScene *s = (RefScene *)h;
   if (!s) return;

@@ -45,6 +45,8 @@ def lib():
         L.ref_scene_from_arrays.argtypes = [vp, sz, vp, sz, vp, vp, vp]
         L.ref_scene_from_file.restype = vp
         L.ref_scene_from_file.argtypes = [C.c_char_p, i32, dbl]
+        L.ref_scene_init.restype = vp
+        L.ref_scene_init.argtypes = [C.c_char_p, i32, dbl, i32, vp]
         L.ref_scene_destroy.argtypes = [vp]
         for f in ("ref_scene_num_vertices", "ref_scene_num_faces", "ref_scene_num_nodes",
                   "ref_scene_num_indices"):
@@ -110,6 +112,19 @@ class RefScene:
     def from_file(cls, path, scene_scale=1.0):
         kind = 1 if path.endswith(".eson") else 0
         return cls(lib().ref_scene_from_file(path.encode(), kind, float(scene_scale)))
+
+    @classmethod
+    def init(cls, path, scene_scale=1.0, scene_fit=False):
+        """The reference's own Scene::Init (load + scene_fit / scene_scale + default build).  self.bounds =
+        Scene::BoundingBox afterwards."""
+        kind = 1 if path.endswith(".eson") else 0
+        b = np.zeros(6, np.float64)
+        h = lib().ref_scene_init(path.encode(), kind, float(scene_scale), int(bool(scene_fit)), _p(b))
+        if not h:
+            raise RuntimeError("reference Scene::Init failed for " + path)
+        self = cls(h)
+        self.bounds = (b[:3].copy(), b[3:].copy())
+        return self
 
     def close(self):
         if self.h:

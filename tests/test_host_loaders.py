@@ -154,3 +154,35 @@ def test_config_type_rules_and_quirks(tmp_path):
     c = M.load_config(path=str(p))
     assert c.obj_filename.decode() == os.path.expanduser("~/x.obj")
     assert c.shader == M.SHADER_PRIMARY_SHADOW and list(c.light) == [1, 2, 3] and c.max_path_length == 5 and c.num_gpus == 8
+
+
+def test_scene_init_matches_the_reference_scene_init(tmp_path):
+    """The reference's own Scene::Init (scene.cc:66-250, through oracle/_ref: load, scene_fit / scene_scale, default
+    build, BoundingBox) against load_mesh + the host builder on the committed fixtures and on a flat mesh, whose zero
+    extent takes the `invExtent = extent` branch of scene_fit (scene.cc:134-137)."""
+    from oracle import refbind as R
+    if not R.available():
+        pytest.skip("oracle/_ref is built where /root/reference is mounted")
+    flat = tmp_path / "flat.obj"
+    with open(flat, "w") as fp:
+        for i in range(6):
+            for j in range(6):
+                fp.write("v %d %g 7.25\n" % (i, 0.5 * j))
+        for i in range(5):
+            for j in range(5):
+                a = i * 6 + j + 1
+                fp.write("f %d %d %d\nf %d %d %d\n" % (a, a + 1, a + 6, a + 1, a + 7, a + 6))
+    with in_dir(T.GOLDEN):
+        for path in ("tricky.obj", "small.eson", str(flat)):
+            for scale, fit in ((1.0, False), (2.5, False), (1.0, True), (0.3, True)):
+                rs = R.RefScene.init(path, scale, fit)
+                want = rs.mesh()
+                got = M.load_mesh(path, scene_scale=scale, scene_fit=fit)
+                assert got["vertices"].tobytes() == want["vertices"].tobytes(), (path, scale, fit)
+                assert np.array_equal(got["faces"], want["faces"])
+                hb = M.HostBVH.build(got["vertices"], got["faces"])
+                nodes, idx = hb.arrays()
+                assert T.tree_fingerprint(nodes, idx) == T.tree_fingerprint(*rs.bvh())
+                assert np.array_equal(nodes[0]["bmin"], rs.bounds[0]) and np.array_equal(nodes[0]["bmax"], rs.bounds[1])
+                hb.close()
+                rs.close()

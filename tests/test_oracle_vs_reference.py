@@ -156,26 +156,31 @@ def test_dump_is_byte_compatible_with_reference(tmp_path):
 
 
 @pytest.mark.parametrize("plane", [False, True])
-def test_render_one_thread_bit_identical(plane):
-    """Render() keeps function-static state (render.cc:113-116,615): run the reference in a fresh process."""
+@pytest.mark.parametrize("mesh,eye,lookat", [("sphere40", (0.3, 0.2, 3), (0, 0, 0)), ("cornellbox", (0, 0, 20), (0, 0, 0)),
+                                             ("teapot", (5, 40, 150), (5, 40, 0))])
+def test_render_one_thread_bit_identical(mesh, eye, lookat, plane):
+    """Render() keeps function-static state (render.cc:113-116,615): run the reference in a fresh process.  The cornell
+    box and the teapot carry material ids, facevarying normals and uvs (BuildIntersection's interpolation feeds the
+    bounce directions)."""
     code = f"""
 import sys; sys.path.insert(0, {ROOT!r})
 import numpy as np
 from oracle import refbind as R, orabind as O
 from tests import common as T
-m = T.load_mesh("sphere40")
-rs = R.RefScene.from_arrays(m["vertices"], m["faces"]); rs.build()
-img, cnt, sec = rs.render(160, 120, (0.3, 0.2, 3), (0, 0, 0), plane={plane}, nthreads=1)
+m = T.load_mesh({mesh!r})
+rs = R.RefScene.from_arrays(m["vertices"], m["faces"], m.get("material_ids"), m.get("normals"), m.get("uvs")); rs.build()
+img, cnt, sec = rs.render(160, 120, {eye!r}, {lookat!r}, plane={plane}, nthreads=1)
 print("RESULT %016x %d" % (O.fnv1a64(img), int(cnt.sum())))
 """
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True).stdout
     line = [l for l in out.splitlines() if l.startswith("RESULT")][0].split()
-    om, ob = T.oracle_scene("sphere40")
+    om, ob = T.oracle_scene(mesh)
     nodes, _ = ob.arrays()
     pl = O.plane_from_bbox(nodes[0]["bmin"], nodes[0]["bmax"]) if plane else None
-    fr = O.camera_frame((0.3, 0.2, 3), (0, 0, 0), width=160, height=120)
+    fr = O.camera_frame(eye, lookat, width=160, height=120)
     img, cnt, _ = ob.render_pass(fr, 160, 120, plane=pl, rng_mode=0, skip_zombies=1, shader=0, nthreads=1)
     assert T.fnv(img) == line[1] and int(cnt.sum()) == int(line[2]) == 160 * 120
+    assert img.max() > 0
 
 
 def test_env_camera_rays_bit_identical():
