@@ -25,6 +25,18 @@ for shader, kw in ((M.SHADER_PRIMARY_SHADOW, dict(light=(2, 4, 3))), (M.SHADER_P
     sc.render_frame(p, 3)
 p = sc.render_params(fg, W, H, shader=M.SHADER_PRIMARY_SHADOW, light=(2, 4, 3), step=4)
 sc.render_pass(p)
+# round 2: frames large enough for the row cut + chunked copy-back and the longest-rays-first order (>= 1024 tiles, twice
+# the same layout), the device LDR resolves, the measured-peaks probes
+Wb, Hb = 512, 264
+fb = M.camera_frame((0.3, 0.2, 3.0), (0, 0, 0), width=Wb, height=Hb)
+pb = sc.render_params(fb, Wb, Hb, shader=M.SHADER_PRIMARY_SHADOW, light=(2, 4, 3))
+for _ in range(2):
+    img, cntb, _ = sc.render_frame(pb, 2)
+for mode in (M.capi.LDR_RGB8_LINEAR, M.capi.LDR_BGRA8_GAMMA22):
+    sc.resolve_ldr(img, cntb, Wb, Hb, mode)
+    sc.render_frame_ldr(pb, 2, mode)
+pp = sc.render_params(fb, Wb, Hb, shader=M.SHADER_PATHTRACE, max_path_length=5, plane=M.plane_from_bounds(*sc.bounds()))
+sc.render_frame(pp, 2)
 p = sc.render_params(fg, W, H, shader=M.SHADER_PRIMARY_SHADOW, light=(2, 4, 3), bands=(4, 3, 1), compact=True)
 sc.render_pass(p)
 sc.close()
