@@ -10,6 +10,7 @@
 #ifndef MALLIE_B200_SHADE_CUH_
 #define MALLIE_B200_SHADE_CUH_
 
+#include "mathd.cuh"
 #include "layout.h"
 #include "mallie_b200.h"
 #include "traverse.cuh"
@@ -69,25 +70,32 @@ __device__ __forceinline__ void generate_env_ray(const double origin[3], int wid
   const double kPi = 3.14159265358979323846;
   ox = origin[0], oy = origin[1], oz = origin[2];
   const double phi = 2.0 * kPi * (u / (double)width);
+  // sin / cos rounded once from double-double values (mathd.cuh): what the host's libm returns in ~99.9 % of its results
+  double st, ct, sp, cp;
+  mathd::sincos_rn(phi, sp, cp);
   if (!stereo) {
     const double theta = kPi * (v / (double)height);
-    dx = sin(theta) * cos(phi);
-    dy = cos(theta);
-    dz = sin(theta) * sin(phi);
+    mathd::sincos_rn(theta, st, ct);
+    dx = st * cp;
+    dy = ct;
+    dz = st * sp;
     return;
   }
   const bool left = v < (double)(height >> 1);
-  const double focal_length = 4.0, r = 0.5;
+  const double r = 0.5; // focal_length = 4.0
   const double theta = kPi * fmod(2.0 * v / (double)height, 1.0);
-  const double ex = sin(theta) * cos(phi), ey = cos(theta), ez = sin(theta) * sin(phi);
+  mathd::sincos_rn(theta, st, ct);
+  const double ex = st * cp, ey = ct, ez = st * sp;
   double px = left ? -ez : ez, py = 0.0, pz = left ? ex : -ex;
   normalize3(px, py, pz);
   ox += px * r, oy += py * r, oz += pz * r;
-  double psi = atan2(r, focal_length);
-  if (left) psi = -psi;
-  dx = ex * cos(psi) - ez * sin(psi);
+  // psi = atan2(r, focal_length) = atan2(0.5, 4.0) is a constant of the reference (camera.cc:308): psi, cos(psi) and
+  // sin(psi) below are the correctly rounded values (= glibc's); the left eye uses -psi, cos even, sin odd
+  const double cpsi = 0.9922778767136676, spsi_abs = 0.12403473458920845;
+  const double spsi = left ? -spsi_abs : spsi_abs;
+  dx = ex * cpsi - ez * spsi;
   dy = ey;
-  dz = ex * sin(psi) + ez * cos(psi);
+  dz = ex * spsi + ez * cpsi;
   normalize3(dx, dy, dz);
 }
 

@@ -63,7 +63,7 @@ def test_pathtrace_matches_oracle(plane):
     img, cnt, st = sc.render_pass(p)
     oimg, ocnt, oc = ob.render_pass(fo, W, H, plane=opl, rng_mode=1, pass_index=3, skip_zombies=1, shader=0)
     same = (img.view(np.uint32) == oimg.view(np.uint32)).all(axis=2)
-    assert same.mean() >= 0.999, f"only {same.mean():.5f} of the pixels are bit-identical"
+    assert same.mean() >= 0.9999, f"only {same.mean():.5f} of the pixels are bit-identical"
     assert abs(float(img.sum(dtype=np.float64)) - float(oimg.sum(dtype=np.float64))) <= 1e-4 * float(oimg.sum(dtype=np.float64))
     # ray accounting: zombies are not rays; traced rays agree up to the few ulp-flipped paths
     traced = st["primary_rays"] + st["bounce_rays"]
@@ -83,7 +83,7 @@ def test_max_path_length_and_unjittered_primary_only():
         img, _, st = sc.render_pass(p)
         oimg, _, oc = ob.render_pass(fo, W, H, rng_mode=1, pass_index=1, max_path_length=L)
         same = (img.view(np.uint32) == oimg.view(np.uint32)).all(axis=2)
-        assert same.mean() >= 0.999
+        assert same.mean() >= 0.9999, same.mean()
         if L == 1:
             assert not img.any() and st["bounce_rays"] == 0
     # primary-only, no jitter: coverage mask == un-jittered closest-hit mask
@@ -220,8 +220,10 @@ def test_kernel_timing_hooks():
 @pytest.mark.parametrize("stereo", [False, True])
 def test_panorama_cameras_and_env_shader(stereo):
     """K1 for Camera::GenerateEnvRay / GenerateStereoEnvRay (camera.cc:242-329) and the PathTraceEnv shader
-    (render.cc:518-590).  CUDA's sin / cos / fmod / atan2 are not glibc's: rays agree to a few ulp (the contract's
-    1e-5 relative leaves nine orders of magnitude), hit records on identical rays are bit-exact as everywhere."""
+    (render.cc:518-590).  The device rounds sin / cos once from double-double values (device/mathd.cuh, held against
+    mpmath in tests/test_mathd.py) and atan2(0.5, 4.0) is a constant, so rays are the reference's bit for bit wherever the
+    host's libm rounds correctly (glibc: ~99.9 % of its results; four or five calls per ray); the rest differ by one ulp
+    of one component.  Hit records on identical rays are bit-exact as everywhere."""
     W, H = 192, 96
     m = T.load_mesh("cornellbox")
     sc = M.Scene(m["vertices"], m["faces"], m["material_ids"], m["normals"], m["uvs"])
@@ -231,7 +233,8 @@ def test_panorama_cameras_and_env_shader(stereo):
     px, py = rng.uniform(-0.5, W - 0.5, 4000), rng.uniform(-0.5, H - 0.5, 4000)
     got = sc.generate_rays_env(origin, W, H, px, py, stereo=stereo)
     want = O.generate_env(origin, W, H, px, py, stereo=stereo)
-    assert np.abs(got - want).max() < 1e-13
+    assert np.abs(got - want).max() < 1e-15
+    assert (got.view(np.uint64) == want.view(np.uint64)).all(axis=1).mean() >= 0.98
     T.assert_hits_equal(sc.trace_closest(want), ob.trace(want)["hits"], "env rays")
     # one pass of the env shader through the frame pipeline vs the oracle
     fg = M.camera_frame(origin, (0, 1, 0), width=W, height=H)
@@ -241,8 +244,8 @@ def test_panorama_cameras_and_env_shader(stereo):
     img, cnt, st = sc.render_pass(p)
     oimg, _, oc = ob.render_pass(fo, W, H, rng_mode=1, pass_index=4, shader=2, camera_mode=int(mode))
     same = (img.view(np.uint32) == oimg.view(np.uint32)).all(axis=2)
-    assert same.mean() >= 0.99, same.mean()
-    assert abs(float(img.sum(dtype=np.float64)) - float(oimg.sum(dtype=np.float64))) <= 2e-3 * float(oimg.sum(dtype=np.float64))
+    assert same.mean() >= 0.999, same.mean()
+    assert abs(float(img.sum(dtype=np.float64)) - float(oimg.sum(dtype=np.float64))) <= 1e-4 * float(oimg.sum(dtype=np.float64))
     assert st["primary_rays"] == W * H and (cnt == 1).all() and img.max() > 0
     # the plane and the materials are ignored by PathTraceEnv
     pl = M.plane_from_bounds(*sc.bounds())
