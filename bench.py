@@ -13,8 +13,9 @@ A "step" is one frame.  Camera eye (0,0,3) -> origin, fov 45, light (2,4,3).
 
 * value : whole-job Mrays/s with everything resident in HBM (the assembled framebuffer stays on the device).
           N > 1: one process per GPU, image rows interleaved over the ranks in bands of 4 scanlines (strong scaling:
-          the frame is fixed), every rank renders its bands straight into the NCCL send buffer and ONE ncclAllGather +
-          the library's row-placement kernel assemble the frame on every rank (mb200_render_frame_gathered).
+          the frame is fixed), every rank renders its bands into a compact buffer and mb200_render_frame_gathered
+          assembles the frame on every rank: one kernel of the library stores the rows into every rank's frame buffer
+          over peer memory (or, MB200_GATHER=nccl / when buffers cannot be mapped: ncclAllGather + row placement).
 * e2e   : the same frame through the C-ABI call a Mallie host makes with a pinned HOST framebuffer
           (mb200_render_frame at N = 1, mb200_render_frame_gathered at N > 1 with the host buffer on rank 0); the
           device->host copy of the framebuffer is inside the timed region (at N = 1 the library copies the rows of the
@@ -86,7 +87,12 @@ def emit(line):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
-def config_dict(wl, name, n_gpus):
+EXCHANGE = {1: "k_exchange_rows: every rank stores its rows straight into every rank's frame buffer over peer memory "
+                 "(cudaIpc-mapped through the communicator), flag barrier in the same kernel",
+            0: "one ncclAllGather of the framebuffer per frame + the library's row-placement kernel"}
+
+
+def config_dict(wl, name, n_gpus, exchange=None):
     return {
         "workload": f"{name}: bumpy-sphere N={wl['sphere_n']} ({wl['triangles']:,} triangles, {wl['vertices']:,} vertices), "
                     f"{wl['W']}x{wl['H']}, {wl['spp']} spp, primary closest-hit + 1 shadow ray per hit, eye (0,0,3) lookat "
@@ -94,8 +100,8 @@ def config_dict(wl, name, n_gpus):
         "triangles": wl["triangles"], "resolution": [wl["W"], wl["H"]], "spp": wl["spp"], "shader": "primary+shadow",
         "parallelism": "1 GPU" if n_gpus == 1 else f"image rows in {BAND_ROWS}-scanline bands interleaved over "
                                                     f"{n_gpus} GPUs (one process each), full scene replica per GPU, "
-                                                    "one ncclAllGather of the framebuffer per frame (C ABI: "
-                                                    "mb200_render_frame_gathered)",
+                                                    f"frame assembled on every rank by mb200_render_frame_gathered (C ABI): "
+                                                    f"{EXCHANGE.get(exchange, EXCHANGE[0])}",
         "l2": f"L2 flushed between timed steps (512 MiB memset); the scene ({wl['scene_mb']} MB) " +
               ("is L2-resident within a step" if wl["scene_mb"] < 126 else "does not fit the 126 MB L2"),
     }
@@ -566,7 +572,7 @@ def main():
             "metric": metric_name(wl), "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(wl, args.workload, world), "clocks": clocks,
+            "config": config_dict(wl, args.workload, world, comm.exchange_path() if comm is not None else None), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * float(e2e_t[0]) / args.steps},
             "gpu_launches": launches, "parity": parity, "roofline": roofline, "cpu_baseline": cpu_baseline,

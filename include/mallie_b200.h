@@ -410,8 +410,13 @@ int mb200_comm_init(mb200_comm **out, mb200_scene *scene, int nranks, int rank, 
 int mb200_comm_adopt(mb200_comm **out, mb200_scene *scene, void *nccl_comm);
 int mb200_comm_size(const mb200_comm *comm);
 int mb200_comm_rank(const mb200_comm *comm);
+/* How the last gathered frame was exchanged: 1 = rows stored straight into every rank's frame buffer over peer memory
+ * (k_exchange_rows; one node, every rank can map every other rank's buffer), 0 = ncclAllGather + row placement. */
+int mb200_comm_exchange_path(const mb200_comm *comm);
 void mb200_comm_destroy(mb200_comm *comm);
-/* All-gather + row placement.  d_bands: this rank's compact band buffer (device, float[channels*width*
+/* The exchange of the bands (peer-memory stores when every rank can map every other rank's frame buffer -- decided once
+ * per frame size by a collective set-up on the first call -- else ncclAllGather + row placement; MB200_GATHER=nccl forces
+ * the latter).  d_bands: this rank's compact band buffer (device, float[channels*width*
  * mb200_band_local_rows()], what a band_compact render call wrote); image: float[channels*width*height], device
  * pointer (enqueue-only on the scene's stream) or host pointer (blocks until readable), or NULL on a rank that
  * does not need the assembled frame (it still takes part in the collective). */

@@ -42,7 +42,7 @@ EXPORTS = [
     "mb200_camera_frame_build", "mb200_generate_rays", "mb200_generate_rays_env", "mb200_generate_rays_grid",
     "mb200_render_params_default", "mb200_plane_from_bounds", "mb200_render_pass", "mb200_render_accumulate",
     "mb200_render_frame", "mb200_render_frame_multi", "mb200_band_local_rows", "mb200_resolve_ldr", "mb200_render_frame_ldr",
-    "mb200_comm_unique_id", "mb200_comm_init", "mb200_comm_adopt", "mb200_comm_size", "mb200_comm_rank",
+    "mb200_comm_unique_id", "mb200_comm_init", "mb200_comm_adopt", "mb200_comm_size", "mb200_comm_rank", "mb200_comm_exchange_path",
     "mb200_comm_destroy", "mb200_gather_framebuffer", "mb200_render_frame_gathered",
     "mb200_mesh_load_obj", "mb200_mesh_load_eson", "mb200_mesh_transform", "mb200_mesh_num_vertices",
     "mb200_mesh_num_faces", "mb200_mesh_vertices", "mb200_mesh_faces", "mb200_mesh_material_ids",
@@ -204,6 +204,7 @@ def lib():
         L.mb200_comm_adopt.argtypes = [C.POINTER(vp), vp, vp]
         L.mb200_comm_size.argtypes = [vp]
         L.mb200_comm_rank.argtypes = [vp]
+        L.mb200_comm_exchange_path.argtypes = [vp]
         L.mb200_comm_destroy.argtypes = [vp]
         L.mb200_gather_framebuffer.argtypes = [vp, i32, i32, i32, i32, vp, vp]
         L.mb200_render_frame_gathered.argtypes = [vp, C.POINTER(RenderParams), i32, i32, vp, vp, C.POINTER(RenderStats)]
@@ -303,6 +304,10 @@ class Comm:
         check(lib().mb200_render_frame_gathered(self.h, C.byref(params), num_passes, band_rows, _p(image), _p(count),
                                                 C.byref(st) if stats else None))
         return st.as_dict() if stats else None
+
+    def exchange_path(self):
+        """1: the last gathered frame went through the peer-memory exchange kernel, 0: through ncclAllGather."""
+        return int(lib().mb200_comm_exchange_path(self.h))
 
     def close(self):
         if self.h:

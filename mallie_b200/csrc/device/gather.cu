@@ -2,9 +2,14 @@
 // row bands over one process per GPU (the reference has no equivalent, its MPI is an
 // init/finalize stub: main.cc:213-236).
 //
-// Every rank renders its bands into a compact buffer that IS the NCCL send buffer (mb200_render_params
-// band_compact), one ncclAllGather on the scene's stream moves the bands, and k_deinterleave_rows -- this
-// library's kernel, on the same stream -- writes the rows into place.  NCCL is bound at run time
+// Every rank renders its bands into a compact buffer (mb200_render_params band_compact).  Two ways to exchange them:
+//   * peer memory (default when every rank of the communicator can map every other rank's frame buffer: one node,
+//     NVLink / NVSwitch): k_exchange_rows -- ONE kernel of this library -- stores the rank's rows straight into place
+//     in every rank's frame buffer (cudaIpc-mapped, found once through the communicator), then its last CTA raises
+//     this rank's flag in every peer and waits for theirs: no all-gather, no row placement pass, no NCCL launch on
+//     the frame's critical path;
+//   * NCCL (MB200_GATHER=nccl, or when the mapping fails on any rank): the compact buffer IS the NCCL send buffer, one
+//     ncclAllGather on the scene's stream moves the bands, and k_deinterleave_rows writes the rows into place.  NCCL is bound at run time
 // (dlopen of libnccl.so.2: inside a PyTorch process that is the copy torch already loaded, so the two never
 // disagree about versions); a host without NCCL gets MB200_ERR_UNSUPPORTED from mb200_comm_*, nothing else changes.
 #include <cuda_runtime.h>
@@ -17,6 +22,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "kernels.h"
 #include "scene.h"
@@ -101,6 +107,55 @@ __global__ void __launch_bounds__(256) k_deinterleave_rows_scalar(const float *_
   }
 }
 
+// ---- exchange over peer memory ---------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+constexpr size_t kPeerHeaderBytes = 1024; // [0, 128): flags[kMaxPeers] (u64), [128, 132): CTA counter; frames follow
+struct PeerTable {
+  char *base[kMaxPeers]; // rank p's buffer as mapped into this process (own rank: the allocation itself)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// bands: this rank's compact rows [local_rows][row_vec4].  Row `local` of the compact buffer is image row
+// ((local / band_rows) * ranks + rank) * band_rows + local % band_rows; it is stored there in EVERY rank's frame
+// (peer stores over NVLink; the own copy is a local store).  Then the exchange is closed: every CTA fences its stores
+// system-wide and counts itself; the last one writes `epoch` into this rank's flag in every peer's header and waits until
+// every peer's flag in the own header has reached `epoch` -- at that point all rows of the frame are in local memory.
+__global__ void __launch_bounds__(256)
+    k_exchange_rows(const float4 *__restrict__ bands, const __grid_constant__ PeerTable t, size_t frame_off, int local_rows,
+                    int row_vec4, int band_rows, int ranks, int rank, unsigned long long epoch) {
+  const size_t total = (size_t)local_rows * row_vec4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int local = (int)(i / row_vec4), x = (int)(i - (size_t)local * row_vec4);
+    const int y = ((local / band_rows) * ranks + rank) * band_rows + local % band_rows;
+    const float4 v = __ldg(bands + i);
+    const size_t at = (size_t)y * row_vec4 + x;
+    for (int p = 0; p < ranks; p++) reinterpret_cast<float4 *>(t.base[p] + frame_off)[at] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  unsigned int *counter = reinterpret_cast<unsigned int *>(t.base[rank] + 128);
+  if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence_system(); // the other CTAs' stores (ordered before their count) before the flags
+  const int p = (int)threadIdx.x;
+  if (p < ranks) {
+    st_release_sys(reinterpret_cast<unsigned long long *>(t.base[p]) + rank, epoch);
+    const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(t.base[rank]) + p;
+    while (ld_acquire_sys(mine) < epoch) __nanosleep(64);
+  }
+  if (threadIdx.x == 0) *counter = 0u; // for the next frame (stream order)
+}
+
 __global__ void __launch_bounds__(256) k_fill_int(int *__restrict__ dst, size_t n, int v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = v;
 }
@@ -136,6 +191,12 @@ struct mb200_comm {
   size_t send_cap = 0, recv_cap = 0, full_cap = 0, cnt_cap = 0;
   void *pinned = nullptr; // staging for pageable host destinations
   size_t pinned_cap = 0;
+  // exchange over peer memory (k_exchange_rows)
+  int peer_state = 0;              // 0 not tried for peer_floats, 1 mapped on every rank, -1 not available
+  size_t peer_floats = 0;          // floats of one frame the mapping was made for
+  char *peer_base[16] = {};        // [rank] = own allocation: header + two frames (alternating by epoch)
+  unsigned long long epoch = 0;
+  int last_path = 0;               // 1: the last frame went through k_exchange_rows, 0: through NCCL
 };
 
 namespace {
@@ -160,6 +221,119 @@ int grow(void **p, size_t *cap, size_t bytes, cudaStream_t s) {
 int nccl_fail(ncclResult_t r, const char *what) {
   NcclApi *n = nccl();
   return mb200::capi_set_error(MB200_ERR_CUDA, std::string(what) + ": " + (n ? n->GetErrorString(r) : "NCCL error"));
+}
+
+void peer_release(mb200_comm *c) {
+  for (int p = 0; p < c->nranks && p < kMaxPeers; p++) {
+    if (!c->peer_base[p]) continue;
+    if (p == c->rank) cudaFree(c->peer_base[p]);
+    else cudaIpcCloseMemHandle(c->peer_base[p]);
+    c->peer_base[p] = nullptr;
+  }
+  c->peer_state = 0, c->peer_floats = 0;
+}
+
+// Maps every rank's frame buffer into every rank (collective over the communicator: every rank reaches it with the
+// same arguments, at the same point of its call sequence).  Returns 1 when the peer-memory exchange can be used by all
+// ranks, -1 when not (then every rank uses NCCL).
+int peer_prepare(mb200_comm *c, size_t frame_floats) {
+  static const bool nccl_only = [] {
+    const char *v = getenv("MB200_GATHER");
+    return v && strcmp(v, "nccl") == 0;
+  }();
+  if (nccl_only || c->nranks < 2 || c->nranks > kMaxPeers) return -1;
+  if (c->peer_state != 0 && c->peer_floats == frame_floats) return c->peer_state;
+  NcclApi *n = nccl();
+  mb200_scene *s = c->scene;
+  if (cudaStreamSynchronize(s->stream) != cudaSuccess) return -1;
+  peer_release(c);
+  struct Record {
+    cudaIpcMemHandle_t handle;
+    long long ok;
+  };
+  static_assert(sizeof(Record) == 72, "record");
+  std::vector<Record> rec((size_t)c->nranks);
+  Record mine;
+  memset(&mine, 0, sizeof(mine));
+  const size_t bytes = kPeerHeaderBytes + 2 * frame_floats * sizeof(float);
+  char *own = nullptr;
+  bool ok = cudaMalloc((void **)&own, bytes) == cudaSuccess;
+  if (ok) ok = cudaMemsetAsync(own, 0, kPeerHeaderBytes, s->stream) == cudaSuccess;
+  if (ok) ok = cudaIpcGetMemHandle(&mine.handle, own) == cudaSuccess;
+  mine.ok = ok ? 1 : 0;
+  cudaGetLastError();
+  // exchange of the handles, then of the outcome of opening them: two tiny all-gathers
+  char *dx = nullptr;
+  if (cudaMalloc((void **)&dx, sizeof(Record) * (size_t)c->nranks) != cudaSuccess) { // cannot even take part: fatal for the path
+    if (own) cudaFree(own);
+    cudaGetLastError();
+    c->peer_state = -1, c->peer_floats = frame_floats;
+    return mb200::capi_set_error(MB200_ERR_OUT_OF_MEMORY, "peer exchange set-up"), -1;
+  }
+  auto all_gather = [&](Record *host) -> bool {
+    if (cudaMemcpyAsync(dx + sizeof(Record) * (size_t)c->rank, &host[c->rank], sizeof(Record), cudaMemcpyHostToDevice, s->stream) != cudaSuccess) return false;
+    if (n->AllGather(dx + sizeof(Record) * (size_t)c->rank, dx, sizeof(Record), ncclChar, c->comm, s->stream) != ncclSuccess) return false;
+    if (cudaMemcpyAsync(host, dx, sizeof(Record) * (size_t)c->nranks, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) return false;
+    return cudaStreamSynchronize(s->stream) == cudaSuccess;
+  };
+  rec[c->rank] = mine;
+  bool comm_ok = all_gather(rec.data());
+  bool all = comm_ok && ok;
+  if (comm_ok) {
+    c->peer_base[c->rank] = own;
+    for (int p = 0; p < c->nranks; p++) {
+      if (p == c->rank) continue;
+      void *ptr = nullptr;
+      if (!rec[p].ok || cudaIpcOpenMemHandle(&ptr, rec[p].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        all = false;
+        continue;
+      }
+      c->peer_base[p] = (char *)ptr;
+    }
+    memset(&mine, 0, sizeof(mine));
+    mine.ok = all ? 1 : 0;
+    rec[c->rank] = mine;
+    comm_ok = all_gather(rec.data());
+    for (int p = 0; p < c->nranks && comm_ok; p++) all = all && rec[p].ok != 0;
+  } else {
+    c->peer_base[c->rank] = own;
+  }
+  cudaFree(dx);
+  if (!(comm_ok && all)) {
+    peer_release(c);
+    c->peer_state = -1, c->peer_floats = frame_floats;
+    return -1;
+  }
+  c->peer_state = 1, c->peer_floats = frame_floats;
+  return 1;
+}
+
+// Delivers `floats` of a device-resident frame to the caller's `image` (device: enqueue-only; host: blocks).
+int deliver_frame(mb200_comm *c, const float *d_frame, size_t floats, float *image) {
+  mb200_scene *s = c->scene;
+  if (device_pointer(image)) {
+    if (cudaMemcpyAsync(image, d_frame, floats * sizeof(float), cudaMemcpyDeviceToDevice, s->stream) != cudaSuccess)
+      return mb200::capi_set_error(MB200_ERR_CUDA, "gathered frame: device copy failed");
+    return MB200_OK;
+  }
+  void *host = image;
+  const bool pinned = pinned_pointer(image);
+  if (!pinned) {
+    if (c->pinned_cap < floats * sizeof(float)) {
+      if (c->pinned) cudaFreeHost(c->pinned);
+      c->pinned = nullptr, c->pinned_cap = 0;
+      if (cudaMallocHost(&c->pinned, floats * sizeof(float)) != cudaSuccess)
+        return mb200::capi_set_error(MB200_ERR_OUT_OF_MEMORY, "pinned staging for the gathered frame");
+      c->pinned_cap = floats * sizeof(float);
+    }
+    host = c->pinned;
+  }
+  if (cudaMemcpyAsync(host, d_frame, floats * sizeof(float), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
+      cudaStreamSynchronize(s->stream) != cudaSuccess)
+    return mb200::capi_set_error(MB200_ERR_CUDA, "gathered frame: device -> host copy failed");
+  if (!pinned) memcpy(image, c->pinned, floats * sizeof(float));
+  return MB200_OK;
 }
 
 int max_band_rows(int height, int band_rows, int ranks) {
@@ -224,6 +398,7 @@ int mb200_comm_adopt(mb200_comm **out, mb200_scene *scene, void *nccl_comm) {
 }
 
 int mb200_comm_size(const mb200_comm *c) { return c ? c->nranks : 0; }
+int mb200_comm_exchange_path(const mb200_comm *c) { return c ? c->last_path : -1; }
 int mb200_comm_rank(const mb200_comm *c) { return c ? c->rank : -1; }
 
 void mb200_comm_destroy(mb200_comm *c) {
@@ -232,6 +407,7 @@ void mb200_comm_destroy(mb200_comm *c) {
     cudaSetDevice(c->scene->device);
     cudaStreamSynchronize(c->scene->stream);
   }
+  peer_release(c);
   NcclApi *n = nccl();
   if (c->owned && c->comm && n) n->CommDestroy(c->comm);
   for (void *p : {(void *)c->send, (void *)c->recv, (void *)c->full, (void *)c->cnt})
@@ -260,6 +436,32 @@ int mb200_gather_framebuffer(mb200_comm *c, int width, int height, int channels,
   const size_t row_floats = (size_t)width * channels;
   const size_t send_floats = (size_t)pad_rows * row_floats, full_floats = (size_t)height * row_floats;
   if (local_rows > 0 && !device_pointer(d_bands)) return mb200::capi_set_error(MB200_ERR_INVALID_ARG, "d_bands must be a device pointer");
+  if (row_floats % 4 == 0 && peer_prepare(c, full_floats) == 1) { // (the same decision on every rank)
+    // exchange over peer memory: the rows go straight into place in every rank's frame, frames alternate by epoch so
+    // that a fast rank's next frame never lands in the buffer a slow rank is still reading
+    if (local_rows > 0 && (reinterpret_cast<size_t>(d_bands) & 15u) != 0) { // float4 loads: through the aligned send buffer
+      if ((rc = grow((void **)&c->send, &c->send_cap, send_floats * sizeof(float), s->stream)) != MB200_OK) return rc;
+      if (cudaMemcpyAsync(c->send, d_bands, (size_t)local_rows * row_floats * sizeof(float), cudaMemcpyDeviceToDevice, s->stream) != cudaSuccess)
+        return mb200::capi_set_error(MB200_ERR_CUDA, "band copy failed");
+      d_bands = c->send;
+    }
+    c->epoch++;
+    PeerTable t;
+    memset(&t, 0, sizeof(t));
+    for (int p = 0; p < c->nranks; p++) t.base[p] = c->peer_base[p];
+    const size_t frame_off = kPeerHeaderBytes + (size_t)(c->epoch & 1ull) * full_floats * sizeof(float);
+    const size_t vec = (size_t)local_rows * (row_floats / 4);
+    size_t ctas = (vec + 255) / 256;
+    if (ctas > 148 * 4) ctas = 148 * 4;
+    if (ctas < 1) ctas = 1;
+    k_exchange_rows<<<(unsigned)ctas, 256, 0, s->stream>>>((const float4 *)d_bands, t, frame_off, local_rows, (int)(row_floats / 4),
+                                                          band_rows, c->nranks, c->rank, c->epoch);
+    mb200::note_launch();
+    if (cudaGetLastError() != cudaSuccess) return mb200::capi_set_error(MB200_ERR_CUDA, "row exchange launch failed");
+    c->last_path = 1;
+    if (!image) return MB200_OK;
+    return deliver_frame(c, reinterpret_cast<const float *>(c->peer_base[c->rank] + frame_off), full_floats, image);
+  }
   if ((rc = grow((void **)&c->recv, &c->recv_cap, send_floats * c->nranks * sizeof(float), s->stream)) != MB200_OK) return rc;
   const float *send = d_bands;
   if (d_bands != c->send) { // a caller's buffer holds local_rows rows: NCCL needs equal counts, pad through our send buffer
@@ -271,6 +473,7 @@ int mb200_gather_framebuffer(mb200_comm *c, int width, int height, int channels,
   }
   const ncclResult_t r = n->AllGather(send, c->recv, send_floats, ncclFloat, c->comm, s->stream);
   if (r != ncclSuccess) return nccl_fail(r, "ncclAllGather");
+  c->last_path = 0;
   if (!image) return MB200_OK; // this rank does not need the frame
   const bool to_device = device_pointer(image);
   float *dst = image;

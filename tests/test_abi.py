@@ -319,7 +319,7 @@ def test_comm_and_probe_entries_reject_bad_arguments_without_a_gpu():
     assert L.mb200_comm_init(None, None, 2, 0, ident) == -1
     assert L.mb200_comm_adopt(C.byref(h), None, None) == -1
     assert L.mb200_comm_unique_id(None) == -1
-    assert L.mb200_comm_size(None) == 0 and L.mb200_comm_rank(None) == -1
+    assert L.mb200_comm_size(None) == 0 and L.mb200_comm_rank(None) == -1 and L.mb200_comm_exchange_path(None) == -1
     L.mb200_comm_destroy(None)
     assert L.mb200_gather_framebuffer(None, 8, 8, 3, 4, None, None) == -1
     p = capi.RenderParams()

@@ -86,8 +86,8 @@ import os, sys, time, numpy as np
 sys.path.insert(0, %(root)r)
 import mallie_b200 as M
 from tests import common as T
-rank, world, idfile = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
-W, H = 333, 150
+rank, world, idfile, W = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], int(sys.argv[4])
+H = 150
 m = T.load_mesh("sphere40")
 sc = M.Scene(m["vertices"], m["faces"], device=rank)
 if rank == 0:
@@ -104,6 +104,7 @@ else:
 comm = M.Comm(sc, world, rank, uid)
 fg = M.camera_frame((0.2, 0.1, 3.0), (0, 0, 0), width=W, height=H)
 out = []
+paths = set()
 for shader in (M.SHADER_PRIMARY_SHADOW, M.SHADER_PATHTRACE):
     p = sc.render_params(fg, W, H, shader=shader, light=(2, 4, 3), pass_index=2, max_path_length=4)
     for band_rows in (4, 12):
@@ -111,6 +112,7 @@ for shader in (M.SHADER_PRIMARY_SHADOW, M.SHADER_PATHTRACE):
         cnt = np.zeros((H, W), np.int32)
         st = comm.render_frame(p, 3, band_rows, img, cnt, stats=True)
         out.append((T.fnv(img), int(cnt.min()), int(cnt.max()), st["primary_rays"]))
+        paths.add(comm.exchange_path())
     # device destination (enqueue-only) and a rank that does not want the frame
     import torch
     torch.cuda.set_device(rank)
@@ -120,20 +122,34 @@ for shader in (M.SHADER_PRIMARY_SHADOW, M.SHADER_PATHTRACE):
     if rank == 0:
         out.append((T.fnv(d_img.cpu().numpy()), 3, 3, 0))
     del d_img
+# frames back to back with one slow consumer: a fast rank's next frame must not land in the buffer the slow rank reads
+p = sc.render_params(fg, W, H, shader=M.SHADER_PRIMARY_SHADOW, light=(2, 4, 3), pass_index=2)
+img = np.zeros((H, W, 3), np.float32)
+seq = set()
+for it in range(12):
+    comm.render_frame(p, 3, 4, img, None)
+    seq.add(T.fnv(img))
+    if rank == 1:
+        time.sleep(0.02)
+out.append((seq.pop() if len(seq) == 1 else "unstable", 3, 3, 0))
+print("PATHS", rank, sorted(paths))
 print("GATHER", rank, out)
 comm.close()
 sc.close()
 """
 
 
-def test_nccl_gathered_frame_is_the_single_gpu_frame(tmp_path):
-    """One process per GPU through the C ABI (mb200_comm_* + mb200_render_frame_gathered): the frame every rank
-    receives from the NCCL all-gather + row placement is bit-identical to the 1-GPU frame."""
+@pytest.mark.parametrize("W,gather,path", [(336, None, 1), (336, "nccl", 0), (333, None, 0)])
+def test_gathered_frame_is_the_single_gpu_frame(tmp_path, W, gather, path):
+    """One process per GPU through the C ABI (mb200_comm_* + mb200_render_frame_gathered): the frame every rank ends up
+    with is bit-identical to the 1-GPU frame -- through the peer-memory exchange kernel (rows of 16-byte multiples, every
+    rank's frame buffer mapped into every rank), through ncclAllGather + row placement when that is forced
+    (MB200_GATHER=nccl), and for a row length the float4 exchange does not take (333 pixels)."""
     need_gpus(2)
     import ast
     import sys
     world = 2
-    W, H = 333, 150
+    H = 150
     m = T.load_mesh("sphere40")
     sc = M.Scene(m["vertices"], m["faces"], device=0)
     fg = M.camera_frame((0.2, 0.1, 3.0), (0, 0, 0), width=W, height=H)
@@ -144,14 +160,20 @@ def test_nccl_gathered_frame_is_the_single_gpu_frame(tmp_path):
     sc.close()
     idfile = str(tmp_path / "nccl_id")
     code = GATHER_RANK % dict(root=os.path.dirname(T.HERE))
-    procs = [subprocess.Popen([sys.executable, "-c", code, str(r), str(world), idfile], stdout=subprocess.PIPE,
-                              stderr=subprocess.PIPE, text=True) for r in range(world)]
+    env = dict(os.environ)
+    env.pop("MB200_GATHER", None)
+    if gather:
+        env["MB200_GATHER"] = gather
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(r), str(world), idfile, str(W)], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True, env=env) for r in range(world)]
     outs = [pr.communicate(timeout=600) for pr in procs]
     total_primary = {}
     for r, (pr, (so, se)) in enumerate(zip(procs, outs)):
         assert pr.returncode == 0, se[-3000:]
         line = [ln for ln in so.splitlines() if ln.startswith("GATHER")][0]
         res = ast.literal_eval(line.split(" ", 2)[2])
+        paths = ast.literal_eval([ln for ln in so.splitlines() if ln.startswith("PATHS")][0].split(" ", 2)[2])
+        assert paths == [path], (r, paths)
         k = 0
         for shader in (M.SHADER_PRIMARY_SHADOW, M.SHADER_PATHTRACE):
             n = 3 if r == 0 else 2
@@ -162,4 +184,5 @@ def test_nccl_gathered_frame_is_the_single_gpu_frame(tmp_path):
                 if j < 2:
                     total_primary[(shader, j)] = total_primary.get((shader, j), 0) + prim
                 k += 1
+        assert res[k][0] == want[M.SHADER_PRIMARY_SHADOW], (r, "back-to-back frames", res[k])
     assert all(v == 3 * W * H for v in total_primary.values()), total_primary
