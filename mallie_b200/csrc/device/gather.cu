@@ -151,7 +151,14 @@ __global__ void __launch_bounds__(256)
   if (p < ranks) {
     st_release_sys(reinterpret_cast<unsigned long long *>(t.base[p]) + rank, epoch);
     const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(t.base[rank]) + p;
-    while (ld_acquire_sys(mine) < epoch) __nanosleep(64);
+    // a peer that died never raises its flag: give up after 5 minutes with a trap (the host sees a CUDA error, not a hang)
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire_sys(mine) < epoch) {
+      __nanosleep(64);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 300000000000ull) __trap();
+    }
   }
   if (threadIdx.x == 0) *counter = 0u; // for the next frame (stream order)
 }
