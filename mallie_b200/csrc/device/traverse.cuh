@@ -140,7 +140,8 @@ template <> __device__ __forceinline__ TriEdges load_tri_edges<kTriF64>(const vo
   return t;
 }
 
-// 64-byte f32 record: two 256-bit loads (two L1 wavefronts per lane instead of three)
+// 64-byte f32 record: two 256-bit loads (two L1 wavefronts per lane instead of three; c4..c7 are the record's padding)
+#pragma nv_diag_suppress 550
 template <> __device__ __forceinline__ TriEdges load_tri_edges<kTriF32x64>(const void *tris, uint32_t i) {
   const char *p = reinterpret_cast<const char *>(tris) + (size_t)i * 64u;
   float a0, a1, a2, a3, b0, b1, b2, b3, c0, c1, c2, c3, c4, c5, c6, c7;
@@ -152,6 +153,8 @@ template <> __device__ __forceinline__ TriEdges load_tri_edges<kTriF32x64>(const
                : "l"(p + 32));
   return tri_edges_from_f32(make_float4(a0, a1, a2, a3), make_float4(b0, b1, b2, b3), make_float4(c0, c1, c2, c3));
 }
+
+#pragma nv_diag_default 550
 
 // 96-byte f64 record: three 256-bit loads, no conversions and no edge subtractions
 template <> __device__ __forceinline__ TriEdges load_tri_edges<kTriF64x96>(const void *tris, uint32_t i) {
