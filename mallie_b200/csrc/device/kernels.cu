@@ -28,7 +28,10 @@ namespace mb200 {
 
 namespace {
 
-constexpr int kBlock = 128; // threads per CTA of the traversal kernels
+#ifndef MB200_BLOCK
+#define MB200_BLOCK 128
+#endif
+constexpr int kBlock = MB200_BLOCK; // threads per CTA of the traversal kernels
 
 // production configuration of the traversal state machine (A/B history: DESIGN.md §5)
 constexpr int kRefillMin = 8;   // idle lanes that trigger a refill
@@ -36,7 +39,7 @@ constexpr int kShadeMin = 8;    // parked lanes that trigger a shade step (fused
 constexpr int kSmemStack = 12;  // stack entries per thread kept in shared memory (24 KB per CTA)
 constexpr int kSmemStackQuery = 8;  // plain closest-hit / any-hit queries over a caller's ray buffer
 constexpr int kSmemStackFused = 10; // fused frames: two more 16-byte units per thread hold the lane slot
-constexpr int kMinBlocks = 8;   // resident CTAs per SM the register allocation targets (64 registers)
+constexpr int kMinBlocks = 1024 / kBlock;   // resident CTAs per SM the register allocation targets (64 registers)
 constexpr unsigned kChunk = 32; // ray indices per atomicAdd
 constexpr int kVar = kVarOctNodes; // octant copies of the pair nodes: no sign selects in the inner step (trace_sm.cuh)
 
