@@ -186,3 +186,15 @@ def test_gathered_frame_is_the_single_gpu_frame(tmp_path, W, gather, path):
                 k += 1
         assert res[k][0] == want[M.SHADER_PRIMARY_SHADOW], (r, "back-to-back frames", res[k])
     assert all(v == 3 * W * H for v in total_primary.values()), total_primary
+
+
+def test_fuzz_gathered_frames_short():
+    """tools/fuzz_gather.py for a few seconds on two GPUs: random frame sizes (so the peer mapping is rebuilt all the time),
+    band rows, sample counts and shaders through mb200_render_frame_gathered, each compared with the same frame rendered by
+    the rank alone; 16-byte-multiple rows go through the peer-memory kernel, the others through NCCL.  (1 200 sizes on four
+    GPUs and 240 on two passed when this test was added.)"""
+    need_gpus(2)
+    import sys
+    tool = os.path.join(os.path.dirname(T.HERE), "tools", "fuzz_gather.py")
+    r = subprocess.run([sys.executable, tool, "2", "5", "3"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.count("FUZZ GATHER OK") == 2, r.stdout[-1500:] + r.stderr[-3000:]
