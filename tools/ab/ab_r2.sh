@@ -1,4 +1,4 @@
-# Round-2 A/B sweep (development): make -C mallie_b200/csrc DEV=1, then under gpurun:  bash tools/ab_r2.sh
+# Round-2 A/B sweep (development): make -C mallie_b200/csrc DEV=1, then under gpurun:  bash tools/ab/ab_r2.sh
 mkdir -p gpurun_out
 run() { env "$@" python tools/ab_frame.py 2>&1 | tail -1; }
 run A=1
