@@ -1001,6 +1001,11 @@ void KernelTimer::collect(double ms[kKClasses], unsigned long long launches[kKCl
       launches[sp.cls]++;
     }
     std::sort(iv.begin(), iv.end(), [](const Iv &x, const Iv &y) { return x.a < y.a; });
+    static const bool dump = env_int("MB200_TIMING_DUMP", 0) != 0; // diagnostics: every span, ms since the first event
+    if (dump) {
+      static const char *names[kKClasses] = {"camera_trace", "shadow_trace", "bounce_trace", "shade", "resolve", "query_trace"};
+      for (const Iv &v : iv) fprintf(stderr, "[mb200 span] %-13s %9.3f -> %9.3f ms\n", names[v.cls], v.a, v.b);
+    }
     auto union_len = [&](auto pred) {
       double total = 0.0;
       float lo = 0.f, hi = -1.f;
