@@ -21,6 +21,7 @@
 #include "shade.cuh"
 #include "trace_sm.cuh"
 #include "trace_ds.cuh"
+#include "trace_ps.cuh"
 #include "trace_tr.cuh"
 #include "traverse.cuh"
 
@@ -138,6 +139,16 @@ __global__ void __launch_bounds__(kBlock, MINB)
   const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_fat + threadIdx.x);
   if (n_dev) n = __ldg(n_dev);
   trace_dual_slot_machine<IO, TRI, CAP, ANYHIT, COUNT, OCT, REFILL_MIN, CHUNK>(sc, io, n, work, base, kBlock * 16u, gcounters);
+}
+
+// The phase-sorted machine (trace_ps.cuh): rays live in shared-memory slots and move between the warps of the CTA.
+template <class IO, int TRI, int NS, int S, bool ANYHIT, int STAY, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
+    k_trace_ps(const __grid_constant__ SceneView sc, const __grid_constant__ IO io, unsigned long long n,
+               const unsigned int *__restrict__ n_dev, unsigned long long *__restrict__ work, uint4 *__restrict__ ovf) {
+  extern __shared__ __align__(16) unsigned char smem_ps[];
+  if (n_dev) n = __ldg(n_dev);
+  trace_phase_sorted<IO, TRI, NS, S, 64, ANYHIT, STAY, kChunk>(sc, io, n, work, smem_ps, ovf + (size_t)blockIdx.x * NS * (64 - S));
 }
 
 // ---------------------------------------------------------------------------
@@ -846,6 +857,47 @@ cudaError_t launch_ds(const SceneView &sc, const IO &io, size_t n, const unsigne
 
 // Picks the kernel instantiation: production parameters, or (development builds, -DMB200_DEV_VARIANTS)
 // the A/B variants selected with MB200_TRACE_VAR.
+template <class IO, int TRI, int NS, int S, bool ANYHIT, int STAY, int MINB>
+cudaError_t launch_ps(const SceneView &sc, const IO &io, size_t n, const unsigned int *n_dev, unsigned long long *work,
+                      cudaStream_t s) {
+  auto k = k_trace_ps<IO, TRI, NS, S, ANYHIT, STAY, MINB>;
+  const size_t smem = ((sizeof(PsShared) + 3 * NS * 2 + 15) & ~(size_t)15) + kPsStageBytes + (size_t)(kPsRoUnits + kPsMutUnits + S) * NS * 16;
+  static int grids[64]; // per instantiation, per device
+  int grid = 0;
+  const cudaError_t ge = persistent_grid(k, smem, MINB, grids, &grid);
+  if (ge != cudaSuccess) return ge;
+  // slot-indexed overflow of the traversal stacks (development variant: one allocation per stream that launches this
+  // instantiation -- launches of the frame pipeline's two streams overlap -- never freed)
+  struct Ovf {
+    cudaStream_t stream;
+    int device;
+    uint4 *p;
+    size_t ctas;
+  };
+  static Ovf table[16];
+  static int used = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  Ovf *o = nullptr;
+  for (int i = 0; i < used; i++)
+    if (table[i].stream == s && table[i].device == dev) o = &table[i];
+  if (!o) {
+    if (used == 16) return cudaErrorMemoryAllocation;
+    o = &table[used++];
+    o->stream = s, o->device = dev, o->p = nullptr, o->ctas = 0;
+  }
+  if (o->ctas < (size_t)grid) {
+    if (o->p) cudaFree(o->p);
+    o->p = nullptr, o->ctas = 0;
+    const cudaError_t e = cudaMalloc((void **)&o->p, (size_t)grid * NS * (64 - S) * sizeof(uint4));
+    if (e != cudaSuccess) return e;
+    o->ctas = (size_t)grid;
+  }
+  k<<<grid, kBlock, smem, s>>>(sc, io, (unsigned long long)n, n_dev, work, o->p);
+  g_launches++;
+  return cudaGetLastError();
+}
+
 template <class IO, int TRI, int CAP, bool ANYHIT, bool COUNT>
 cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const unsigned int *n_dev,
                               unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
@@ -859,6 +911,18 @@ cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const
     static const int tr = env_int("MB200_TRACE_TR", 0);
 #define MB200_TR(R, H, B) launch_tr<IO, TRI, CAP, ANYHIT, COUNT, R, H, B, kChunk>(sc, io, n, n_dev, work, counters, s)
     // one slot per phase per lane (trace_ds.cuh): MB200_TRACE_DS = CTAs per SM * 100 + refill threshold
+    // rays move between the warps of a CTA, one step body per warp round (trace_ps.cuh): MB200_TRACE_PS = slots per CTA
+    // * 100 + lanes below which a round ends (19216: 192 slots, 16 lanes)
+    static const int ps = env_int("MB200_TRACE_PS", 0);
+    if (ps && sc.nodes_oct && !COUNT && TRI == kTriF32) {
+      if constexpr (!COUNT && TRI == kTriF32) {
+        if (ps == 19216) return launch_ps<IO, TRI, 192, 4, ANYHIT, 16, 6>(sc, io, n, n_dev, work, s);
+        if (ps == 19208) return launch_ps<IO, TRI, 192, 4, ANYHIT, 8, 6>(sc, io, n, n_dev, work, s);
+        if (ps == 19224) return launch_ps<IO, TRI, 192, 4, ANYHIT, 24, 6>(sc, io, n, n_dev, work, s);
+        if (ps == 25616) return launch_ps<IO, TRI, 256, 4, ANYHIT, 16, 5>(sc, io, n, n_dev, work, s);
+        if (ps == 16016) return launch_ps<IO, TRI, 160, 4, ANYHIT, 16, 7>(sc, io, n, n_dev, work, s);
+      }
+    }
     static const int ds = env_int("MB200_TRACE_DS", 0);
     if (ds && sc.nodes_oct) {
 #define MB200_DS(R, B) launch_ds<IO, TRI, CAP, ANYHIT, COUNT, true, R, B, kChunk>(sc, io, n, n_dev, work, counters, s)
