@@ -15,8 +15,15 @@
 //   0 (ox, oy)  1 (oz, ix)  2 (iy, iz)  3 (dx, dy)  4 (dz, -)     written once when the ray is loaded
 //   5 (hitT, ref | rc << 32)            6 (item, sp, -, -)        the state a round changes
 //   7 .. 7 + S - 1                      traversal stack entries; deeper ones in a slot-indexed global scratch
-// Queues are three LIFO arrays of slot ids (INNER, LEAF, free) under one CTA-wide spin lock taken by lane 0 of a warp for
-// the few instructions of a pop / push; `held` counts the rays that are in registers, for the exit test.
+// Queues are three LIFO arrays of slot ids (INNER, LEAF, free) under one CTA-wide spin lock.  In this first version every
+// queue operation is a critical section executed by LANE 0 ALONE (the other lanes hand their slot ids over through a
+// 32-word staging area per warp); `held` counts the rays that are in registers, for the exit test.
+//
+// Measured (profiles/r2_trace_phase_sorted_variant.md): bit-identical, FP64 instructions per launch -33 ... -37 % -- the
+// bodies do run a third fuller -- and 32.0 ms per bench frame against 19.9, because the serial critical sections add
+// ~40 % instructions at one active lane, 8-14 x the shared-memory wavefronts and lock waits at 24 warps per SM.  A
+// version with warp-wide critical sections (one queue entry per lane) corrupted its queues under some interleavings
+// although the same protocol passes a standalone stress test; DESIGN.md section 10 lists what the next version needs.
 //
 // Exactness: per ray the sequence of pair-node visits, triangle tests and pop-time decisions is trace_sm.cuh's (the
 // bodies are the same code); only where and when a step executes changes.  Needs the octant copies of the pair nodes.
