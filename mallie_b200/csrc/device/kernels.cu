@@ -20,9 +20,11 @@
 
 #include "shade.cuh"
 #include "trace_sm.cuh"
+#ifdef MB200_DEV_VARIANTS // measured-and-rejected machines, development builds only
 #include "trace_ds.cuh"
 #include "trace_ps.cuh"
 #include "trace_tr.cuh"
+#endif
 #include "traverse.cuh"
 
 namespace mb200 {
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(kBlock, MINB)
                                                                                        top_table);
 }
 
+#ifdef MB200_DEV_VARIANTS
 // The two-rays-per-lane machine (trace_tr.cuh): the rays' read-only halves in dynamic shared memory.
 template <class IO, int TRI, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int HYST, int MINB, unsigned CHUNK>
 __global__ void __launch_bounds__(kBlock, MINB)
@@ -150,6 +153,8 @@ __global__ void __launch_bounds__(kBlock, MINB)
   if (n_dev) n = __ldg(n_dev);
   trace_phase_sorted<IO, TRI, NS, S, 64, ANYHIT, STAY, kChunk>(sc, io, n, work, smem_ps, ovf + (size_t)blockIdx.x * NS * (64 - S));
 }
+
+#endif // MB200_DEV_VARIANTS
 
 // ---------------------------------------------------------------------------
 // K3: BuildIntersection for a buffer of rays + hit records -> full 184-byte Intersection records
@@ -827,6 +832,7 @@ cudaError_t launch_sm(const SceneView &sc, const IO &io, size_t n, const unsigne
   return cudaGetLastError();
 }
 
+#ifdef MB200_DEV_VARIANTS
 template <class IO, int TRI, int CAP, bool ANYHIT, bool COUNT, int REFILL_MIN, int HYST, int MINB, unsigned CHUNK>
 cudaError_t launch_tr(const SceneView &sc, const IO &io, size_t n, const unsigned int *n_dev, unsigned long long *work,
                       unsigned long long *counters, cudaStream_t s) {
@@ -855,8 +861,6 @@ cudaError_t launch_ds(const SceneView &sc, const IO &io, size_t n, const unsigne
   return cudaGetLastError();
 }
 
-// Picks the kernel instantiation: production parameters, or (development builds, -DMB200_DEV_VARIANTS)
-// the A/B variants selected with MB200_TRACE_VAR.
 template <class IO, int TRI, int NS, int S, bool ANYHIT, int STAY, int MINB>
 cudaError_t launch_ps(const SceneView &sc, const IO &io, size_t n, const unsigned int *n_dev, unsigned long long *work,
                       cudaStream_t s) {
@@ -898,6 +902,10 @@ cudaError_t launch_ps(const SceneView &sc, const IO &io, size_t n, const unsigne
   return cudaGetLastError();
 }
 
+#endif // MB200_DEV_VARIANTS
+
+// Picks the kernel instantiation: production parameters, or (development builds, -DMB200_DEV_VARIANTS)
+// the A/B variants selected with MB200_TRACE_VAR.
 template <class IO, int TRI, int CAP, bool ANYHIT, bool COUNT>
 cudaError_t launch_sm_variant(const SceneView &sc, const IO &io, size_t n, const unsigned int *n_dev,
                               unsigned long long *work, unsigned long long *counters, cudaStream_t s) {
